@@ -1,0 +1,156 @@
+"""Build and bind libb2f.so (the C-ABI of include/b2f.h) through ctypes.
+
+There is no CPU fallback: `lib()` raises if the shared library is missing or cannot be loaded,
+and every compute wrapper raises on a non-zero status with the library's own error text.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+from typing import List
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+SO_PATH = os.path.join(CSRC, "libb2f.so")
+SOURCES = ["core.cu", "postproc.cu", "aux_ops.cu", "umma_conv.cu"]
+HEADERS = ["b2f_common.cuh", os.path.join("..", "..", "include", "b2f.h")]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+_lock = threading.Lock()
+_lib = None
+
+
+class B2FError(RuntimeError):
+    pass
+
+
+def _stale() -> bool:
+    if not os.path.exists(SO_PATH):
+        return True
+    so_m = os.path.getmtime(SO_PATH)
+    for f in SOURCES + HEADERS:
+        p = os.path.join(CSRC, f)
+        if os.path.exists(p) and os.path.getmtime(p) > so_m:
+            return True
+    return False
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into csrc/libb2f.so (in-tree, travels with the repo snapshot)."""
+    if not force and not _stale():
+        return SO_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", SO_PATH + ".tmp"] + SOURCES
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise B2FError(f"nvcc failed ({' '.join(cmd)}):\n{res.stdout}\n{res.stderr}")
+    os.replace(SO_PATH + ".tmp", SO_PATH)
+    if verbose:
+        print(res.stdout, res.stderr)
+    return SO_PATH
+
+
+class DetLevels(C.Structure):
+    _fields_ = [("score", C.c_void_p * 3), ("bbox", C.c_void_p * 3), ("kps", C.c_void_p * 3),
+                ("score_ps", C.c_int * 3), ("bbox_ps", C.c_int * 3), ("kps_ps", C.c_int * 3)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("cin_p", C.c_int),
+                ("ho", C.c_int), ("wo", C.c_int), ("cout_p", C.c_int),
+                ("kh", C.c_int), ("kw", C.c_int), ("stride", C.c_int), ("pad", C.c_int),
+                ("dtype", C.c_int), ("out_dtype", C.c_int), ("act", C.c_int), ("bias_classes", C.c_int),
+                ("res_mode", C.c_int), ("res_h", C.c_int), ("res_w", C.c_int), ("force_kchunk", C.c_int),
+                ("in_", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p), ("slope", C.c_void_p),
+                ("residual", C.c_void_p), ("out", C.c_void_p)]
+
+
+_vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+# name -> argtypes; every entry returns int status unless listed in _RESTYPES
+SIGNATURES = {
+    "b2f_version": [],
+    "b2f_last_error": [],
+    "b2f_launch_count": [],
+    "b2f_set_tuning": [_i, _i],
+    "b2f_letterbox_u8": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "b2f_preprocess": [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _i, _i, _vp],
+    "b2f_blob_nchw_f32": [_vp, _i, _i, _i, _f, _f, _vp, _vp],
+    "b2f_decode_nms": [C.POINTER(DetLevels), _i, _i, _i, _vp, _vp, _f, _f, _i, _i, _i, _i, _vp, _vp, _vp, _vp,
+                       _vp, _ll, _vp],
+    "b2f_decode_nms_workspace": [_i, _i],
+    "b2f_estimate_norm": [_vp, _i, _i, _vp, _vp],
+    "b2f_warp_affine_u8": [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp],
+    "b2f_norm_crop": [_vp, _i, _i, _vp, _vp, _i, _i, _f, _f, _vp, _i, _i, _vp, _vp, _vp],
+    "b2f_conv2d": [C.POINTER(ConvDesc), _vp],
+    "b2f_stem_conv3x3": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "b2f_dwconv": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp],
+    "b2f_pool": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "b2f_eltwise": [_vp, _vp, _ll, _i, _vp, _vp, _vp, _i, _i, _vp, _vp],
+    "b2f_l2norm_rows": [_vp, _ll, _i, _vp, _vp, _i, _vp, _vp],
+    "b2f_cosine_pairs": [_vp, _vp, _i, _i, _vp, _vp],
+    "b2f_match_partial": [_vp, _i, _vp, _ll, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp],
+    "b2f_match_splits": [_ll, _i],
+    "b2f_match_merge": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _f, _i, _ll, _vp, _vp, _vp],
+    "b2f_pairs_threshold": [_vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _ll, _vp, _vp],
+    "b2f_cluster_resolve": [_vp, _ll, _i, _vp, _vp],
+    "b2f_debug_tma_probe": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp],
+}
+_RESTYPES = {"b2f_last_error": C.c_char_p, "b2f_launch_count": _ll, "b2f_decode_nms_workspace": _ll}
+_NO_STATUS = {"b2f_version", "b2f_last_error", "b2f_launch_count", "b2f_decode_nms_workspace", "b2f_match_splits"}
+
+
+def declared_symbols() -> List[str]:
+    """extern-C names declared in include/b2f.h (used by the CPU-side export test)."""
+    import re
+    with open(os.path.join(_HERE, "..", "include", "b2f.h")) as f:
+        text = f.read()
+    return sorted(set(re.findall(r"\b(b2f_[a-z0-9_]+)\s*\(", text)))
+
+
+def lib() -> C.CDLL:
+    """Load libb2f.so, building it first if sources are newer.  Raises -- never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if _stale():
+            try:
+                build()
+            except Exception as e:  # no nvcc on the box and no prebuilt .so: fail loudly
+                if not os.path.exists(SO_PATH):
+                    raise B2FError(f"libb2f.so is missing and could not be built: {e}") from e
+        try:
+            handle = C.CDLL(SO_PATH)
+        except OSError as e:
+            raise B2FError(f"cannot load {SO_PATH}: {e}") from e
+        for name, args in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = args
+            fn.restype = _RESTYPES.get(name, C.c_int)
+        _lib = handle
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = lib().b2f_last_error()
+        raise B2FError(f"{what or 'b2f call'} failed with status {status}: {msg.decode() if msg else ''}")
+
+
+def call(name: str, *args):
+    """Invoke a status-returning entry point and raise B2FError on failure."""
+    fn = getattr(lib(), name)
+    rc = fn(*args)
+    if name not in _NO_STATUS:
+        check(rc, name)
+    return rc
+
+
+def launch_count() -> int:
+    return int(lib().b2f_launch_count())

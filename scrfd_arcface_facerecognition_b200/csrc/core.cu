@@ -1,0 +1,40 @@
+// Library-wide state of libb2f.so: last-error text, launch counter, tuning knobs.
+#include "b2f_common.cuh"
+#include "../../include/b2f.h"
+
+#include <atomic>
+#include <stdarg.h>
+
+namespace b2f {
+std::atomic<long long> g_launches{0};
+extern int g_smem_budget_single;
+extern int g_max_block_n;
+}  // namespace b2f
+
+static thread_local char g_err[1024] = "";
+
+void b2f_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int b2f_version(void) { return B2F_ABI_VERSION; }
+extern "C" const char* b2f_last_error(void) { return g_err; }
+extern "C" long long b2f_launch_count(void) { return b2f::g_launches.load(); }
+
+extern "C" int b2f_set_tuning(int key, int value) {
+  if (key == 0) {
+    B2F_REQUIRE(value >= 48 * 1024 && value <= 224 * 1024, "tuning 0 (smem budget) out of range: %d", value);
+    b2f::g_smem_budget_single = value;
+    return 0;
+  }
+  if (key == 1) {
+    B2F_REQUIRE(value >= 16 && value <= 256 && value % 16 == 0, "tuning 1 (max UMMA N) out of range: %d", value);
+    b2f::g_max_block_n = value;
+    return 0;
+  }
+  b2f_set_error("unknown tuning key %d", key);
+  return 2;
+}

@@ -1,0 +1,645 @@
+// Integer / float32-exact pre- and post-processing kernels (HBM- and latency-bound; CUDA cores).
+//   letterbox / preprocess / blob   : reference models/scrfd.py:122-138, 76-82; models/arcface.py:44-50
+//   decode + threshold + sort + NMS : reference models/scrfd.py:89-119,142-177,180-207; utils/helpers.py:62-107
+//   estimate_norm / warpAffine      : reference utils/helpers.py:18-59
+// Every arithmetic step that the reference performs in numpy float32 / cv2 fixed point is spelled
+// with round-to-nearest intrinsics so the compiler cannot contract it into FMAs.
+#include "b2f_common.cuh"
+#include "../../include/b2f.h"
+
+#include <atomic>
+
+namespace b2f {
+extern std::atomic<long long> g_launches;
+
+// ============================================================================================
+// resize + letterbox
+// ============================================================================================
+struct ResizeGeom {
+  int H, W, new_w, new_h, in_w, in_h;
+  int mode;  // 0 copy, 1 exact-2x area average, 2 fixed-point bilinear
+  double scale_x, scale_y;
+};
+
+__device__ __forceinline__ void linear_coeff(int d, double scale, int src, bool horizontal, int& s0, int& s1, int& w0,
+                                             int& w1) {
+  const double fd = __dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5);
+  float f = __double2float_rn(fd);
+  int s = (int)floorf(f);
+  f = __fsub_rn(f, (float)s);
+  if (horizontal) {
+    if (s < 0) {
+      f = 0.f;
+      s = 0;
+    }
+    if (s >= src - 1) {
+      f = 0.f;
+      s = src - 1;
+    }
+  }
+  w1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  w0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  s0 = min(max(s, 0), src - 1);
+  s1 = min(max(s + 1, 0), src - 1);
+}
+
+// one letterboxed BGR pixel (uint8 values as int)
+__device__ __forceinline__ void letterbox_pixel(const uint8_t* __restrict__ img, const ResizeGeom& g, int x, int y,
+                                                int (&bgr)[3]) {
+  if (x >= g.new_w || y >= g.new_h) {
+    bgr[0] = bgr[1] = bgr[2] = 0;
+    return;
+  }
+  if (g.mode == 0) {
+    const uint8_t* p = img + ((size_t)y * g.W + x) * 3;
+    bgr[0] = p[0], bgr[1] = p[1], bgr[2] = p[2];
+  } else if (g.mode == 1) {
+    const uint8_t* p0 = img + ((size_t)(2 * y) * g.W + 2 * x) * 3;
+    const uint8_t* p1 = p0 + (size_t)g.W * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) bgr[c] = (p0[c] + p0[3 + c] + p1[c] + p1[3 + c] + 2) >> 2;
+  } else {
+    int x0, x1, a0, a1, y0, y1, b0, b1;
+    linear_coeff(x, g.scale_x, g.W, true, x0, x1, a0, a1);
+    linear_coeff(y, g.scale_y, g.H, false, y0, y1, b0, b1);
+    const uint8_t* r0 = img + (size_t)y0 * g.W * 3;
+    const uint8_t* r1 = img + (size_t)y1 * g.W * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int h0 = r0[x0 * 3 + c] * a0 + r0[x1 * 3 + c] * a1;
+      const int h1 = r1[x0 * 3 + c] * a0 + r1[x1 * 3 + c] * a1;
+      const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      bgr[c] = min(max(v, 0), 255);
+    }
+  }
+}
+
+template <int OUT>  // 0: uint8 BGR canvas, 1: normalised 16-bit NHWC RGB (channel-padded)
+__global__ void letterbox_kernel(const uint8_t* __restrict__ frames, ResizeGeom g, int batch, float mean, float scale,
+                                 void* __restrict__ out, int c_pad, int is_bf16) {
+  const long long total = (long long)batch * g.in_h * g.in_w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % g.in_w);
+    const int y = (int)((i / g.in_w) % g.in_h);
+    const int b = (int)(i / ((long long)g.in_w * g.in_h));
+    int bgr[3];
+    letterbox_pixel(frames + (size_t)b * g.H * g.W * 3, g, x, y, bgr);
+    if (OUT == 0) {
+      uint8_t* o = reinterpret_cast<uint8_t*>(out) + (size_t)i * 3;
+      o[0] = (uint8_t)bgr[0], o[1] = (uint8_t)bgr[1], o[2] = (uint8_t)bgr[2];
+    } else {
+      float v[4];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = __fmul_rn(__fsub_rn((float)bgr[2 - c], mean), scale);
+      v[3] = 0.f;
+      uint16_t* o = reinterpret_cast<uint16_t*>(out) + (size_t)i * c_pad;
+      uint16_t h[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (is_bf16) {
+          __nv_bfloat16 t = __float2bfloat16_rn(v[c]);
+          h[c] = *reinterpret_cast<uint16_t*>(&t);
+        } else {
+          __half t = __float2half_rn(v[c]);
+          h[c] = *reinterpret_cast<uint16_t*>(&t);
+        }
+      }
+      *reinterpret_cast<uint2*>(o) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
+      for (int c = 4; c < c_pad; c += 4) *reinterpret_cast<uint2*>(o + c) = make_uint2(0u, 0u);
+    }
+  }
+}
+
+static int make_geom(ResizeGeom* g, int h, int w, int new_w, int new_h, int in_w, int in_h) {
+  B2F_REQUIRE(h > 0 && w > 0 && new_w > 0 && new_h > 0 && new_w <= in_w && new_h <= in_h,
+              "letterbox: bad geometry %dx%d -> %dx%d in %dx%d", w, h, new_w, new_h, in_w, in_h);
+  g->H = h, g->W = w, g->new_w = new_w, g->new_h = new_h, g->in_w = in_w, g->in_h = in_h;
+  if (new_w == w && new_h == h)
+    g->mode = 0;
+  else if (w == 2 * new_w && h == 2 * new_h)
+    g->mode = 1;
+  else
+    g->mode = 2;
+  g->scale_x = 1.0 / ((double)new_w / (double)w);
+  g->scale_y = 1.0 / ((double)new_h / (double)h);
+  return 0;
+}
+
+static int grid_for(long long total, int block) {
+  long long blocks = (total + block - 1) / block;
+  const long long cap = 148LL * 16;
+  return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+__global__ void blob_kernel(const uint8_t* __restrict__ img, int batch, int h, int w, float mean, float scale,
+                            float* __restrict__ out) {
+  const long long plane = (long long)h * w;
+  const long long total = (long long)batch * 3 * plane;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % plane;
+    const int c = (int)((i / plane) % 3);
+    const long long b = i / (3 * plane);
+    const float v = (float)img[(b * plane + pix) * 3 + (2 - c)];
+    out[i] = __fmul_rn(__fsub_rn(v, mean), scale);
+  }
+}
+
+// ============================================================================================
+// decode + threshold + sort + greedy NMS + max_num
+// ============================================================================================
+struct DecodeParams {
+  b2f_det_levels lv;
+  int batch, in_h, in_w;
+  const float* det_scale;
+  const int* image_hw;
+  float conf, iou;
+  int max_num, metric, max_cand, cap2, max_det;
+  int forward_mode;  // 1: no NMS, anchor order, unscaled (the reference's SCRFD.forward view)
+  float* det;
+  float* kps;
+  int* keep_idx;
+  int* counts;
+  uint8_t* ws;
+  long long ws_per_frame;
+};
+
+constexpr int kSmemKeys = 4096;
+constexpr int kAliveWords = 1024;  // up to 32768 candidates
+
+__device__ __forceinline__ uint32_t float_order_bits(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_order_bits(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+}
+
+__device__ void bitonic_sort_desc(uint64_t* k, int P) {
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const uint64_t a = k[lo], b = k[hi];
+        if (desc ? (a < b) : (a > b)) {
+          k[lo] = b;
+          k[hi] = a;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+struct AnchorRef {
+  int level, pix, anchor, stride, ws;
+};
+__device__ __forceinline__ AnchorRef anchor_ref(int a, int in_h, int in_w) {
+  AnchorRef r;
+  int base = 0;
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    const int s = 8 << l;
+    const int cnt = (in_h / s) * (in_w / s) * 2;
+    if (a < base + cnt || l == 2) {
+      r.level = l, r.stride = s, r.ws = in_w / s;
+      r.pix = (a - base) >> 1, r.anchor = (a - base) & 1;
+      return r;
+    }
+    base += cnt;
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(1024, 1) decode_nms_kernel(DecodeParams p) {
+  extern __shared__ uint64_t smem_keys[];
+  __shared__ uint32_t alive[kAliveWords];
+  __shared__ int word_prefix[kAliveWords];
+  __shared__ int s_count, s_keep;
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int nthreads = blockDim.x;
+  uint8_t* ws = p.ws + (size_t)b * p.ws_per_frame;
+  uint64_t* keys_g = reinterpret_cast<uint64_t*>(ws);
+  uint64_t* keys2 = keys_g + p.cap2;
+  float4* boxes = reinterpret_cast<float4*>(keys2 + p.cap2);
+  int* kept_pos = reinterpret_cast<int*>(boxes + p.max_cand);
+  int* sel = kept_pos + p.max_cand;
+
+  int lvl_cnt[3], lvl_base[3];
+  int total = 0;
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    const int s = 8 << l;
+    lvl_cnt[l] = (p.in_h / s) * (p.in_w / s) * 2;
+    lvl_base[l] = total;
+    total += lvl_cnt[l];
+  }
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+
+  // ---- A. threshold + compaction (order restored by the sort) ----------------------------------
+  // keys live in shared memory when they fit, else in the global workspace
+  uint64_t* keys = (p.cap2 <= kSmemKeys) ? smem_keys : keys_g;
+  for (int a = tid; a < total; a += nthreads) {
+    const int l = a < lvl_base[1] ? 0 : (a < lvl_base[2] ? 1 : 2);
+    const int local = a - lvl_base[l];
+    const size_t npix = (size_t)(lvl_cnt[l] >> 1);
+    const float sc = p.lv.score[l][((size_t)b * npix + (local >> 1)) * p.lv.score_ps[l] + (local & 1)];
+    if (sc >= p.conf) {
+      const int slot = atomicAdd(&s_count, 1);
+      if (slot < p.max_cand)
+        keys[slot] = (p.forward_mode ? 0ull : ((uint64_t)float_order_bits(sc) << 32)) |
+                     (uint64_t)(0xFFFFFFFFu - (uint32_t)a) | (p.forward_mode ? (1ull << 63) : 0ull);
+    }
+  }
+  __syncthreads();
+  const int n_found = s_count;
+  const int n = min(n_found, p.max_cand);
+  int P = 32;
+  while (P < n) P <<= 1;
+  for (int i = n + tid; i < P; i += nthreads) keys[i] = 0ull;
+  // ---- B. sort: (score desc, anchor asc) == the order the reference's NMS visits candidates ------
+  bitonic_sort_desc(keys, P);
+
+  // ---- C. decode boxes for the sorted candidates ------------------------------------------------
+  const float dscale = p.det_scale[b];
+  for (int i = tid; i < n; i += nthreads) {
+    const int a = (int)(0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull));
+    const AnchorRef r = anchor_ref(a, p.in_h, p.in_w);
+    const size_t npix = (size_t)(lvl_cnt[r.level] >> 1);
+    const float* bp = p.lv.bbox[r.level] + ((size_t)b * npix + r.pix) * p.lv.bbox_ps[r.level] + r.anchor * 4;
+    const float fs = (float)r.stride;
+    const float cx = (float)((r.pix % r.ws) * r.stride), cy = (float)((r.pix / r.ws) * r.stride);
+    float4 bx;
+    bx.x = __fdiv_rn(__fsub_rn(cx, __fmul_rn(bp[0], fs)), dscale);
+    bx.y = __fdiv_rn(__fsub_rn(cy, __fmul_rn(bp[1], fs)), dscale);
+    bx.z = __fdiv_rn(__fadd_rn(cx, __fmul_rn(bp[2], fs)), dscale);
+    bx.w = __fdiv_rn(__fadd_rn(cy, __fmul_rn(bp[3], fs)), dscale);
+    boxes[i] = bx;
+  }
+  const int words = (n + 31) >> 5;
+  for (int w = tid; w < words; w += nthreads) {
+    const int rem = n - w * 32;
+    alive[w] = rem >= 32 ? 0xFFFFFFFFu : ((1u << rem) - 1u);
+  }
+  __syncthreads();
+
+  // ---- D. greedy NMS over a shared alive bitmask: one warp owns one 32-candidate word at a time ----
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+  for (int i = 0; i < (p.forward_mode ? 0 : n); ++i) {
+    if (!((alive[i >> 5] >> (i & 31)) & 1u)) continue;  // block-uniform: bits only ever clear, and only for j > i
+    const float4 bi = boxes[i];
+    const float ai = __fmul_rn(__fadd_rn(__fsub_rn(bi.z, bi.x), 1.f), __fadd_rn(__fsub_rn(bi.w, bi.y), 1.f));
+    for (int w = ((i + 1) >> 5) + warp; w < words; w += nwarps) {
+      const int j = w * 32 + lane;
+      bool suppress = false;
+      if (j > i && j < n) {
+        const float4 bj = boxes[j];
+        const float aj = __fmul_rn(__fadd_rn(__fsub_rn(bj.z, bj.x), 1.f), __fadd_rn(__fsub_rn(bj.w, bj.y), 1.f));
+        const float ww = fmaxf(0.f, __fadd_rn(__fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), 1.f));
+        const float hh = fmaxf(0.f, __fadd_rn(__fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)), 1.f));
+        const float inter = __fmul_rn(ww, hh);
+        const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter));
+        suppress = !(ovr <= p.iou);  // NaN (0/0 on degenerate boxes) suppresses, as np.where(ovr <= thr) does
+      }
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, suppress);
+      if (lane == 0 && m) alive[w] &= ~m;
+    }
+    __syncthreads();
+  }
+
+  // ---- E. rank the survivors ----------------------------------------------------------------------
+  if (tid == 0) {
+    int acc = 0;
+    for (int w = 0; w < words; ++w) {
+      word_prefix[w] = acc;
+      acc += __popc(alive[w]);
+    }
+    s_keep = acc;
+  }
+  __syncthreads();
+  const int n_keep = s_keep;
+  for (int i = tid; i < n; i += nthreads) {
+    const uint32_t wbits = alive[i >> 5];
+    if ((wbits >> (i & 31)) & 1u) kept_pos[word_prefix[i >> 5] + __popc(wbits & ((1u << (i & 31)) - 1u))] = i;
+  }
+  __syncthreads();
+
+  // ---- F. optional max_num selection by area (or centre-weighted area) -------------------------------
+  int n_out = n_keep;
+  const bool select = p.max_num > 0 && p.max_num < n_keep;
+  if (select) {
+    int P2 = 32;
+    while (P2 < n_keep) P2 <<= 1;
+    uint64_t* k2 = (P2 <= kSmemKeys && keys != smem_keys) ? smem_keys : keys2;
+    float cx = 0.f, cy = 0.f;
+    if (p.metric != 0 && p.image_hw) {
+      cy = (float)(p.image_hw[2 * b] / 2);
+      cx = (float)(p.image_hw[2 * b + 1] / 2);
+    }
+    for (int r = tid; r < P2; r += nthreads) {
+      uint64_t key = 0ull;
+      if (r < n_keep) {
+        const float4 bx = boxes[kept_pos[r]];
+        float v = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+        if (p.metric != 0) {
+          const float ox = __fsub_rn(__fdiv_rn(__fadd_rn(bx.x, bx.z), 2.f), cx);
+          const float oy = __fsub_rn(__fdiv_rn(__fadd_rn(bx.y, bx.w), 2.f), cy);
+          v = __fsub_rn(v, __fmul_rn(__fadd_rn(__fmul_rn(ox, ox), __fmul_rn(oy, oy)), 2.f));
+        }
+        key = ((uint64_t)float_order_bits(v) << 32) | (uint32_t)r;
+      }
+      k2[r] = key;
+    }
+    bitonic_sort_desc(k2, P2);
+    n_out = p.max_num;
+    for (int t = tid; t < n_out; t += nthreads) sel[t] = (int)(k2[t] & 0xFFFFFFFFull);
+    __syncthreads();
+  }
+  const int n_write = min(n_out, p.max_det);
+
+  // ---- G. emit rows ------------------------------------------------------------------------------------
+  for (int t = tid; t < n_write; t += nthreads) {
+    const int r = select ? sel[t] : t;
+    const int i = kept_pos[r];
+    const uint64_t key = keys[i];
+    const int a = (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+    const AnchorRef ar = anchor_ref(a, p.in_h, p.in_w);
+    const float score = p.lv.score[ar.level][((size_t)b * (size_t)(lvl_cnt[ar.level] >> 1) + ar.pix) *
+                                                 p.lv.score_ps[ar.level] + ar.anchor];
+    const float4 bx = boxes[i];
+    float* d = p.det + ((size_t)b * p.max_det + t) * 5;
+    d[0] = bx.x, d[1] = bx.y, d[2] = bx.z, d[3] = bx.w, d[4] = score;
+    const size_t npix = (size_t)(lvl_cnt[ar.level] >> 1);
+    const float* kp = p.lv.kps[ar.level] + ((size_t)b * npix + ar.pix) * p.lv.kps_ps[ar.level] + ar.anchor * 10;
+    const float fs = (float)ar.stride;
+    const float cx = (float)((ar.pix % ar.ws) * ar.stride), cy = (float)((ar.pix / ar.ws) * ar.stride);
+    float* ko = p.kps + ((size_t)b * p.max_det + t) * 10;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      ko[2 * j] = __fdiv_rn(__fadd_rn(cx, __fmul_rn(kp[2 * j], fs)), dscale);
+      ko[2 * j + 1] = __fdiv_rn(__fadd_rn(cy, __fmul_rn(kp[2 * j + 1], fs)), dscale);
+    }
+    if (p.keep_idx && p.forward_mode) {
+      p.keep_idx[(size_t)b * p.max_det + t] = a;
+    } else if (p.keep_idx) {
+      // index into the reference's pre_det order (score desc, anchor DESC): mirror i inside its tie run
+      const uint32_t sb = (uint32_t)(key >> 32);
+      int rs = i, re = i + 1;
+      while (rs > 0 && (uint32_t)(keys[rs - 1] >> 32) == sb) --rs;
+      while (re < n && (uint32_t)(keys[re] >> 32) == sb) ++re;
+      p.keep_idx[(size_t)b * p.max_det + t] = rs + (re - 1 - i);
+    }
+  }
+  if (tid == 0) {
+    int* c = p.counts + 4 * b;
+    c[0] = n_write;
+    c[1] = n_found;
+    c[2] = n_keep;
+    c[3] = (n_found > p.max_cand ? 1 : 0) | (n_out > p.max_det ? 2 : 0);
+  }
+}
+
+// ============================================================================================
+// five-point similarity + warpAffine
+// ============================================================================================
+__constant__ float c_template[10] = {38.2946f, 51.6963f, 73.5318f, 51.5014f, 56.0252f,
+                                     71.7366f, 41.5493f, 92.3655f, 70.7299f, 92.2041f};
+
+__device__ void estimate_norm_dev(const float* __restrict__ lm, int image_size, double* M) {
+  double sx[5], sy[5], dx[5], dy[5];
+  const float ratio = (float)((double)image_size / 112.0);
+  double msx = 0, msy = 0, mdx = 0, mdy = 0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    sx[i] = (double)lm[2 * i], sy[i] = (double)lm[2 * i + 1];
+    const float tx = image_size == 112 ? c_template[2 * i] : __fmul_rn(ratio, c_template[2 * i]);
+    const float ty = image_size == 112 ? c_template[2 * i + 1] : __fmul_rn(ratio, c_template[2 * i + 1]);
+    dx[i] = (double)tx, dy[i] = (double)ty;
+    msx += sx[i], msy += sy[i], mdx += dx[i], mdy += dy[i];
+  }
+  msx /= 5.0, msy /= 5.0, mdx /= 5.0, mdy /= 5.0;
+  double a = 0, bq = 0, v = 0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const double px = sx[i] - msx, py = sy[i] - msy, qx = dx[i] - mdx, qy = dy[i] - mdy;
+    a += px * qx + py * qy;
+    bq += px * qy - py * qx;
+    v += px * px + py * py;
+  }
+  const double pp = a / v, qq = bq / v;
+  M[0] = pp, M[1] = -qq, M[2] = mdx - (pp * msx - qq * msy);
+  M[3] = qq, M[4] = pp, M[5] = mdy - (qq * msx + pp * msy);
+}
+
+__global__ void estimate_norm_kernel(const float* __restrict__ lm, int faces, int image_size, double* __restrict__ out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < faces) estimate_norm_dev(lm + (size_t)f * 10, image_size, out + (size_t)f * 6);
+}
+
+struct WarpParams {
+  const uint8_t* frames;
+  int h, w;
+  const int* frame_idx;
+  const float* landmarks;  // used when m == nullptr
+  const double* m;
+  int faces, size;
+  float mean, scale;
+  void* out_nhwc;
+  int c_pad, is_bf16;
+  uint8_t* crop_u8;
+  double* m_out;
+};
+
+__global__ void __launch_bounds__(256) warp_affine_kernel(WarpParams p) {
+  const int f = blockIdx.y;
+  __shared__ double sM[6];
+  if (threadIdx.x == 0) {
+    if (p.m) {
+      for (int i = 0; i < 6; ++i) sM[i] = p.m[(size_t)f * 6 + i];
+    } else {
+      estimate_norm_dev(p.landmarks + (size_t)f * 10, p.size, sM);
+    }
+    if (p.m_out && blockIdx.x == 0)
+      for (int i = 0; i < 6; ++i) p.m_out[(size_t)f * 6 + i] = sM[i];
+  }
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.size * p.size) return;
+  const int x = idx % p.size, y = idx / p.size;
+  // invert the forward transform exactly as cv2.warpAffine does (float64, no fused multiply-add)
+  double D = __dsub_rn(__dmul_rn(sM[0], sM[4]), __dmul_rn(sM[1], sM[3]));
+  D = D != 0.0 ? 1.0 / D : 0.0;
+  const double i00 = __dmul_rn(sM[4], D), i11 = __dmul_rn(sM[0], D);
+  const double i01 = __dmul_rn(sM[1], -D), i10 = __dmul_rn(sM[3], -D);
+  const double i02 = __dsub_rn(__dmul_rn(-i00, sM[2]), __dmul_rn(i01, sM[5]));
+  const double i12 = __dsub_rn(__dmul_rn(-i10, sM[2]), __dmul_rn(i11, sM[5]));
+  const int adelta = (int)__double2ll_rn(__dmul_rn(__dmul_rn(i00, (double)x), 1024.0));
+  const int bdelta = (int)__double2ll_rn(__dmul_rn(__dmul_rn(i10, (double)x), 1024.0));
+  const int X0 = (int)__double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(i01, (double)y), i02), 1024.0)) + 16;
+  const int Y0 = (int)__double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(i11, (double)y), i12), 1024.0)) + 16;
+  const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+  const int sx = min(max(X >> 5, -32768), 32767), sy = min(max(Y >> 5, -32768), 32767);
+  const int fx = X & 31, fy = Y & 31;
+  const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+  const uint8_t* img = p.frames + (size_t)p.frame_idx[f] * p.h * p.w * 3;
+  const bool x0ok = sx >= 0 && sx < p.w, x1ok = sx + 1 >= 0 && sx + 1 < p.w;
+  const bool y0ok = sy >= 0 && sy < p.h, y1ok = sy + 1 >= 0 && sy + 1 < p.h;
+  int bgr[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    int acc = 0;
+    if (y0ok && x0ok) acc += img[((size_t)sy * p.w + sx) * 3 + c] * w00;
+    if (y0ok && x1ok) acc += img[((size_t)sy * p.w + sx + 1) * 3 + c] * w01;
+    if (y1ok && x0ok) acc += img[((size_t)(sy + 1) * p.w + sx) * 3 + c] * w10;
+    if (y1ok && x1ok) acc += img[((size_t)(sy + 1) * p.w + sx + 1) * 3 + c] * w11;
+    bgr[c] = (acc + 16384) >> 15;
+  }
+  const size_t opix = (size_t)f * p.size * p.size + idx;
+  if (p.crop_u8) {
+    uint8_t* o = p.crop_u8 + opix * 3;
+    o[0] = (uint8_t)bgr[0], o[1] = (uint8_t)bgr[1], o[2] = (uint8_t)bgr[2];
+  }
+  if (p.out_nhwc) {
+    uint16_t h[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float v = c < 3 ? __fmul_rn(__fsub_rn((float)bgr[2 - c], p.mean), p.scale) : 0.f;
+      if (p.is_bf16) {
+        __nv_bfloat16 t = __float2bfloat16_rn(v);
+        h[c] = *reinterpret_cast<uint16_t*>(&t);
+      } else {
+        __half t = __float2half_rn(v);
+        h[c] = *reinterpret_cast<uint16_t*>(&t);
+      }
+    }
+    uint16_t* o = reinterpret_cast<uint16_t*>(p.out_nhwc) + opix * p.c_pad;
+    *reinterpret_cast<uint2*>(o) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
+    for (int c = 4; c < p.c_pad; c += 4) *reinterpret_cast<uint2*>(o + c) = make_uint2(0u, 0u);
+  }
+}
+
+}  // namespace b2f
+
+using namespace b2f;
+
+extern "C" int b2f_letterbox_u8(const uint8_t* frames, int batch, int h, int w, int new_w, int new_h, int in_w,
+                                int in_h, uint8_t* out, void* stream) {
+  ResizeGeom g;
+  int rc = make_geom(&g, h, w, new_w, new_h, in_w, in_h);
+  if (rc) return rc;
+  const long long total = (long long)batch * in_h * in_w;
+  letterbox_kernel<0><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(frames, g, batch, 0.f, 1.f, out, 3, 0);
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b2f_preprocess(const uint8_t* frames, int batch, int h, int w, int new_w, int new_h, int in_w, int in_h,
+                              float mean, float scale, void* out_nhwc, int c_pad, int dtype, void* stream) {
+  B2F_REQUIRE(c_pad >= 4 && c_pad % 4 == 0, "b2f_preprocess: c_pad must be a multiple of 4 (got %d)", c_pad);
+  B2F_REQUIRE(dtype == B2F_F16 || dtype == B2F_BF16, "b2f_preprocess: dtype must be f16 or bf16");
+  ResizeGeom g;
+  int rc = make_geom(&g, h, w, new_w, new_h, in_w, in_h);
+  if (rc) return rc;
+  const long long total = (long long)batch * in_h * in_w;
+  letterbox_kernel<1><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(frames, g, batch, mean, scale, out_nhwc,
+                                                                            c_pad, dtype == B2F_BF16);
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b2f_blob_nchw_f32(const uint8_t* images, int batch, int h, int w, float mean, float scale, float* out,
+                                 void* stream) {
+  const long long total = (long long)batch * 3 * h * w;
+  blob_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(images, batch, h, w, mean, scale, out);
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
+
+static int cap_pow2(int n) {
+  int p = 32;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+extern "C" long long b2f_decode_nms_workspace(int batch, int max_cand) {
+  const long long cap2 = cap_pow2(max_cand);
+  const long long per = cap2 * 8 * 2 + (long long)max_cand * 16 + (long long)max_cand * 8;
+  return ((per + 255) & ~255LL) * batch;
+}
+
+extern "C" int b2f_decode_nms(const b2f_det_levels* lv, int batch, int in_h, int in_w, const float* det_scale,
+                              const int* image_hw, float conf_thres, float iou_thres, int max_num, int metric,
+                              int max_cand, int max_det, float* det, float* kps, int* keep_idx, int* counts,
+                              void* workspace, long long workspace_bytes, void* stream) {
+  B2F_REQUIRE(lv && det_scale && det && kps && counts && workspace, "b2f_decode_nms: null argument");
+  B2F_REQUIRE(in_h % 32 == 0 && in_w % 32 == 0, "b2f_decode_nms: input size must be a multiple of 32");
+  const int total = (in_h / 8) * (in_w / 8) * 2 + (in_h / 16) * (in_w / 16) * 2 + (in_h / 32) * (in_w / 32) * 2;
+  if (max_cand > total) max_cand = total;
+  B2F_REQUIRE(max_cand >= 1 && max_cand <= kAliveWords * 32, "b2f_decode_nms: max_cand %d out of range", max_cand);
+  B2F_REQUIRE(max_det >= 1, "b2f_decode_nms: max_det must be positive");
+  B2F_REQUIRE(workspace_bytes >= b2f_decode_nms_workspace(batch, max_cand), "b2f_decode_nms: workspace too small");
+  DecodeParams p;
+  p.lv = *lv;
+  p.batch = batch, p.in_h = in_h, p.in_w = in_w;
+  p.det_scale = det_scale, p.image_hw = image_hw;
+  p.conf = conf_thres, p.iou = iou_thres;
+  p.forward_mode = iou_thres < 0.f ? 1 : 0;   // negative IoU threshold selects the SCRFD.forward() view
+  p.max_num = p.forward_mode ? 0 : max_num, p.metric = metric, p.max_cand = max_cand, p.cap2 = cap_pow2(max_cand);
+  p.max_det = max_det;
+  p.det = det, p.kps = kps, p.keep_idx = keep_idx, p.counts = counts;
+  p.ws = reinterpret_cast<uint8_t*>(workspace);
+  p.ws_per_frame = b2f_decode_nms_workspace(1, max_cand);
+  decode_nms_kernel<<<batch, 1024, kSmemKeys * 8, (cudaStream_t)stream>>>(p);
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b2f_estimate_norm(const float* landmarks, int faces, int image_size, double* m_out, void* stream) {
+  if (faces <= 0) return 0;
+  estimate_norm_kernel<<<(faces + 127) / 128, 128, 0, (cudaStream_t)stream>>>(landmarks, faces, image_size, m_out);
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
+
+static int launch_warp(WarpParams& p, void* stream) {
+  if (p.faces <= 0) return 0;
+  B2F_REQUIRE(p.faces <= 65535, "norm_crop: at most 65535 faces per call (got %d)", p.faces);
+  dim3 grid((p.size * p.size + 255) / 256, p.faces);
+  warp_affine_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b2f_warp_affine_u8(const uint8_t* frames, int h, int w, const int* frame_idx, const double* m, int faces,
+                                  int size, uint8_t* out, void* stream) {
+  WarpParams p;
+  memset(&p, 0, sizeof(p));
+  p.frames = frames, p.h = h, p.w = w, p.frame_idx = frame_idx, p.m = m, p.faces = faces, p.size = size;
+  p.crop_u8 = out;
+  return launch_warp(p, stream);
+}
+
+extern "C" int b2f_norm_crop(const uint8_t* frames, int h, int w, const int* frame_idx, const float* landmarks,
+                             int faces, int size, float mean, float scale, void* out_nhwc, int c_pad, int dtype,
+                             uint8_t* crop_u8, double* m_out, void* stream) {
+  B2F_REQUIRE(out_nhwc == nullptr || (c_pad >= 4 && c_pad % 4 == 0), "b2f_norm_crop: c_pad must be a multiple of 4");
+  WarpParams p;
+  memset(&p, 0, sizeof(p));
+  p.frames = frames, p.h = h, p.w = w, p.frame_idx = frame_idx, p.landmarks = landmarks, p.faces = faces;
+  p.size = size, p.mean = mean, p.scale = scale, p.out_nhwc = out_nhwc, p.c_pad = c_pad, p.is_bf16 = dtype == B2F_BF16;
+  p.crop_u8 = crop_u8, p.m_out = m_out;
+  return launch_warp(p, stream);
+}

@@ -1,0 +1,759 @@
+// tcgen05 / TMEM / TMA implicit-GEMM kernel for sm_100a.
+//
+// One warp-specialised kernel serves three callers:
+//   * conv2d (3x3 / 1x1 / kxk, stride 1|2) on NHWC fp16|bf16 activations  -- replaces the ONNX Runtime
+//     Conv/BN/Relu/PRelu/Add nodes behind reference models/scrfd.py:83 and models/arcface.py:51
+//   * fully-connected (a kxk "valid" conv over a kxk map)                 -- the ArcFace Gemm node
+//   * cosine top-k matching (1x1 "conv" whose weights are the gallery)    -- reference main.py:136-142,
+//     qdrant_manager.py:164-170, duplicate.py:2726-2797
+//
+// Data path per CTA: TMA (4-D tiled map over the NHWC input, one box per filter tap, OOB zero fill
+// = conv padding, elementStrides = conv stride) -> 128B/64B/32B-swizzled smem ring -> tcgen05.mma
+// (M=128 output pixels x N<=256 output channels, fp32 accumulators in TMEM) -> tcgen05.ld epilogue
+// (bias table / residual / ReLU|PReLU|sigmoid, or running top-k) -> global.
+#include "b2f_common.cuh"
+#include "../../include/b2f.h"
+
+#include <atomic>
+#include <mutex>
+
+namespace b2f {
+
+extern std::atomic<long long> g_launches;
+
+// ------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// rank-R map over 2-byte elements; dims/strides innermost first; strides in bytes for dims 1..R-1
+static int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+                     const uint32_t* box, const uint32_t* estr, int swizzle_bytes, int is_bf16) {
+  EncodeTiledFn fn = get_encode_fn();
+  B2F_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = estr[i];
+  }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_b[i];
+  CUresult r = fn(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank,
+                  const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B2F_REQUIRE(r == CUDA_SUCCESS,
+              "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u] estr [%u %u %u %u] sw %d",
+              (int)r, rank, (unsigned long long)gd[0], (unsigned long long)gd[1],
+              (unsigned long long)(rank > 2 ? gd[2] : 0), (unsigned long long)(rank > 3 ? gd[3] : 0), bx[0], bx[1],
+              rank > 2 ? bx[2] : 0, rank > 3 ? bx[3] : 0, es[0], es[1], rank > 2 ? es[2] : 0, rank > 3 ? es[3] : 0,
+              swizzle_bytes);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel parameters
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxStages = 8;
+constexpr int kATileBytes = 128 * 128;  // 128 rows x 128 B (largest swizzle span)
+constexpr int kTopKMax = 8;
+
+enum { EPI_STORE = 0, EPI_TOPK = 1, EPI_PAIRS = 2 };
+
+struct UmmaParams {
+  // problem geometry (output space)
+  int N, Ho, Wo;            // batch, output height/width
+  int H, W;                 // input height/width (border classes)
+  int cout_p;               // padded output channels (row pitch of `out`)
+  int kh, kw, stride, pad;
+  int cchunks;              // Cin_p / kchunk
+  int kchunk;               // K elements per pipeline stage: 64 / 32 / 16
+  int tw, th, tn;           // M-tile geometry: tw*th*tn <= 128 output pixels
+  int tiles_x, tiles_y;     // tiles along Wo, Ho
+  int block_n;              // UMMA N
+  int n_tiles;              // ceil(cout / block_n)
+  int n_per_cta;            // N tiles looped by one CTA (grid.y = ceil(n_tiles / n_per_cta))
+  int stages, b_tile_bytes, tmem_cols;
+  int is_bf16;
+  // EPI_STORE
+  void* out;
+  int out_dtype;            // 0 f16, 1 bf16, 2 f32
+  const float* bias;        // [bias_classes][cout_p]
+  int bias_classes;         // 1 or 9 (3x3 border classes: which taps fall inside the image)
+  const float* slope;       // PReLU slope [cout_p] (act == 2)
+  int act;                  // 0 none, 1 relu, 2 prelu, 3 sigmoid
+  const void* residual;     // same dtype as activations
+  int res_mode;             // 0 none, 1 same-size, 2 nearest 2x upsample of a (res_h,res_w) map
+  int res_h, res_w;
+  // EPI_TOPK
+  int topk;                 // <= kTopKMax
+  long long n_valid;        // gallery rows
+  const float* row_scale;   // per query (M) multiplier or null
+  const float* col_scale;   // per gallery row (N) multiplier or null
+  float* part_score;        // [Q][gridDim.y][topk]
+  int* part_idx;
+  // EPI_PAIRS (rows row_begin.. of the same matrix against all rows; only j > i is reported)
+  int row_begin;
+  int diag_skip;            // 1: skip column tiles that lie entirely at or below the diagonal
+  float thr_coarse, thr_exact;
+  const float* exact_rows;  // unit fp32 rows for the exact re-check (may be null)
+  int exact_dim;
+  long long* pairs;
+  long long max_pairs;
+  unsigned long long* pair_count;
+};
+
+// ------------------------------------------------------------------------------------------
+// epilogue helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_apply(float v, int act, float slope) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return v >= 0.f ? v : v * slope;
+  if (act == 3) return 1.f / (1.f + expf(-v));
+  return v;
+}
+
+__device__ __forceinline__ void load16_as_float(const void* p, int is_bf16, float (&f)[16]) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (is_bf16) {
+      __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&w[i]);
+      f[2 * i] = __bfloat162float(h.x);
+      f[2 * i + 1] = __bfloat162float(h.y);
+    } else {
+      __half2 h = *reinterpret_cast<__half2*>(&w[i]);
+      f[2 * i] = __half2float(h.x);
+      f[2 * i + 1] = __half2float(h.y);
+    }
+  }
+}
+
+__device__ __forceinline__ void store16(void* p, int dtype, const float (&f)[16]) {
+  if (dtype == 2) {
+    float4* q = reinterpret_cast<float4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+    return;
+  }
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (dtype == 1) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    } else {
+      __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+  }
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// ------------------------------------------------------------------------------------------
+// the kernel: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue
+// ------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(192, 1)
+umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const UmmaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+
+  const int stage_bytes = kATileBytes + p.b_tile_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;
+  uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  const int m_tile = blockIdx.x;
+  const int tx = m_tile % p.tiles_x;
+  const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+  const int tz = m_tile / (p.tiles_x * p.tiles_y);
+  const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tz * p.tn;
+  int nt_begin = blockIdx.y * p.n_per_cta;
+  const int nt_end = min(nt_begin + p.n_per_cta, p.n_tiles);
+  if (EPI == EPI_PAIRS && p.diag_skip) nt_begin = max(nt_begin, (p.row_begin + n0) / p.block_n);
+  const int k_iters = p.kh * p.kw * p.cchunks;
+  const uint32_t row_bytes = p.kchunk * 2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      const uint32_t tx_bytes = (uint32_t)(p.tw * p.th * p.tn) * row_bytes + (uint32_t)p.block_n * row_bytes;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int nt = nt_begin; nt < nt_end; ++nt) {
+        for (int kk = 0; kk < k_iters; ++kk) {
+          const int tap = kk / p.cchunks;
+          const int cc = kk - tap * p.cchunks;
+          const int r = tap / p.kw;
+          const int s = tap - r * p.kw;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = smem + stage * stage_bytes;
+          uint8_t* b_dst = a_dst + kATileBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          tma_load_4d(a_dst, &tmA, &full_bar[stage], cc * p.kchunk, x0 * p.stride + s - p.pad,
+                      y0 * p.stride + r - p.pad, n0);
+          tma_load_3d(b_dst, &tmB, &full_bar[stage], cc * p.kchunk, nt * p.block_n, tap);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    const uint32_t idesc = umma_idesc(128, (uint32_t)p.block_n, (uint32_t)p.is_bf16);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int nt = nt_begin; nt < nt_end; ++nt, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
+      for (int kk = 0; kk < k_iters; ++kk) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          const uint32_t b_addr = a_addr + kATileBytes;
+          const uint64_t da = umma_smem_desc(a_addr, row_bytes);
+          const uint64_t db = umma_smem_desc(b_addr, row_bytes);
+          const int ksteps = p.kchunk >> 4;
+          for (int k = 0; k < ksteps; ++k) {
+            // advance 16 elements (32 B) along K inside the swizzle span: +2 in the (addr >> 4) field
+            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kk | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);           // frees the smem slot when these MMAs retire
+          if (kk == k_iters - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue (4 warps) ================================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may touch
+    const int m = q * 32 + lane;                  // accumulator row == output pixel within the tile
+    const int lx = m % p.tw;
+    const int ly = (m / p.tw) % p.th;
+    const int lz = m / (p.tw * p.th);
+    const int ox = x0 + lx, oy = y0 + ly, on = n0 + lz;
+    const bool valid = (lz < p.tn) && ox < p.Wo && oy < p.Ho && on < p.N;
+
+    if (EPI == EPI_STORE) {
+      int cls = 0;
+      if (p.bias_classes == 9) {
+        const int iy = oy * p.stride - p.pad, ix = ox * p.stride - p.pad;
+        const int cy = iy < 0 ? 0 : (iy + p.kh - 1 >= p.H ? 2 : 1);
+        const int cx = ix < 0 ? 0 : (ix + p.kw - 1 >= p.W ? 2 : 1);
+        cls = cy * 3 + cx;
+      }
+      const float* bias_row = p.bias + (size_t)cls * p.cout_p;
+      const size_t pix = ((size_t)on * p.Ho + oy) * p.Wo + ox;
+      const int esz = p.out_dtype == 2 ? 4 : 2;
+      size_t res_pix = pix;
+      if (p.res_mode == 2) {
+        const int ry = min(oy >> 1, p.res_h - 1), rx = min(ox >> 1, p.res_w - 1);
+        res_pix = ((size_t)on * p.res_h + ry) * p.res_w + rx;
+      }
+      int it = 0;
+      for (int nt = nt_begin; nt < nt_end; ++nt, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
+        const int cbase = nt * p.block_n;
+        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(t_addr + (uint32_t)c0, r);
+          tmem_ld_wait();
+          const int c = cbase + c0;
+          if (valid && c < p.cout_p) {
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(r[i]) + __ldg(bias_row + c + i);
+            if (p.res_mode) {
+              float rs[16];
+              load16_as_float(reinterpret_cast<const uint8_t*>(p.residual) + (res_pix * p.cout_p + c) * 2, p.is_bf16,
+                              rs);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] += rs[i];
+            }
+            if (p.act) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = act_apply(f[i], p.act, p.act == 2 ? __ldg(p.slope + c + i) : 0.f);
+            }
+            store16(reinterpret_cast<uint8_t*>(p.out) + (pix * p.cout_p + c) * esz, p.out_dtype, f);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
+    } else if (EPI == EPI_PAIRS) {
+      const long long gi = (long long)p.row_begin + on;   // global row of this thread
+      int it = 0;
+      for (int nt = nt_begin; nt < nt_end; ++nt, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
+        const long long cbase = (long long)nt * p.block_n;
+        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(t_addr + (uint32_t)c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const long long gj = cbase + c0 + i;
+            const float v = __uint_as_float(r[i]);
+            if (valid && gj > gi && gj < p.n_valid && v >= p.thr_coarse) {
+              bool hit = true;
+              if (p.exact_rows) {
+                const float* a = p.exact_rows + (size_t)gi * p.exact_dim;
+                const float* b = p.exact_rows + (size_t)gj * p.exact_dim;
+                float d = 0.f;
+                for (int k = 0; k < p.exact_dim; ++k) d = fmaf(a[k], b[k], d);
+                hit = d >= p.thr_exact;
+              }
+              if (hit) {
+                const unsigned long long slot = atomicAdd(p.pair_count, 1ull);
+                if ((long long)slot < p.max_pairs) p.pairs[slot] = (gi << 32) | gj;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
+    } else {
+      // running top-k over this CTA's slice of gallery rows; one query row per thread
+      float best_s[kTopKMax];
+      int best_i[kTopKMax];
+#pragma unroll
+      for (int t = 0; t < kTopKMax; ++t) {
+        best_s[t] = -INFINITY;
+        best_i[t] = -1;
+      }
+      const float rsc = (valid && p.row_scale) ? __ldg(p.row_scale + on) : 1.f;
+      float worst = -INFINITY;   // current k-th best: most columns fail this test and skip the insertion
+      int it = 0;
+      for (int nt = nt_begin; nt < nt_end; ++nt, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
+        const long long cbase = (long long)nt * p.block_n;
+        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(t_addr + (uint32_t)c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const long long g = cbase + c0 + i;
+            if (g < p.n_valid) {
+              float v = __uint_as_float(r[i]) * rsc;
+              if (p.col_scale) v *= __ldg(p.col_scale + g);
+              if (v > worst) {
+                // insertion into the descending list; strict '>' keeps the lowest index among equals
+                float cs = v;
+                int ci = (int)g;
+#pragma unroll
+                for (int t = 0; t < kTopKMax; ++t) {
+                  if (t < p.topk && cs > best_s[t]) {
+                    const float ts = best_s[t];
+                    const int ti = best_i[t];
+                    best_s[t] = cs;
+                    best_i[t] = ci;
+                    cs = ts;
+                    ci = ti;
+                  }
+                }
+#pragma unroll
+                for (int t = 0; t < kTopKMax; ++t)
+                  if (t == p.topk - 1) worst = best_s[t];
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
+      if (valid) {
+        const size_t o = ((size_t)on * gridDim.y + blockIdx.y) * p.topk;
+#pragma unroll
+        for (int t = 0; t < kTopKMax; ++t) {
+          if (t < p.topk) {
+            p.part_score[o + t] = best_s[t];
+            p.part_idx[o + t] = best_i[t];
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side planning
+// ------------------------------------------------------------------------------------------
+static int pow2_cols(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+static void pick_m_tile(int N, int Ho, int Wo, int stride, int* tw, int* th, int* tn) {
+  long long best = -1;
+  int bw = 1, bh = 1, bn = 1;
+  const int max_w = Wo < 128 ? Wo : 128;
+  for (int w = 1; w <= max_w; ++w) {
+    if (w * stride > 256) break;
+    const int max_h = (128 / w) < Ho ? (128 / w) : Ho;
+    for (int h = 1; h <= max_h; ++h) {
+      if (h * stride > 256) break;
+      int n = 128 / (w * h);
+      if (n > N) n = N;
+      if (n < 1) continue;
+      const long long tiles = (long long)((Wo + w - 1) / w) * ((Ho + h - 1) / h) * ((N + n - 1) / n);
+      // fewer tiles first; then wider rows (longer contiguous runs in NHWC)
+      if (best < 0 || tiles < best || (tiles == best && w > bw)) {
+        best = tiles;
+        bw = w, bh = h, bn = n;
+      }
+    }
+  }
+  *tw = bw, *th = bh, *tn = bn;
+}
+
+int g_smem_budget_single = 100 * 1024;  // lets two CTAs share an SM when each owns one N tile
+int g_smem_budget_loop = 200 * 1024;
+int g_max_block_n = 256;
+
+template <int EPI>
+static int launch_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaParams& p, int m_tiles, int grid_y,
+                       cudaStream_t stream) {
+  const int stage_bytes = kATileBytes + p.b_tile_bytes;
+  const int budget = p.n_per_cta > 1 ? g_smem_budget_loop : g_smem_budget_single;
+  int stages = (budget - 2048) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  const int k_iters = p.kh * p.kw * p.cchunks;
+  if (stages > k_iters * p.n_per_cta && k_iters * p.n_per_cta >= 2) stages = k_iters * p.n_per_cta;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static std::once_flag once;
+  static cudaError_t attr_rc = cudaSuccess;
+  std::call_once(once, [] {
+    attr_rc = cudaFuncSetAttribute(umma_conv_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  B2F_CHECK_CUDA(attr_rc);
+  B2F_REQUIRE(smem <= 227 * 1024, "umma kernel: %zu bytes of shared memory requested", smem);
+  umma_conv_kernel<EPI><<<dim3(m_tiles, grid_y), 192, smem, stream>>>(tmA, tmB, p);
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
+
+static int pick_kchunk(int cin_p) {
+  if (cin_p % 64 == 0) return 64;
+  if (cin_p % 32 == 0) return 32;
+  return 16;
+}
+
+}  // namespace b2f
+
+using namespace b2f;
+
+extern "C" int b2f_conv2d(const b2f_conv_desc* d, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B2F_REQUIRE(d != nullptr, "b2f_conv2d: null descriptor");
+  B2F_REQUIRE(d->cin_p % 16 == 0 && d->cout_p % 16 == 0, "b2f_conv2d: channels must be padded to 16 (got %d, %d)",
+              d->cin_p, d->cout_p);
+  B2F_REQUIRE(d->stride == 1 || d->stride == 2, "b2f_conv2d: stride %d unsupported", d->stride);
+  B2F_REQUIRE(d->bias != nullptr && d->in != nullptr && d->weight != nullptr && d->out != nullptr,
+              "b2f_conv2d: null tensor");
+  B2F_REQUIRE(d->bias_classes == 1 || (d->bias_classes == 9 && d->kh <= 3 && d->kw <= 3),
+              "b2f_conv2d: bias_classes must be 1 or 9 (3x3)");
+  const int Ho = (d->h + 2 * d->pad - d->kh) / d->stride + 1;
+  const int Wo = (d->w + 2 * d->pad - d->kw) / d->stride + 1;
+  B2F_REQUIRE(Ho == d->ho && Wo == d->wo, "b2f_conv2d: output size mismatch (%dx%d vs %dx%d)", d->ho, d->wo, Ho, Wo);
+
+  UmmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->n, p.Ho = Ho, p.Wo = Wo, p.H = d->h, p.W = d->w;
+  p.cout_p = d->cout_p;
+  p.kh = d->kh, p.kw = d->kw, p.stride = d->stride, p.pad = d->pad;
+  p.kchunk = d->force_kchunk ? d->force_kchunk : pick_kchunk(d->cin_p);
+  B2F_REQUIRE(d->cin_p % p.kchunk == 0, "b2f_conv2d: kchunk %d does not divide cin_p %d", p.kchunk, d->cin_p);
+  p.cchunks = d->cin_p / p.kchunk;
+  pick_m_tile(d->n, Ho, Wo, d->stride, &p.tw, &p.th, &p.tn);
+  p.tiles_x = (Wo + p.tw - 1) / p.tw;
+  p.tiles_y = (Ho + p.th - 1) / p.th;
+  const int tiles_z = (d->n + p.tn - 1) / p.tn;
+  // N tiling: largest block_n <= 256 that divides cout_p evenly into equal 16-multiples
+  int n_tiles = (d->cout_p + g_max_block_n - 1) / g_max_block_n;
+  while ((d->cout_p % n_tiles) != 0 || ((d->cout_p / n_tiles) % 16) != 0) ++n_tiles;
+  p.n_tiles = n_tiles;
+  p.block_n = d->cout_p / n_tiles;
+  p.n_per_cta = 1;
+  p.b_tile_bytes = ((p.block_n * p.kchunk * 2) + 1023) & ~1023;
+  p.tmem_cols = pow2_cols(p.block_n);
+  p.is_bf16 = d->dtype == 1;
+  p.out = d->out, p.out_dtype = d->out_dtype;
+  p.bias = d->bias, p.bias_classes = d->bias_classes;
+  p.slope = d->slope, p.act = d->act;
+  B2F_REQUIRE(d->act != 2 || d->slope != nullptr, "b2f_conv2d: PReLU needs a slope vector");
+  p.residual = d->residual, p.res_mode = d->residual ? d->res_mode : 0;
+  p.res_h = d->res_h, p.res_w = d->res_w;
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)d->cin_p, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
+    uint64_t str[3] = {(uint64_t)d->cin_p * 2, (uint64_t)d->w * d->cin_p * 2, (uint64_t)d->h * d->w * d->cin_p * 2};
+    uint32_t box[4] = {(uint32_t)p.kchunk, (uint32_t)(p.tw * d->stride), (uint32_t)(p.th * d->stride), (uint32_t)p.tn};
+    uint32_t es[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
+    int rc = make_tmap(&tmA, d->in, 4, dims, str, box, es, p.kchunk * 2, p.is_bf16);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)d->cin_p, (uint64_t)d->cout_p, (uint64_t)(d->kh * d->kw)};
+    uint64_t str[2] = {(uint64_t)d->cin_p * 2, (uint64_t)d->cout_p * d->cin_p * 2};
+    uint32_t box[3] = {(uint32_t)p.kchunk, (uint32_t)p.block_n, 1};
+    uint32_t es[3] = {1, 1, 1};
+    int rc = make_tmap(&tmB, d->weight, 3, dims, str, box, es, p.kchunk * 2, p.is_bf16);
+    if (rc) return rc;
+  }
+  const int m_tiles = p.tiles_x * p.tiles_y * tiles_z;
+  return launch_umma<EPI_STORE>(tmA, tmB, p, m_tiles, p.n_tiles, stream);
+}
+
+// partial top-k of Q x G cosine scores: queries [Q][D], gallery [G][D] (both fp16 or bf16, K-major)
+extern "C" int b2f_match_partial(const void* queries, int q, const void* gallery, long long g, int dim, int dtype,
+                                 const float* row_scale, const float* col_scale, int topk, int n_splits,
+                                 float* part_score, int* part_idx, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B2F_REQUIRE(topk >= 1 && topk <= kTopKMax, "b2f_match_partial: topk must be in [1,%d]", kTopKMax);
+  B2F_REQUIRE(dim % 64 == 0, "b2f_match_partial: dim must be a multiple of 64");
+  B2F_REQUIRE(q > 0 && g > 0 && n_splits >= 1, "b2f_match_partial: empty problem");
+  UmmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = q, p.Ho = 1, p.Wo = 1, p.H = 1, p.W = 1;
+  p.kh = p.kw = 1, p.stride = 1, p.pad = 0;
+  p.kchunk = 64, p.cchunks = dim / 64;
+  p.tw = 1, p.th = 1, p.tn = 128;
+  p.tiles_x = p.tiles_y = 1;
+  p.block_n = 256;
+  p.n_tiles = (int)((g + 255) / 256);
+  if (n_splits > p.n_tiles) n_splits = p.n_tiles;
+  p.n_per_cta = (p.n_tiles + n_splits - 1) / n_splits;
+  const int grid_y = (p.n_tiles + p.n_per_cta - 1) / p.n_per_cta;
+  B2F_REQUIRE(grid_y == n_splits, "b2f_match_partial: n_splits %d does not tile %d column tiles evenly (use %d)",
+              n_splits, p.n_tiles, grid_y);
+  p.b_tile_bytes = 256 * 64 * 2;
+  p.tmem_cols = p.n_per_cta > 1 ? 512 : 256;
+  p.is_bf16 = dtype == 1;
+  p.topk = topk, p.n_valid = g;
+  p.row_scale = row_scale, p.col_scale = col_scale;
+  p.part_score = part_score, p.part_idx = part_idx;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)dim, 1, 1, (uint64_t)q};
+    uint64_t str[3] = {(uint64_t)dim * 2, (uint64_t)dim * 2, (uint64_t)dim * 2};
+    uint32_t box[4] = {64, 1, 1, 128};
+    uint32_t es[4] = {1, 1, 1, 1};
+    int rc = make_tmap(&tmA, queries, 4, dims, str, box, es, 128, p.is_bf16);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)dim, (uint64_t)g, 1};
+    uint64_t str[2] = {(uint64_t)dim * 2, (uint64_t)g * dim * 2};
+    uint32_t box[3] = {64, 256, 1};
+    uint32_t es[3] = {1, 1, 1};
+    int rc = make_tmap(&tmB, gallery, 3, dims, str, box, es, 128, p.is_bf16);
+    if (rc) return rc;
+  }
+  const int m_tiles = (q + 127) / 128;
+  return launch_umma<EPI_TOPK>(tmA, tmB, p, m_tiles, grid_y, stream);
+}
+
+
+// all-pairs cosine >= threshold among unit rows: rows [row_begin,row_end) against every row j > i
+extern "C" int b2f_pairs_threshold(const void* emb16, int n, int dim, int dtype, int row_begin, int row_end,
+                                   float threshold, const float* emb_f32, long long* pairs, long long max_pairs,
+                                   unsigned long long* pair_count, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B2F_REQUIRE(dim % 64 == 0, "b2f_pairs_threshold: dim must be a multiple of 64");
+  B2F_REQUIRE(0 <= row_begin && row_begin < row_end && row_end <= n, "b2f_pairs_threshold: bad row range");
+  const int rows = row_end - row_begin;
+  UmmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = rows, p.Ho = 1, p.Wo = 1, p.H = 1, p.W = 1;
+  p.kh = p.kw = 1, p.stride = 1, p.pad = 0;
+  p.kchunk = 64, p.cchunks = dim / 64;
+  p.tw = 1, p.th = 1, p.tn = 128;
+  p.tiles_x = p.tiles_y = 1;
+  p.block_n = 256;
+  p.n_tiles = (n + 255) / 256;
+  const int m_tiles = (rows + 127) / 128;
+  int n_splits = (296 + m_tiles - 1) / m_tiles;
+  if (n_splits > p.n_tiles) n_splits = p.n_tiles;
+  if (n_splits < 1) n_splits = 1;
+  p.n_per_cta = (p.n_tiles + n_splits - 1) / n_splits;
+  const int grid_y = (p.n_tiles + p.n_per_cta - 1) / p.n_per_cta;
+  p.b_tile_bytes = 256 * 64 * 2;
+  p.tmem_cols = 512;
+  p.is_bf16 = dtype == 1;
+  p.n_valid = n;
+  p.row_begin = row_begin, p.diag_skip = 1;
+  // the 16-bit coarse score may sit a little under the exact one: widen the gate, re-check in fp32
+  p.thr_coarse = emb_f32 ? threshold - 0.02f : threshold;
+  p.thr_exact = threshold;
+  p.exact_rows = emb_f32, p.exact_dim = dim;
+  p.pairs = pairs, p.max_pairs = max_pairs, p.pair_count = pair_count;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)dim, 1, 1, (uint64_t)rows};
+    uint64_t str[3] = {(uint64_t)dim * 2, (uint64_t)dim * 2, (uint64_t)dim * 2};
+    uint32_t box[4] = {64, 1, 1, 128};
+    uint32_t es[4] = {1, 1, 1, 1};
+    int rc = make_tmap(&tmA, reinterpret_cast<const uint8_t*>(emb16) + (size_t)row_begin * dim * 2, 4, dims, str, box,
+                       es, 128, p.is_bf16);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)dim, (uint64_t)n, 1};
+    uint64_t str[2] = {(uint64_t)dim * 2, (uint64_t)n * dim * 2};
+    uint32_t box[3] = {64, 256, 1};
+    uint32_t es[3] = {1, 1, 1};
+    int rc = make_tmap(&tmB, emb16, 3, dims, str, box, es, 128, p.is_bf16);
+    if (rc) return rc;
+  }
+  return launch_umma<EPI_PAIRS>(tmA, tmB, p, m_tiles, grid_y, stream);
+}
+
+extern "C" int b2f_match_splits(long long g, int want) {
+  int n_tiles = (int)((g + 255) / 256);
+  if (want > n_tiles) want = n_tiles;
+  if (want < 1) want = 1;
+  int per = (n_tiles + want - 1) / want;
+  return (n_tiles + per - 1) / per;
+}
+
+// ------------------------------------------------------------------------------------------
+// debug: load one TMA box and dump the raw shared-memory image (validates maps / swizzle / strides)
+// ------------------------------------------------------------------------------------------
+namespace b2f {
+__global__ void tma_probe_kernel(const __grid_constant__ CUtensorMap tm, int c0, int c1, int c2, int c3,
+                                 uint32_t bytes, uint8_t* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  __shared__ uint64_t bar;
+  for (uint32_t i = threadIdx.x; i < bytes; i += blockDim.x) smem[i] = 0xAB;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bar, bytes);
+    tma_load_4d(smem, &tm, &bar, c0, c1, c2, c3);
+  }
+  mbar_wait(&bar, 0);
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < bytes; i += blockDim.x) out[i] = smem[i];
+}
+}  // namespace b2f
+
+extern "C" int b2f_debug_tma_probe(const void* src, const long long* dims4, const int* box4, const int* estr4,
+                                   int swizzle_bytes, const int* coords4, unsigned char* out_dev, int out_bytes,
+                                   void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  uint64_t dims[4], str[3];
+  uint32_t box[4], es[4];
+  for (int i = 0; i < 4; ++i) dims[i] = (uint64_t)dims4[i], box[i] = (uint32_t)box4[i], es[i] = (uint32_t)estr4[i];
+  str[0] = dims[0] * 2, str[1] = str[0] * dims[1], str[2] = str[1] * dims[2];
+  CUtensorMap tm;
+  int rc = make_tmap(&tm, src, 4, dims, str, box, es, swizzle_bytes, 0);
+  if (rc) return rc;
+  uint32_t bytes = 2;
+  for (int i = 0; i < 4; ++i) bytes *= (uint32_t)((box4[i] + estr4[i] - 1) / estr4[i]);
+  B2F_REQUIRE((int)bytes <= out_bytes && bytes <= 64 * 1024, "tma probe: box of %u bytes too large", bytes);
+  tma_probe_kernel<<<1, 128, bytes + 1024, stream>>>(tm, coords4[0], coords4[1], coords4[2], coords4[3], bytes, out_dev);
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
