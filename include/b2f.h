@@ -77,6 +77,14 @@ int b2f_decode_nms(const b2f_det_levels* lv, int batch, int in_h, int in_w,
                    void* workspace, long long workspace_bytes, void* stream);
 long long b2f_decode_nms_workspace(int batch, int max_cand);
 
+/* stand-alone NMS over a (K,5) [x1,y1,x2,y2,score] array; `keep` receives indices into dets in visiting
+ * order -- reference SCRFD.nms, models/scrfd.py:180-207.  workspace >= 8 * next_pow2(max(n,32)) bytes. */
+int b2f_nms(const float* dets, int n, float iou_thres, int* keep, int* n_keep, void* workspace,
+            long long workspace_bytes, void* stream);
+/* reference utils/helpers.py:62-83 and :86-107 (float32 add/sub, no clamping: max_shape is never passed) */
+int b2f_distance2bbox(const float* points, const float* distance, int n, float* out, void* stream);
+int b2f_distance2kps(const float* points, const float* distance, int n, int k2, float* out, void* stream);
+
 /* ---- a12: five-point similarity transform (closed-form 2-D Umeyama, float64) -------------------
  * replaces skimage SimilarityTransform.estimate at reference utils/helpers.py:18-53.
  * landmarks [F][5][2] f32 -> M [F][6] f64 row-major 2x3. */

@@ -38,15 +38,21 @@ def load() -> Optional[SimpleNamespace]:
         return name in ("models", "utils") or name.startswith("models.") or name.startswith("utils.")
 
     saved = {k: sys.modules.pop(k) for k in list(sys.modules) if _ours(k)}
-    sys.path.insert(0, root)
+    # the reference's `utils/` has no __init__.py (namespace package), and a regular package of the same
+    # name anywhere on sys.path would win over it: hide this repo's own drop-in `models`/`utils` meanwhile
+    repo_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    saved_path = list(sys.path)
+    sys.path[:] = [root] + [p for p in sys.path
+                            if os.path.abspath(p or os.getcwd()) not in (repo_root, os.path.abspath(root))]
     try:
         importlib.invalidate_caches()
         models = importlib.import_module("models")
         helpers = importlib.import_module("utils.helpers")
         assert os.path.abspath(models.__file__).startswith(os.path.abspath(root))
+        assert os.path.abspath(helpers.__file__).startswith(os.path.abspath(root))
         ns = SimpleNamespace(SCRFD=models.SCRFD, ArcFace=models.ArcFace, helpers=helpers, root=root)
     finally:
-        sys.path.remove(root)
+        sys.path[:] = saved_path
         for k in [k for k in sys.modules if _ours(k)]:
             del sys.modules[k]
         sys.modules.update(saved)

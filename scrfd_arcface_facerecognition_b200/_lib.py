@@ -82,6 +82,9 @@ SIGNATURES = {
     "b2f_decode_nms": [C.POINTER(DetLevels), _i, _i, _i, _vp, _vp, _f, _f, _i, _i, _i, _i, _vp, _vp, _vp, _vp,
                        _vp, _ll, _vp],
     "b2f_decode_nms_workspace": [_i, _i],
+    "b2f_nms": [_vp, _i, _f, _vp, _vp, _vp, _ll, _vp],
+    "b2f_distance2bbox": [_vp, _vp, _i, _vp, _vp],
+    "b2f_distance2kps": [_vp, _vp, _i, _i, _vp, _vp],
     "b2f_estimate_norm": [_vp, _i, _i, _vp, _vp],
     "b2f_warp_affine_u8": [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp],
     "b2f_norm_crop": [_vp, _i, _i, _vp, _vp, _i, _i, _f, _f, _vp, _i, _i, _vp, _vp, _vp],

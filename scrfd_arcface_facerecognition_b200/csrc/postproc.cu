@@ -406,6 +406,77 @@ __global__ void __launch_bounds__(1024, 1) decode_nms_kernel(DecodeParams p) {
   }
 }
 
+
+// ============================================================================================
+// stand-alone greedy NMS over an arbitrary (K,5) array (reference SCRFD.nms, models/scrfd.py:180-207)
+// and the two anchor-decode helpers (reference utils/helpers.py:62-107)
+// ============================================================================================
+__global__ void __launch_bounds__(1024, 1)
+nms_kernel(const float* __restrict__ dets, int n, float iou, uint64_t* __restrict__ keys_g, int P,
+           int* __restrict__ keep, int* __restrict__ n_keep) {
+  extern __shared__ uint64_t smem_keys[];
+  __shared__ uint32_t alive[kAliveWords];
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  uint64_t* keys = (P <= kSmemKeys) ? smem_keys : keys_g;
+  // scores.argsort()[::-1] with a stable sort: score descending, equal scores by DEscending index
+  for (int i = tid; i < P; i += nthreads)
+    keys[i] = i < n ? (((uint64_t)float_order_bits(dets[5 * i + 4]) << 32) | (uint32_t)i) : 0ull;
+  bitonic_sort_desc(keys, P);
+  const int words = (n + 31) >> 5;
+  for (int w = tid; w < words; w += nthreads) {
+    const int rem = n - w * 32;
+    alive[w] = rem >= 32 ? 0xFFFFFFFFu : ((1u << rem) - 1u);
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+  for (int i = 0; i < n; ++i) {
+    if (!((alive[i >> 5] >> (i & 31)) & 1u)) continue;
+    const float* di = dets + 5 * (size_t)(keys[i] & 0xFFFFFFFFull);
+    const float bx1 = di[0], by1 = di[1], bx2 = di[2], by2 = di[3];
+    const float ai = __fmul_rn(__fadd_rn(__fsub_rn(bx2, bx1), 1.f), __fadd_rn(__fsub_rn(by2, by1), 1.f));
+    for (int w = ((i + 1) >> 5) + warp; w < words; w += nwarps) {
+      const int j = w * 32 + lane;
+      bool suppress = false;
+      if (j > i && j < n) {
+        const float* dj = dets + 5 * (size_t)(keys[j] & 0xFFFFFFFFull);
+        const float aj = __fmul_rn(__fadd_rn(__fsub_rn(dj[2], dj[0]), 1.f), __fadd_rn(__fsub_rn(dj[3], dj[1]), 1.f));
+        const float ww = fmaxf(0.f, __fadd_rn(__fsub_rn(fminf(bx2, dj[2]), fmaxf(bx1, dj[0])), 1.f));
+        const float hh = fmaxf(0.f, __fadd_rn(__fsub_rn(fminf(by2, dj[3]), fmaxf(by1, dj[1])), 1.f));
+        const float inter = __fmul_rn(ww, hh);
+        const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter));
+        suppress = !(ovr <= iou);
+      }
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, suppress);
+      if (lane == 0 && m) alive[w] &= ~m;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int c = 0;
+    for (int i = 0; i < n; ++i)
+      if ((alive[i >> 5] >> (i & 31)) & 1u) keep[c++] = (int)(keys[i] & 0xFFFFFFFFull);
+    *n_keep = c;
+  }
+}
+
+__global__ void distance2bbox_kernel(const float* __restrict__ pts, const float* __restrict__ d, int n,
+                                     float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = pts[2 * i], y = pts[2 * i + 1];
+  out[4 * i + 0] = __fsub_rn(x, d[4 * i + 0]);
+  out[4 * i + 1] = __fsub_rn(y, d[4 * i + 1]);
+  out[4 * i + 2] = __fadd_rn(x, d[4 * i + 2]);
+  out[4 * i + 3] = __fadd_rn(y, d[4 * i + 3]);
+}
+__global__ void distance2kps_kernel(const float* __restrict__ pts, const float* __restrict__ d, int n, int k2,
+                                    float* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * k2) return;
+  const int i = t / k2, j = t % k2;
+  out[t] = __fadd_rn(pts[2 * i + (j & 1)], d[t]);
+}
+
 // ============================================================================================
 // five-point similarity + warpAffine
 // ============================================================================================
@@ -600,6 +671,35 @@ extern "C" int b2f_decode_nms(const b2f_det_levels* lv, int batch, int in_h, int
   p.ws = reinterpret_cast<uint8_t*>(workspace);
   p.ws_per_frame = b2f_decode_nms_workspace(1, max_cand);
   decode_nms_kernel<<<batch, 1024, kSmemKeys * 8, (cudaStream_t)stream>>>(p);
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
+
+
+extern "C" int b2f_nms(const float* dets, int n, float iou_thres, int* keep, int* n_keep, void* workspace,
+                       long long workspace_bytes, void* stream) {
+  B2F_REQUIRE(n >= 0 && n <= kAliveWords * 32, "b2f_nms: at most %d boxes (got %d)", kAliveWords * 32, n);
+  const int P = cap_pow2(n);
+  B2F_REQUIRE(workspace_bytes >= (long long)P * 8, "b2f_nms: workspace must hold %d keys", P);
+  nms_kernel<<<1, 1024, kSmemKeys * 8, (cudaStream_t)stream>>>(dets, n, iou_thres,
+                                                              reinterpret_cast<uint64_t*>(workspace), P, keep, n_keep);
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b2f_distance2bbox(const float* points, const float* distance, int n, float* out, void* stream) {
+  if (n <= 0) return 0;
+  distance2bbox_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(points, distance, n, out);
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int b2f_distance2kps(const float* points, const float* distance, int n, int k2, float* out, void* stream) {
+  if (n <= 0) return 0;
+  B2F_REQUIRE(k2 > 0 && k2 % 2 == 0, "b2f_distance2kps: distance must have an even number of columns");
+  distance2kps_kernel<<<(n * k2 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(points, distance, n, k2, out);
   g_launches.fetch_add(1);
   B2F_LAUNCH_CHECK();
   return 0;

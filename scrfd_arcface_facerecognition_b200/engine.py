@@ -1,0 +1,184 @@
+"""Executes a compiled Plan on one B200 through the C-ABI (ctypes) -- PyTorch only owns memory/streams.
+
+Replaces `onnxruntime.InferenceSession.run` at reference models/scrfd.py:83 and
+models/arcface.py:51.  Activations are NHWC fp16 (or bf16) with channels padded to 16; detector
+heads and the embedding come back as fp32.  There is no CPU path: constructing a NetEngine without
+CUDA raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .graph import Plan, FusedOp
+
+F16, BF16, F32 = 0, 1, 2
+
+
+def default_dtype() -> int:
+    return BF16 if os.environ.get("B2F_DTYPE", "f16").lower() in ("bf16", "bfloat16") else F16
+
+
+def torch_dtype(code: int) -> torch.dtype:
+    return torch.bfloat16 if code == BF16 else torch.float16
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Bound:
+    """One op bound to concrete buffers for a given batch size: a ready-to-call closure."""
+    __slots__ = ("fn", "args", "keep")
+
+    def __init__(self, fn, args, keep):
+        self.fn, self.args, self.keep = fn, args, keep
+
+
+class NetEngine:
+    def __init__(self, plan: Plan, device: Optional[torch.device] = None, dtype: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise _lib.B2FError("NetEngine needs a CUDA device: there is no CPU fallback")
+        self.plan = plan
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.dtype = default_dtype() if dtype is None else dtype
+        self.lib = _lib.lib()
+        self._weights: List[Dict[str, torch.Tensor]] = []
+        tdt = torch_dtype(self.dtype)
+        for op in plan.ops:
+            dev: Dict[str, torch.Tensor] = {}
+            for k, arr in op.arrays.items():
+                t = torch.from_numpy(np.ascontiguousarray(arr))
+                if op.kind == "conv" and k == "weight":
+                    t = t.to(tdt)
+                dev[k] = t.to(self.device).contiguous()
+            self._weights.append(dev)
+        self._bound: Dict[int, Tuple[List[_Bound], Dict[str, torch.Tensor], List[torch.Tensor]]] = {}
+        # liveness: last op index that reads each tensor
+        self._last_use: Dict[str, int] = {}
+        for i, op in enumerate(plan.ops):
+            self._last_use[op.src] = i
+            if op.residual:
+                self._last_use[op.residual] = i
+        self._out_tensors = {t for _, t, _ in plan.outputs}
+
+    # ------------------------------------------------------------------------------------------
+    def _bind(self, n: int):
+        plan = self.plan
+        esz = 2
+        free: List[torch.Tensor] = []
+        all_bufs: List[torch.Tensor] = []
+        tens: Dict[str, torch.Tensor] = {}
+        bound: List[_Bound] = []
+        h0, w0 = plan.in_hw
+        in_buf = torch.empty((n, h0, w0, 4), dtype=torch_dtype(self.dtype), device=self.device)
+        tens[plan.input_name] = in_buf
+
+        def alloc(nbytes: int) -> torch.Tensor:
+            best = None
+            for b in free:
+                if b.numel() >= nbytes and (best is None or b.numel() < best.numel()):
+                    best = b
+            if best is not None:
+                free.remove(best)
+                return best
+            b = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            all_bufs.append(b)
+            return b
+
+        backing: Dict[str, torch.Tensor] = {}
+        for i, op in enumerate(plan.ops):
+            spec = plan.tensors[op.dst]
+            nbytes = n * spec.h * spec.w * spec.cp * (4 if spec.f32 else esz)
+            raw = alloc((nbytes + 255) // 256 * 256)
+            backing[op.dst] = raw
+            view = raw[:nbytes].view(torch.float32 if spec.f32 else torch_dtype(self.dtype))
+            tens[op.dst] = view.view(n, spec.h, spec.w, spec.cp)
+            bound.append(self._bind_op(i, op, n, tens))
+            for name in (op.src, op.residual):
+                if name and name in backing and self._last_use.get(name) == i and name not in self._out_tensors:
+                    free.append(backing.pop(name))
+        return bound, tens, all_bufs
+
+    def _bind_op(self, i: int, op: FusedOp, n: int, tens: Dict[str, torch.Tensor]) -> _Bound:
+        a, w = op.attrs, self._weights[i]
+        lib = self.lib
+        src, dst = tens[op.src], tens[op.dst]
+        res = tens[op.residual] if op.residual else None
+        spec_in, spec_out = self.plan.tensors[op.src], self.plan.tensors[op.dst]
+        if op.kind == "conv":
+            d = _lib.ConvDesc()
+            d.n, d.h, d.w, d.cin_p = n, a["h"], a["w"], spec_in.cp
+            d.ho, d.wo, d.cout_p = a["ho"], a["wo"], spec_out.cp
+            d.kh, d.kw, d.stride, d.pad = a["kh"], a["kw"], a["stride"], a["pad"]
+            d.dtype = self.dtype
+            d.out_dtype = F32 if spec_out.f32 else self.dtype
+            d.act = op.act
+            d.bias_classes = a["bias_classes"]
+            d.res_mode = op.res_mode if res is not None else 0
+            if res is not None:
+                rs = self.plan.tensors[op.residual]
+                d.res_h, d.res_w = rs.h, rs.w
+            d.force_kchunk = 0
+            d.in_, d.weight, d.bias = src.data_ptr(), w["weight"].data_ptr(), w["bias"].data_ptr()
+            d.slope = _ptr(w.get("slope"))
+            d.residual = _ptr(res)
+            d.out = dst.data_ptr()
+            return _Bound(lib.b2f_conv2d, (C.byref(d),), (d, src, dst, res))
+        if op.kind == "stem":
+            return _Bound(lib.b2f_stem_conv3x3,
+                          (src.data_ptr(), n, a["h"], a["w"], 4, a["stride"], w["weight"].data_ptr(),
+                           w["bias"].data_ptr(), _ptr(w.get("slope")), op.act, spec_out.cp, self.dtype,
+                           dst.data_ptr()), (src, dst))
+        if op.kind == "dwconv":
+            return _Bound(lib.b2f_dwconv,
+                          (src.data_ptr(), n, a["h"], a["w"], spec_in.cp, a["kh"], a["stride"], a["pad"],
+                           w["weight"].data_ptr(), w["bias"].data_ptr(), _ptr(w.get("slope")), op.act, self.dtype,
+                           dst.data_ptr()), (src, dst))
+        if op.kind == "pool":
+            return _Bound(lib.b2f_pool,
+                          (src.data_ptr(), n, a["h"], a["w"], spec_in.cp, a["k"], a["stride"], a["pad"], a["mode"],
+                           a["ho"], a["wo"], self.dtype, dst.data_ptr()), (src, dst))
+        if op.kind == "eltwise":
+            return _Bound(lib.b2f_eltwise,
+                          (src.data_ptr(), _ptr(res), n * a["h"] * a["w"], spec_in.cp, _ptr(w.get("scale")),
+                           _ptr(w.get("shift")), _ptr(w.get("slope")), op.act, self.dtype, dst.data_ptr()),
+                          (src, dst, res))
+        raise AssertionError(op.kind)
+
+    # ------------------------------------------------------------------------------------------
+    def input_buffer(self, n: int) -> torch.Tensor:
+        """[n, H, W, 4] 16-bit NHWC buffer the preprocess / norm_crop kernels write into."""
+        if n not in self._bound:
+            self._bound[n] = self._bind(n)
+        return self._bound[n][1][self.plan.input_name]
+
+    def run(self, n: int) -> Dict[str, torch.Tensor]:
+        """Run the net on whatever `input_buffer(n)` holds; returns {graph output name: [n,H,W,Cp] fp32}."""
+        if n not in self._bound:
+            self._bound[n] = self._bind(n)
+        bound, tens, _ = self._bound[n]
+        sp = stream_ptr()
+        for b in bound:
+            rc = b.fn(*b.args, sp)
+            if rc != 0:
+                _lib.check(rc, b.fn.__name__)
+        return {name: tens[t] for name, t, _ in self.plan.outputs}
+
+    def num_kernels(self) -> int:
+        return len(self.plan.ops)
+
+    def release(self, n: Optional[int] = None) -> None:
+        if n is None:
+            self._bound.clear()
+        else:
+            self._bound.pop(n, None)

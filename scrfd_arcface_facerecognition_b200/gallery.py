@@ -1,0 +1,237 @@
+"""GPU-resident gallery: cosine top-k matching and duplicate-merge clustering.
+
+Mirrors the matching semantics of the reference:
+  * `best_match`      -- strict-greater scan with threshold, lowest index on ties, "Unknown" = -1
+                         (reference main.py:136-142 over `compute_similarity`, utils/helpers.py:110-123)
+  * `search_similar`  -- exact cosine top-k with score >= threshold, sorted descending
+                         (reference qdrant_manager.py:138-188; Cosine collection, config.json:99-100)
+  * `merge_duplicates`-- greedy one-hop leader merge in ascending id order
+                         (reference duplicate.py:2726-2797)
+The gallery rows are L2-normalised once at insert (qdrant does the same for Cosine); queries are
+normalised on the fly.  The coarse pass is a tcgen05 GEMM with a running top-k epilogue (Q x G is never
+materialised); the k' best coarse candidates are re-scored exactly in fp32 before ranking.
+Sharding: rows are split G/P per rank; each rank matches all queries against its shard and the
+per-shard top-k (score, global index) are exchanged with one NCCL all_gather and merged locally.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import default_dtype, stream_ptr, torch_dtype
+
+KMAX = 8   # kTopKMax / kRescore in the kernels
+
+
+def merge_shard_topk(scores: torch.Tensor, idx: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge per-shard top-k lists [P,Q,k] into a global [Q,k] by (score desc, index asc); -1 = empty slot.
+    Pure index plumbing over a few KB per query batch (runs on whatever device holds the lists)."""
+    p, q, kk = scores.shape
+    s = scores.permute(1, 0, 2).reshape(q, p * kk)
+    i = idx.permute(1, 0, 2).reshape(q, p * kk)
+    s = torch.where(i < 0, torch.full_like(s, float("-inf")), s)
+    big = torch.iinfo(torch.int64).max
+    order = torch.argsort(torch.where(i < 0, torch.full_like(i, big), i), dim=1, stable=True)
+    s, i = torch.gather(s, 1, order), torch.gather(i, 1, order)
+    order = torch.argsort(s, dim=1, descending=True, stable=True)
+    s, i = torch.gather(s, 1, order)[:, :k], torch.gather(i, 1, order)[:, :k]
+    return torch.where(i < 0, torch.zeros_like(s), s), i
+
+
+class Gallery:
+    def __init__(self, dim: int = 512, device: Optional[torch.device] = None, dtype: Optional[int] = None,
+                 rank: int = 0, world_size: int = 1, process_group=None):
+        if not torch.cuda.is_available():
+            raise _lib.B2FError("Gallery needs a CUDA device: there is no CPU fallback")
+        self.dim = dim
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.dtype = default_dtype() if dtype is None else dtype
+        self.rank, self.world_size, self.group = rank, world_size, process_group
+        self.lib = _lib.lib()
+        self.f32 = torch.empty((0, dim), dtype=torch.float32, device=self.device)      # unit rows (this shard)
+        self.h16 = torch.empty((0, dim), dtype=torch_dtype(self.dtype), device=self.device)
+        self.ids: List = []
+        self.payloads: List[dict] = []
+        self.idx_base = 0            # global index of this shard's first row
+        self._scratch = {}
+
+    # ---- population ------------------------------------------------------------------------------
+    def __len__(self) -> int:
+        return int(self.f32.shape[0])
+
+    def _normalise(self, x: torch.Tensor):
+        x = x.to(self.device, torch.float32).contiguous().reshape(-1, self.dim)
+        n = x.shape[0]
+        f32 = torch.empty_like(x)
+        h16 = torch.empty((n, self.dim), dtype=torch_dtype(self.dtype), device=self.device)
+        _lib.check(self.lib.b2f_l2norm_rows(x.data_ptr(), n, self.dim, f32.data_ptr(), h16.data_ptr(), self.dtype,
+                                            None, stream_ptr()), "b2f_l2norm_rows")
+        return f32, h16
+
+    def add(self, embeddings, ids: Optional[List] = None, payloads: Optional[List[dict]] = None) -> None:
+        if isinstance(embeddings, np.ndarray):
+            embeddings = torch.from_numpy(np.ascontiguousarray(embeddings, dtype=np.float32))
+        f32, h16 = self._normalise(embeddings)
+        start = len(self)
+        self.f32 = torch.cat([self.f32, f32])
+        self.h16 = torch.cat([self.h16, h16])
+        n = f32.shape[0]
+        self.ids.extend(ids if ids is not None else range(start, start + n))
+        self.payloads.extend(payloads if payloads is not None else [{} for _ in range(n)])
+
+    def set_shard(self, embeddings, idx_base: int) -> None:
+        """Replace the contents with one shard of a larger gallery whose first row has global index idx_base."""
+        self.f32 = torch.empty((0, self.dim), dtype=torch.float32, device=self.device)
+        self.h16 = torch.empty((0, self.dim), dtype=torch_dtype(self.dtype), device=self.device)
+        self.ids, self.payloads = [], []
+        self.add(embeddings)
+        self.idx_base = int(idx_base)
+
+    def remove(self, row: int) -> None:
+        keep = torch.ones(len(self), dtype=torch.bool, device=self.device)
+        keep[row] = False
+        self.f32, self.h16 = self.f32[keep].contiguous(), self.h16[keep].contiguous()
+        del self.ids[row], self.payloads[row]
+
+    def clear(self) -> None:
+        self.set_shard(torch.empty((0, self.dim)), 0)
+
+    # ---- matching ----------------------------------------------------------------------------------
+    def _scratch_for(self, q: int, splits: int):
+        key = (q, splits)
+        if key not in self._scratch:
+            self._scratch[key] = dict(
+                ps=torch.empty((q, splits, KMAX), dtype=torch.float32, device=self.device),
+                pi=torch.empty((q, splits, KMAX), dtype=torch.int32, device=self.device),
+                os=torch.empty((q, KMAX), dtype=torch.float32, device=self.device),
+                oi=torch.empty((q, KMAX), dtype=torch.int64, device=self.device))
+        return self._scratch[key]
+
+    def match_local(self, queries: torch.Tensor, k: int = 1, threshold: float = float("-inf"),
+                    strict: bool = False, splits: Optional[int] = None):
+        """Top-k of this shard for raw (un-normalised) fp32 queries [Q,dim] on the device.
+        Returns (scores [Q,k] f32, global indices [Q,k] int64 with -1 for empty slots)."""
+        assert 1 <= k <= KMAX
+        q = int(queries.shape[0])
+        g = len(self)
+        if q == 0 or g == 0:
+            return (torch.zeros((q, k), dtype=torch.float32, device=self.device),
+                    torch.full((q, k), -1, dtype=torch.int64, device=self.device))
+        qf, qh = self._normalise(queries)
+        m_tiles = (q + 127) // 128
+        want = splits if splits is not None else max(1, (2 * 148 + m_tiles - 1) // m_tiles)
+        splits = int(self.lib.b2f_match_splits(g, want))
+        sc = self._scratch_for(q, splits)
+        _lib.check(self.lib.b2f_match_partial(qh.data_ptr(), q, self.h16.data_ptr(), g, self.dim, self.dtype, None,
+                                              None, KMAX, splits, sc["ps"].data_ptr(), sc["pi"].data_ptr(),
+                                              stream_ptr()), "b2f_match_partial")
+        thr = float(threshold) if np.isfinite(threshold) else -3.0e38
+        _lib.check(self.lib.b2f_match_merge(sc["ps"].data_ptr(), sc["pi"].data_ptr(), q, splits * KMAX,
+                                            qf.data_ptr(), self.f32.data_ptr(), self.dim, KMAX, thr,
+                                            1 if strict else 0, self.idx_base, sc["os"].data_ptr(),
+                                            sc["oi"].data_ptr(), stream_ptr()), "b2f_match_merge")
+        return sc["os"][:, :k], sc["oi"][:, :k]
+
+    def match(self, queries: torch.Tensor, k: int = 1, threshold: float = float("-inf"), strict: bool = False):
+        """Global top-k across all shards: local match, one all_gather of (score, index), local merge."""
+        s, i = self.match_local(queries, k, threshold, strict)
+        if self.world_size == 1:
+            return s, i
+        import torch.distributed as dist
+        s, i = s.contiguous(), i.contiguous()
+        gs = [torch.empty_like(s) for _ in range(self.world_size)]
+        gi = [torch.empty_like(i) for _ in range(self.world_size)]
+        dist.all_gather(gs, s, group=self.group)
+        dist.all_gather(gi, i, group=self.group)
+        return merge_shard_topk(torch.stack(gs), torch.stack(gi), k)
+
+    # ---- reference-shaped conveniences ------------------------------------------------------------
+    def best_match(self, embedding: np.ndarray, similarity_thresh: float) -> Tuple[int, float]:
+        """(index or -1, similarity) with the strict '>' semantics of reference main.py:136-142
+        (initial best 0, so a match must also be positive)."""
+        q = torch.from_numpy(np.asarray(embedding, np.float32).reshape(1, -1)).to(self.device)
+        s, i = self.match(q, 1, max(float(similarity_thresh), 0.0), strict=True)
+        idx = int(i[0, 0].item())
+        return (idx, float(s[0, 0].item())) if idx >= 0 else (-1, 0.0)
+
+    def search_similar(self, query_embedding, k: int = 5, threshold: float = 0.0) -> List[dict]:
+        """[{person_id, name, similarity, quality, metadata}] like reference qdrant_manager.py:138-188."""
+        q = torch.from_numpy(np.asarray(query_embedding, np.float32).reshape(1, -1)).to(self.device)
+        if q.shape[1] != self.dim:
+            return []
+        out: List[dict] = []
+        kk = min(k, KMAX)
+        s, i = self.match(q, kk, threshold)
+        for sc, ix in zip(s[0].tolist(), i[0].tolist()):
+            if ix < 0:
+                continue
+            row = ix - self.idx_base
+            payload = self.payloads[row] if 0 <= row < len(self.payloads) else {}
+            pid = self.ids[row] if 0 <= row < len(self.ids) else ix
+            out.append({"person_id": payload.get("person_id", pid), "name": payload.get("name", "Unknown"),
+                        "similarity": float(sc), "quality": payload.get("quality", 0.0), "metadata": payload})
+        return out
+
+    # ---- duplicate merge ---------------------------------------------------------------------------
+    def duplicate_pairs(self, threshold: float, row_begin: int = 0, row_end: Optional[int] = None,
+                        max_pairs: Optional[int] = None) -> torch.Tensor:
+        """Sorted int64 keys (i<<32 | j), i<j, cos(i,j) >= threshold, for i in [row_begin,row_end)."""
+        n = len(self)
+        row_end = n if row_end is None else row_end
+        if n < 2 or row_begin >= row_end:
+            return torch.empty(0, dtype=torch.int64, device=self.device)
+        cap = int(max_pairs or max(1 << 20, 64 * (row_end - row_begin)))
+        while True:
+            pairs = torch.empty(cap, dtype=torch.int64, device=self.device)
+            count = torch.zeros(1, dtype=torch.int64, device=self.device)
+            _lib.check(self.lib.b2f_pairs_threshold(self.h16.data_ptr(), n, self.dim, self.dtype, row_begin, row_end,
+                                                    float(threshold), self.f32.data_ptr(), pairs.data_ptr(), cap,
+                                                    count.data_ptr(), stream_ptr()), "b2f_pairs_threshold")
+            found = int(count.item())
+            if found <= cap:
+                return torch.sort(pairs[:found]).values
+            cap = found
+
+    def merge_duplicates(self, threshold: float) -> np.ndarray:
+        """leader[i] for every row (leader[i] == i for survivors), reference duplicate.py:2726-2797 semantics.
+        With world_size > 1 the upper-triangle row blocks are dealt cyclically to ranks and the pair
+        lists are exchanged with all_gather before the (cheap, order-dependent) resolve."""
+        n = len(self)
+        if self.world_size == 1:
+            pairs = self.duplicate_pairs(threshold)
+        else:
+            import torch.distributed as dist
+            blocks = row_blocks(n, self.world_size)
+            mine = [self.duplicate_pairs(threshold, b, e) for r, b, e in blocks if r == self.rank]
+            local = torch.cat(mine) if mine else torch.empty(0, dtype=torch.int64, device=self.device)
+            cnt = torch.tensor([local.numel()], dtype=torch.int64, device=self.device)
+            cnts = [torch.zeros_like(cnt) for _ in range(self.world_size)]
+            dist.all_gather(cnts, cnt, group=self.group)
+            mx = int(max(c.item() for c in cnts))
+            padded = torch.full((max(mx, 1),), -1, dtype=torch.int64, device=self.device)
+            padded[:local.numel()] = local
+            bufs = [torch.empty_like(padded) for _ in range(self.world_size)]
+            dist.all_gather(bufs, padded, group=self.group)
+            pairs = torch.sort(torch.cat([b[:int(c.item())] for b, c in zip(bufs, cnts)])).values
+        leader = torch.empty(3 * n + 8, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.b2f_cluster_resolve(pairs.data_ptr(), pairs.numel(), n, leader.data_ptr(), stream_ptr()),
+                   "b2f_cluster_resolve")
+        return leader[:n].cpu().numpy()
+
+
+def row_blocks(n: int, world_size: int, block: int = 4096) -> List[Tuple[int, int, int]]:
+    """(rank, row_begin, row_end) for the block-partitioned upper triangle: early row blocks see more
+    columns than late ones, so blocks are dealt cyclically for balance."""
+    out = []
+    for bi, start in enumerate(range(0, n, block)):
+        out.append((bi % world_size, start, min(start + block, n)))
+    return out
+
+
+def shard_range(total: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) slice of `total` items owned by `rank` (frames, crops, gallery rows)."""
+    per = (total + world_size - 1) // world_size
+    return min(rank * per, total), min((rank + 1) * per, total)

@@ -1,0 +1,417 @@
+"""ONNX graph -> fused layer plan for the sm_100a kernels (host side, numpy only).
+
+The reference hands its .onnx files to onnxruntime (reference models/scrfd.py:59-62,83;
+models/arcface.py:18-21,51).  Here the same graph is compiled into a short list of fused ops:
+
+  * every Conv absorbs a preceding BatchNormalization (scale folded into the weights, shift turned
+    into a per-border-class bias table so zero padding stays exact), the following
+    BatchNormalization / Mul-by-constant, one residual Add (optionally of a nearest-2x Resize) and
+    the activation (Relu / PRelu / Sigmoid);
+  * Flatten + Gemm become a kxk "valid" convolution over the kxk map (same tensor-core kernel);
+  * Transpose(0,2,3,1) + Reshape(-1,k) on the detector heads are no-ops in NHWC;
+  * whatever is left (pools, stray BN / Add / activations) maps to the small CUDA-core kernels.
+
+Nothing here touches the GPU: `compile_graph` returns numpy weights in kernel layout, so the
+folding arithmetic is unit-tested on the CPU box (tests/test_graph_compile.py).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .onnx_wire import Graph, Node
+
+ACT_NONE, ACT_RELU, ACT_PRELU, ACT_SIGMOID = 0, 1, 2, 3
+_ACT = {"Relu": ACT_RELU, "PRelu": ACT_PRELU, "Sigmoid": ACT_SIGMOID}
+
+
+def pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+@dataclass
+class TensorSpec:
+    name: str
+    c: int
+    h: int
+    w: int
+    cp: int
+    f32: bool = False
+
+
+@dataclass
+class FusedOp:
+    kind: str                       # stem | conv | dwconv | pool | eltwise
+    src: str
+    dst: str
+    residual: Optional[str] = None
+    res_mode: int = 0
+    act: int = ACT_NONE
+    attrs: Dict[str, int] = field(default_factory=dict)
+    arrays: Dict[str, np.ndarray] = field(default_factory=dict)   # kernel-layout host arrays
+    order: int = 0
+
+
+@dataclass
+class Plan:
+    input_name: str
+    in_hw: Tuple[int, int]
+    ops: List[FusedOp]
+    tensors: Dict[str, TensorSpec]
+    outputs: List[Tuple[str, str, int]]      # (graph output name, tensor name, channels used)
+
+    def conv_flops(self, n: int = 1) -> int:
+        total = 0
+        for op in self.ops:
+            if op.kind in ("conv", "stem", "dwconv"):
+                total += 2 * op.attrs["macs_per_image"] * n
+        return total
+
+
+def _bn_affine(g: Graph, node: Node) -> Tuple[np.ndarray, np.ndarray]:
+    gamma, beta, mean, var = (g.initializers[k].astype(np.float64) for k in node.inputs[1:5])
+    s = gamma / np.sqrt(var + float(node.attrs.get("epsilon", 1e-5)))
+    return s, beta - mean * s
+
+
+def _infer_shapes(g: Graph, in_hw: Tuple[int, int]) -> Dict[str, Tuple[int, ...]]:
+    inp = g.real_inputs()[0]
+    shapes: Dict[str, Tuple[int, ...]] = {inp.name: (3, in_hw[0], in_hw[1])}
+    for n in g.nodes:
+        a = n.attrs
+        t = n.op_type
+        if t == "Conv":
+            c, h, w = shapes[n.inputs[0]]
+            wt = g.initializers[n.inputs[1]]
+            p, s = a.get("pads", [0, 0, 0, 0]), a.get("strides", [1, 1])
+            shapes[n.outputs[0]] = (wt.shape[0], (h + p[0] + p[2] - wt.shape[2]) // s[0] + 1,
+                                    (w + p[1] + p[3] - wt.shape[3]) // s[1] + 1)
+        elif t in ("MaxPool", "AveragePool"):
+            c, h, w = shapes[n.inputs[0]]
+            k, s, p = a["kernel_shape"], a.get("strides", [1, 1]), a.get("pads", [0, 0, 0, 0])
+            if a.get("ceil_mode", 0):
+                ho = -(-(h + p[0] + p[2] - k[0]) // s[0]) + 1
+                wo = -(-(w + p[1] + p[3] - k[1]) // s[1]) + 1
+            else:
+                ho = (h + p[0] + p[2] - k[0]) // s[0] + 1
+                wo = (w + p[1] + p[3] - k[1]) // s[1] + 1
+            shapes[n.outputs[0]] = (c, ho, wo)
+        elif t in ("Resize", "Upsample"):
+            c, h, w = shapes[n.inputs[0]]
+            sc = None
+            for nm in n.inputs[1:]:
+                if nm and nm in g.initializers and g.initializers[nm].size == 4:
+                    sc = g.initializers[nm]
+            if sc is None:
+                raise NotImplementedError("Resize without constant scales/sizes is not supported")
+            if sc.dtype.kind == "f":
+                shapes[n.outputs[0]] = (c, int(h * float(sc[2])), int(w * float(sc[3])))
+            else:
+                shapes[n.outputs[0]] = (c, int(sc[2]), int(sc[3]))
+        elif t == "Flatten":
+            shapes[n.outputs[0]] = (int(np.prod(shapes[n.inputs[0]])),)
+        elif t == "Gemm":
+            wt = g.initializers[n.inputs[1]]
+            shapes[n.outputs[0]] = (wt.shape[0] if a.get("transB", 0) else wt.shape[1],)
+        elif t in ("Transpose", "Reshape"):
+            shapes[n.outputs[0]] = shapes[n.inputs[0]]
+        else:
+            src = [i for i in n.inputs if i in shapes]
+            if not src:
+                raise NotImplementedError(f"cannot infer shape for {t}")
+            shapes[n.outputs[0]] = shapes[src[0]]
+    return shapes
+
+
+def compile_graph(g: Graph, in_hw: Tuple[int, int]) -> Plan:
+    nodes = g.nodes
+    init = g.initializers
+    shapes = _infer_shapes(g, in_hw)
+    prod: Dict[str, int] = {}
+    cons: Dict[str, List[int]] = {}
+    for i, n in enumerate(nodes):
+        for o in n.outputs:
+            prod[o] = i
+        for x in n.inputs:
+            if x and x not in init:
+                cons.setdefault(x, []).append(i)
+    graph_out = {o.name for o in g.outputs}
+
+    def single(name: str) -> bool:
+        return len(cons.get(name, [])) == 1 and name not in graph_out
+
+    def const_operand(node: Node, other_than: str) -> Optional[np.ndarray]:
+        for x in node.inputs:
+            if x != other_than and x in init:
+                return init[x].astype(np.float64)
+        return None
+
+    def conv_can_residual(i: int) -> bool:
+        n = nodes[i]
+        wt = init[n.inputs[1]]
+        return n.op_type == "Gemm" or (n.attrs.get("group", 1) == 1 and wt.shape[1] > 4)
+
+    def root_conv_of(name: str) -> Optional[int]:
+        """conv whose pre-Add chain ends at `name` (walk back through single-consumer BN / Mul-const)."""
+        while name in prod and single(name):
+            i = prod[name]
+            n = nodes[i]
+            if n.op_type in ("Conv", "Gemm"):
+                return i if conv_can_residual(i) else None
+            if n.op_type == "BatchNormalization" or (n.op_type == "Mul" and const_operand(n, n.inputs[0]) is not None):
+                name = n.inputs[0]
+                continue
+            return None
+        return None
+
+    absorbed: set = set()
+    alias: Dict[str, str] = {}           # Flatten / Transpose / Reshape outputs -> underlying tensor
+    ops: List[FusedOp] = []
+
+    def resolve(name: str) -> str:
+        while name in alias:
+            name = alias[name]
+        return name
+
+    def follow_chain(idx: int, cout: int, bias: np.ndarray, allow_add: bool):
+        """absorb BN / Mul / Add / activation after node idx.  Returns (scale, shift, residual, res_mode, act, slope, out)."""
+        cur = nodes[idx].outputs[0]
+        scale = np.ones(cout, np.float64)
+        shift = bias.astype(np.float64).copy()
+        residual, res_mode, act, slope = None, 0, ACT_NONE, None
+        stage = 0
+        while single(cur):
+            ni = cons[cur][0]
+            nx = nodes[ni]
+            t = nx.op_type
+            if t == "BatchNormalization" and stage == 0:
+                s, sh = _bn_affine(g, nx)
+                scale, shift = scale * s, shift * s + sh
+            elif t == "Mul" and stage == 0 and const_operand(nx, cur) is not None:
+                m = const_operand(nx, cur).reshape(-1)
+                if m.size not in (1, cout):
+                    break
+                scale, shift = scale * m, shift * m
+            elif t == "Add" and stage == 0 and const_operand(nx, cur) is not None:
+                m = const_operand(nx, cur).reshape(-1)
+                if m.size not in (1, cout):
+                    break
+                shift = shift + m
+            elif t == "Add" and stage == 0 and allow_add:
+                other = [x for x in nx.inputs if x != cur]
+                if len(other) != 1:
+                    break
+                other = other[0]
+                root = root_conv_of(other)
+                if root is not None and root > idx:
+                    break                                   # the later convolution absorbs this Add
+                on = nodes[prod[other]] if other in prod else None
+                if on is not None and on.op_type in ("Resize", "Upsample") and single(other):
+                    ci, hi, wi = shapes[on.inputs[0]]
+                    co, ho, wo = shapes[other]
+                    if on.attrs.get("mode", "nearest") != "nearest" or (ho, wo) != (2 * hi, 2 * wi):
+                        break
+                    residual, res_mode = on.inputs[0], 2
+                    absorbed.add(prod[other])
+                else:
+                    residual, res_mode = other, 1
+                stage = 1
+            elif t in _ACT and stage <= 1:
+                act = _ACT[t]
+                if t == "PRelu":
+                    sl = init[nx.inputs[1]].astype(np.float64).reshape(-1)
+                    slope = np.broadcast_to(sl, (cout,)).copy() if sl.size in (1, cout) else None
+                    if slope is None:
+                        break
+                stage = 2
+            else:
+                break
+            absorbed.add(ni)
+            cur = nx.outputs[0]
+            if stage == 2:
+                break
+        return scale, shift, residual, res_mode, act, slope, cur
+
+    for idx, n in enumerate(nodes):
+        t = n.op_type
+        if t in ("Flatten", "Transpose", "Reshape"):
+            if t == "Transpose" and list(n.attrs.get("perm", [])) != [0, 2, 3, 1]:
+                raise NotImplementedError("only the NCHW->NHWC head transpose is supported")
+            alias[n.outputs[0]] = n.inputs[0]
+            absorbed.add(idx)
+            continue
+        if t not in ("Conv", "Gemm"):
+            continue
+        a = n.attrs
+        x = n.inputs[0]
+        if t == "Conv":
+            W = init[n.inputs[1]].astype(np.float64)
+            group = a.get("group", 1)
+            pads, strides = a.get("pads", [0, 0, 0, 0]), a.get("strides", [1, 1])
+            if len(set(pads)) != 1 or strides[0] != strides[1] or list(a.get("dilations", [1, 1])) != [1, 1]:
+                raise NotImplementedError(f"conv {n.name}: asymmetric pads/strides or dilation unsupported")
+            pad, stride = pads[0], strides[0]
+            cin, hi, wi = shapes[resolve(x)] if resolve(x) in shapes else shapes[x]
+        else:
+            if not a.get("transB", 0) or a.get("transA", 0) or a.get("alpha", 1.0) != 1.0 or a.get("beta", 1.0) != 1.0:
+                raise NotImplementedError("Gemm must be y = x @ W.T + b")
+            base = resolve(x)
+            cin, hi, wi = shapes[base]
+            W = init[n.inputs[1]].astype(np.float64).reshape(-1, cin, hi, wi)
+            group, pad, stride = 1, 0, 1
+        cout, cpg, kh, kw = W.shape
+        b = init[n.inputs[2]].astype(np.float64) if len(n.inputs) > 2 and n.inputs[2] else np.zeros(cout)
+        depthwise = group > 1
+        if depthwise and not (group == cin == cout and cpg == 1):
+            raise NotImplementedError("grouped convolution other than depthwise is unsupported")
+        stem = (not depthwise) and cin <= 4
+        if stem and not (kh == kw == 3 and pad == 1):
+            raise NotImplementedError("first-layer convolution must be 3x3 pad 1")
+
+        # ---- preceding BatchNormalization (input affine) ----------------------------------------
+        src = resolve(x)
+        pre = None
+        if src in prod and not depthwise and not stem:
+            pn = nodes[prod[src]]
+            if pn.op_type == "BatchNormalization" and prod[src] not in absorbed \
+                    and len(cons.get(src, [])) == 1 and src not in graph_out \
+                    and (pad == 0 or (kh <= 3 and kw <= 3 and pad == 1 and hi >= 2 and wi >= 2)):
+                pre = _bn_affine(g, pn)
+                absorbed.add(prod[src])
+                src = resolve(pn.inputs[0])
+        scale, shift, residual, res_mode, act, slope, out = follow_chain(
+            idx, cout, b, allow_add=(not depthwise and not stem))
+        absorbed.add(idx)
+
+        ho = (hi + 2 * pad - kh) // stride + 1
+        wo = (wi + 2 * pad - kw) // stride + 1
+        attrs = dict(cin=cin, cout=cout, kh=kh, kw=kw, stride=stride, pad=pad, h=hi, w=wi, ho=ho, wo=wo,
+                     macs_per_image=cout * cpg * kh * kw * ho * wo)
+        arrays: Dict[str, np.ndarray] = {}
+        cout_p = pad16(cout)
+        if slope is not None:
+            sl = np.zeros(cout_p, np.float32)
+            sl[:cout] = slope
+            arrays["slope"] = sl
+        if depthwise:
+            Wf = W[:, 0] * scale[:, None, None]                      # (C, kh, kw)
+            wk = np.zeros((kh * kw, cout_p), np.float32)
+            wk[:, :cout] = Wf.reshape(cout, kh * kw).T
+            bias = np.zeros(cout_p, np.float32)
+            bias[:cout] = shift
+            arrays.update(weight=wk, bias=bias)
+            kind = "dwconv"
+        elif stem:
+            Wf = W * scale[:, None, None, None]                      # (Cout, Cin, 3, 3)
+            wk = np.zeros((9, 4, cout_p), np.float32)
+            wk[:, :cin, :cout] = Wf.transpose(2, 3, 1, 0).reshape(9, cin, cout)
+            bias = np.zeros(cout_p, np.float32)
+            bias[:cout] = shift
+            arrays.update(weight=wk, bias=bias)
+            kind = "stem"
+        else:
+            cin_p = pad16(cin)
+            classes = 1
+            if pre is not None:
+                s_in, t_in = pre
+                T = np.einsum("oirs,i->rso", W, t_in)                # (kh, kw, Cout): shift seen through each tap
+                W = W * s_in[None, :, None, None]
+                if pad > 0:
+                    classes = 9
+                    table = np.zeros((9, cout), np.float64)
+                    for cy in range(3):
+                        rs = [r for r in range(kh) if not ((cy == 0 and r < pad) or (cy == 2 and r >= kh - pad))]
+                        for cx in range(3):
+                            ss = [s for s in range(kw) if not ((cx == 0 and s < pad) or (cx == 2 and s >= kw - pad))]
+                            table[cy * 3 + cx] = T[np.ix_(rs, ss)].sum(axis=(0, 1))
+                    bias_tab = shift[None, :] + scale[None, :] * table
+                else:
+                    bias_tab = (shift + scale * T.sum(axis=(0, 1)))[None, :]
+            else:
+                bias_tab = shift[None, :]
+            Wf = W * scale[:, None, None, None]
+            wk = np.zeros((kh * kw, cout_p, cin_p), np.float32)
+            wk[:, :cout, :cin] = Wf.transpose(2, 3, 0, 1).reshape(kh * kw, cout, cin)
+            bias = np.zeros((classes, cout_p), np.float32)
+            bias[:, :cout] = bias_tab
+            arrays.update(weight=wk, bias=bias)
+            attrs["bias_classes"] = classes
+            kind = "conv"
+        ops.append(FusedOp(kind, src, out, resolve(residual) if residual else None, res_mode, act, attrs, arrays, idx))
+
+    # ---- everything no convolution absorbed ------------------------------------------------------
+    for idx, n in enumerate(nodes):
+        if idx in absorbed:
+            continue
+        t, a = n.op_type, n.attrs
+        src = resolve(n.inputs[0])
+        c, h, w = shapes[src]
+        if t in ("MaxPool", "AveragePool"):
+            k, s, p = a["kernel_shape"], a.get("strides", [1, 1]), a.get("pads", [0, 0, 0, 0])
+            if k[0] != k[1] or s[0] != s[1] or len(set(p)) != 1:
+                raise NotImplementedError("pooling must be square and symmetric")
+            if t == "AveragePool" and a.get("count_include_pad", 0) and p[0] > 0:
+                raise NotImplementedError("AveragePool with count_include_pad=1 and padding is unsupported")
+            co, ho, wo = shapes[n.outputs[0]]
+            ops.append(FusedOp("pool", src, n.outputs[0], attrs=dict(
+                k=k[0], stride=s[0], pad=p[0], mode=0 if t == "MaxPool" else 1, h=h, w=w, ho=ho, wo=wo, c=c), order=idx))
+        elif t == "BatchNormalization":
+            s, sh = _bn_affine(g, n)
+            cp = pad16(c)
+            sc = np.zeros(cp, np.float32)
+            sf = np.zeros(cp, np.float32)
+            sc[:c], sf[:c] = s, sh
+            ops.append(FusedOp("eltwise", src, n.outputs[0], arrays=dict(scale=sc, shift=sf),
+                               attrs=dict(h=h, w=w, c=c), order=idx))
+        elif t in _ACT:
+            arrays = {}
+            if t == "PRelu":
+                sl = np.zeros(pad16(c), np.float32)
+                sl[:c] = np.broadcast_to(init[n.inputs[1]].reshape(-1), (c,))
+                arrays["slope"] = sl
+            ops.append(FusedOp("eltwise", src, n.outputs[0], act=_ACT[t], arrays=arrays,
+                               attrs=dict(h=h, w=w, c=c), order=idx))
+        elif t == "Add":
+            ops.append(FusedOp("eltwise", src, n.outputs[0], residual=resolve(n.inputs[1]), res_mode=1,
+                               attrs=dict(h=h, w=w, c=c), order=idx))
+        else:
+            raise NotImplementedError(f"ONNX op {t} ({n.name}) is not supported by the B200 engine")
+
+    # ---- topological order over fused ops ------------------------------------------------------------
+    inp = g.real_inputs()[0].name
+    produced_by = {op.dst: op for op in ops}
+    done = {inp}
+    ordered: List[FusedOp] = []
+    pending = sorted(ops, key=lambda o: o.order)
+    while pending:
+        progressed = False
+        for op in list(pending):
+            deps = [op.src] + ([op.residual] if op.residual else [])
+            if all(d in done for d in deps):
+                ordered.append(op)
+                done.add(op.dst)
+                pending.remove(op)
+                progressed = True
+        if not progressed:
+            missing = {d for op in pending for d in [op.src, op.residual] if d and d not in done and d not in produced_by}
+            raise RuntimeError(f"graph compile: unresolved tensors {sorted(missing)[:5]}")
+
+    # ---- tensor table ----------------------------------------------------------------------------------
+    out_tensors = {resolve(o.name) for o in g.outputs}
+    tensors: Dict[str, TensorSpec] = {inp: TensorSpec(inp, 3, in_hw[0], in_hw[1], 4)}
+    for op in ordered:
+        shp = shapes[op.dst]
+        if len(shp) == 1:
+            c, h, w = shp[0], 1, 1
+        else:
+            c, h, w = shp
+        tensors[op.dst] = TensorSpec(op.dst, c, h, w, pad16(c), f32=op.dst in out_tensors)
+        if op.dst in out_tensors and op.kind != "conv":
+            raise NotImplementedError("graph outputs must be produced by a tensor-core convolution / Gemm")
+    outputs = []
+    for o in g.outputs:
+        tname = resolve(o.name)
+        outputs.append((o.name, tname, tensors[tname].c))
+    return Plan(inp, in_hw, ordered, tensors, outputs)

@@ -1,0 +1,64 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/b2f.h declares.
+No compute entry is called here (there is no GPU on the build box and no CPU fallback to call)."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+
+from scrfd_arcface_facerecognition_b200 import _lib
+
+
+def test_library_builds_and_loads():
+    path = _lib.build()
+    assert os.path.exists(path)
+    lib = _lib.lib()
+    assert lib.b2f_version() == 1
+    assert lib.b2f_launch_count() == 0 or lib.b2f_launch_count() > 0
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    declared = _lib.declared_symbols()
+    assert len(declared) >= 25
+    handle = ctypes.CDLL(_lib.SO_PATH)
+    missing = [s for s in declared if not hasattr(handle, s)]
+    assert not missing, f"declared in include/b2f.h but not exported: {missing}"
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes signature table and header disagree"
+
+
+def test_sass_contains_tcgen05_and_tma():
+    out = subprocess.run(["cuobjdump", "-sass", _lib.SO_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "UTCHMMA" in out.stdout and "UTMALDG" in out.stdout and "LDTM" in out.stdout
+    assert "HMMA.16" not in out.stdout                       # no legacy mma.sync path
+
+
+def test_product_modules_do_not_import_the_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "scrfd_arcface_facerecognition_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                if "import oracle" in text or "from oracle" in text:
+                    offenders.append(f)
+    for f in ("models/__init__.py", "models/scrfd.py", "models/arcface.py", "utils/helpers.py"):
+        text = open(os.path.join(root, f)).read()
+        if "oracle" in text:
+            offenders.append(f)
+    assert not offenders
+
+
+def test_compute_without_cuda_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from scrfd_arcface_facerecognition_b200 import helpers
+    import numpy as np
+    with pytest.raises(_lib.B2FError):
+        helpers.compute_similarity(np.ones(4, np.float32), np.ones(4, np.float32))
+    from models import SCRFD
+    with pytest.raises(_lib.B2FError):
+        SCRFD("weights/det_500m.onnx")

@@ -1,0 +1,77 @@
+"""CPU, world_size 2 over gloo: the host-side sharding logic of the multi-GPU path --
+gallery row shards -> per-shard top-k -> all_gather -> merge must equal the single-shard answer,
+and the clustering row blocks must cover the upper triangle exactly once."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from scrfd_arcface_facerecognition_b200.gallery import merge_shard_topk, row_blocks, shard_range
+from tests.golden import inputs
+
+
+def _topk_rows(q, g, k, base):
+    s = q @ g.T
+    sc, ix = torch.sort(s, dim=1, descending=True, stable=True)
+    return sc[:, :k].contiguous(), (ix[:, :k] + base).contiguous()
+
+
+def _worker(rank, world, port, q_np, g_np, k, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    q, g = torch.from_numpy(q_np), torch.from_numpy(g_np)
+    b, e = shard_range(len(g), rank, world)
+    s, i = _topk_rows(q, g[b:e], k, b)
+    gs = [torch.empty_like(s) for _ in range(world)]
+    gi = [torch.empty_like(i) for _ in range(world)]
+    dist.all_gather(gs, s)
+    dist.all_gather(gi, i)
+    ms, mi = merge_shard_topk(torch.stack(gs), torch.stack(gi), k)
+    if rank == 0:
+        ret["s"], ret["i"] = ms.numpy(), mi.numpy()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_sharded_topk_equals_single_shard():
+    g = inputs.embeddings(70, 301)
+    g /= np.linalg.norm(g, axis=1, keepdims=True)
+    q, ids = inputs.planted_queries(g, 71, 9)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    k = 5
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), q, g, k, ret), nprocs=2, join=True)
+    s, i = _topk_rows(torch.from_numpy(q), torch.from_numpy(g), k, 0)
+    np.testing.assert_array_equal(ret["i"], i.numpy())
+    np.testing.assert_array_equal(ret["s"], s.numpy())
+    np.testing.assert_array_equal(ret["i"][:, 0], ids)
+
+
+def test_merge_handles_empty_slots_and_ties():
+    s = torch.tensor([[[0.9, 0.5], [0.9, 0.0]]]).permute(1, 0, 2)          # [P=2, Q=1, k=2]
+    i = torch.tensor([[[7, 3], [2, -1]]]).permute(1, 0, 2)
+    ms, mi = merge_shard_topk(s, i, 2)
+    assert mi.tolist() == [[2, 7]] and torch.allclose(ms, torch.tensor([[0.9, 0.9]]))          # equal scores: lower index first
+    ms, mi = merge_shard_topk(s, i, 4)
+    assert mi.tolist() == [[2, 7, 3, -1]]
+
+
+def test_row_blocks_partition():
+    for n, world in ((10000, 2), (4096 * 3 + 5, 4), (100, 8)):
+        blocks = row_blocks(n, world)
+        covered = np.zeros(n, int)
+        for r, b, e in blocks:
+            assert 0 <= r < world
+            covered[b:e] += 1
+        assert (covered == 1).all()
+    assert shard_range(10, 0, 4) == (0, 3) and shard_range(10, 3, 4) == (9, 10) and shard_range(2, 3, 4) == (2, 2)

@@ -1,0 +1,98 @@
+"""CPU: the fused plan (BN folding, border-class bias tables, residual / upsample fusion, FC-as-conv)
+reproduces the node-by-node fp32 oracle, and the ONNX reader/writer round-trips."""
+import numpy as np
+import pytest
+import torch
+
+import plan_sim
+from oracle import restate
+from oracle.torch_exec import TorchGraph
+from scrfd_arcface_facerecognition_b200 import archs, graph, onnx_wire
+from tests.golden import inputs
+
+
+def _check(key, hw, n=1, tol=2e-5):
+    g = archs.build_arch(key)
+    plan = graph.compile_graph(g, hw)
+    det = key.startswith("scrfd")
+    x = restate.blob_from_bgr(np.stack([inputs.frame(50 + i, hw[0], hw[1]) for i in range(n)]),
+                              1 / 128 if det else 1 / 127.5, 127.5)
+    tg = TorchGraph(g)
+    ref = tg.run(x)
+    out = plan_sim.run_plan(plan, x)
+    for name in tg.output_names:
+        r = ref[name]
+        o = out[name][..., :plan.tensors[dict((a, b) for a, b, _ in plan.outputs)[name]].c]
+        np.testing.assert_allclose(o.reshape(r.shape), r, rtol=0, atol=tol * max(1.0, np.abs(r).max()))
+    return plan
+
+
+def test_scrfd_500m_plan_matches_oracle():
+    plan = _check("scrfd_500m", (160, 160))
+    kinds = {o.kind for o in plan.ops}
+    assert kinds == {"stem", "conv", "dwconv"}
+
+
+def test_scrfd_2p5g_plan_matches_oracle():
+    plan = _check("scrfd_2.5g", (160, 192))
+    assert sum(o.res_mode == 2 for o in plan.ops) == 2            # both top-down upsample-adds are fused
+    assert sum(o.kind == "pool" for o in plan.ops) == 4            # stem max-pool + three avg_down shortcuts
+
+
+def test_arcface_mbf_plan_matches_oracle():
+    _check("arcface_mbf", (112, 112), n=2)
+
+
+@pytest.mark.slow
+def test_arcface_r50_plan_matches_oracle_and_uses_border_tables():
+    plan = _check("arcface_r50", (112, 112), n=1)
+    assert sum(o.attrs.get("bias_classes") == 9 for o in plan.ops) == 24        # one pre-BN per IBasicBlock
+    assert all(o.kind in ("conv", "stem") for o in plan.ops) and len(plan.ops) == 54
+    assert abs(plan.conv_flops() / 1e9 - 12.62) < 0.01                            # SURVEY 8d per-face figure
+
+
+def test_scrfd_10g_flops():
+    plan = graph.compile_graph(archs.build_arch("scrfd_10g"), (640, 640))
+    assert abs(plan.conv_flops() / 1e9 - 26.68) < 0.01                            # SURVEY 8d per-frame figure
+    assert [c for _, _, c in plan.outputs] == [2, 2, 2, 8, 8, 8, 20, 20, 20]
+
+
+def test_fp16_activations_keep_embedding_cosine():
+    g = archs.build_arch("arcface_mbf")
+    plan = graph.compile_graph(g, (112, 112))
+    x = restate.blob_from_bgr(np.stack([inputs.smooth_frame(60 + i, 112, 112) for i in range(2)]), 1 / 127.5, 127.5)
+    ref = TorchGraph(g).run(x)
+    ref = next(iter(ref.values()))
+    for q in (torch.float16, torch.bfloat16):
+        out = next(iter(plan_sim.run_plan(plan, x, quantize=q).values())).reshape(2, -1)
+        cos = (out * ref).sum(1) / np.linalg.norm(out, axis=1) / np.linalg.norm(ref, axis=1)
+        assert cos.min() >= 0.999
+
+
+def test_onnx_roundtrip_and_hand_built_model(tmp_path):
+    g = archs.build_arch("scrfd_500m")
+    path = tmp_path / "m.onnx"
+    onnx_wire.save_model(g, str(path))
+    g2 = onnx_wire.load_model(str(path))
+    assert [n.op_type for n in g2.nodes] == [n.op_type for n in g.nodes]
+    assert [n.inputs for n in g2.nodes] == [n.inputs for n in g.nodes]
+    assert all(np.array_equal(g.initializers[k], g2.initializers[k]) for k in g.initializers)
+    assert [(v.name, v.shape) for v in g2.outputs] == [(v.name, v.shape) for v in g.outputs]
+    for a, b in zip(g.nodes, g2.nodes):
+        for k, v in a.attrs.items():
+            if isinstance(v, float):
+                assert abs(v - b.attrs[k]) < 1e-6
+            else:
+                assert v == b.attrs[k]
+    # a file that is not a model fails loudly
+    bad = tmp_path / "bad.onnx"
+    bad.write_bytes(b"\x08\x07")
+    with pytest.raises(ValueError):
+        onnx_wire.load_model(str(bad))
+
+
+def test_known_weight_names_resolve_to_architectures():
+    assert archs.arch_for_path("./weights/det_10g.onnx") == "scrfd_10g"
+    assert archs.arch_for_path("/x/w600k_r50.onnx") == "arcface_r50"
+    assert archs.arch_for_path("other.onnx") is None
+    assert abs(archs.count_macs(archs.build_arch("scrfd_10g"), (1, 3, 480, 640)) / 1e9 - 10.006) < 0.01
