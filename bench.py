@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the detect -> align -> embed -> match hot path.
+
+Workload (BASELINE.json configs[1]): SCRFD-10G + ArcFace-R50, one step = one batch of 64 synthetic
+1920x1080 frames per GPU, max_num = 16 faces per frame (1024 faces), top-1 against a 1M x 512 gallery.
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference ...                      (reference CPU path on the host cores)
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (frames already in HBM),
+`e2e.value` goes through pinned host buffers with H2D / D2H copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "end-to-end faces/sec SCRFD-10G+ArcFace-R50 (detect->align->embed->match vs 1M gallery)"
+UNIT = "faces/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--faces", type=int, default=16, help="max_num: face slots per frame")
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--gallery", type=int, default=1_000_000, help="total gallery rows (sharded over ranks)")
+    ap.add_argument("--det", default="weights/det_10g.onnx")
+    ap.add_argument("--rec", default="weights/w600k_r50.onnx")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {
+        "workload": (f"configs[1]: SCRFD-10G + ArcFace R50, {a.frames} synthetic {a.width}x{a.height} frames per GPU per step, "
+                     f"max_num={a.faces} ({a.frames * a.faces} faces), top-1 vs {a.gallery} x 512 gallery"),
+        "frames_per_gpu": a.frames, "faces_per_frame": a.faces, "frame_hw": [a.height, a.width],
+        "gallery_rows": a.gallery, "global_frames": a.frames * n_gpus,
+        "l2_policy": f"inputs larger than L2: {a.frames * a.height * a.width * 3 / 1e6:.0f} MB of frames per step",
+        "parallelism": ("single GPU" if n_gpus == 1 else
+                        f"frames split {a.frames}/rank; gallery rows split {a.gallery // n_gpus}/rank; "
+                        "NCCL all_gather of embeddings and of per-shard top-k"),
+        "weights": "random-init synthetic (weights/*.onnx absent offline)",
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference CPU path (oracle port; the reference's own Python when its tree is present)
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_step(a, state, n_frames: int):
+    """One bounded sample of the workload on the host: n_frames frames -> detect -> align -> embed -> match."""
+    det, rec, gal_n, frames = state["det"], state["rec"], state["gallery"], state["frames"]
+    faces = 0
+    for i in range(n_frames):
+        f = frames[i % len(frames)]
+        boxes, kpss = det(f)
+        embs = [rec(f, k) for k in kpss]
+        if embs:
+            e = np.stack(embs)
+            e = e / np.linalg.norm(e, axis=1, keepdims=True)
+            sims = e @ gal_n.T
+            _ = sims.argmax(1), sims.max(1)
+        faces += len(embs)
+    return faces
+
+
+def make_cpu_state(a, gallery_rows: int):
+    import cv2
+    import torch
+    from oracle import ref_loader, restate, shims
+    from oracle.torch_exec import TorchGraph
+    from scrfd_arcface_facerecognition_b200 import archs
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    cv2.setNumThreads(cores)
+    ref = ref_loader.load()
+    rng = np.random.default_rng(0)
+    frames = [rng.integers(0, 256, (a.height, a.width, 3), dtype=np.uint8) for _ in range(2)]
+    gal = np.random.default_rng(2).standard_normal((gallery_rows, 512)).astype(np.float32)
+    gal /= np.linalg.norm(gal, axis=1, keepdims=True)
+    if ref is not None:                     # the reference's own classes, verbatim, over the torch-CPU session shim
+        d = ref.SCRFD(a.det)
+        r = ref.ArcFace(a.rec)
+        det = lambda f: d.detect(f, max_num=a.faces)
+        rec = lambda f, k: r(f, k)
+        kind = "reference"
+    else:                                    # GPU box: no reference tree -> restated oracle around the same net
+        dg, rg = TorchGraph(archs.build_arch(archs.arch_for_path(a.det))), TorchGraph(archs.build_arch(archs.arch_for_path(a.rec)))
+
+        def det(f):
+            canvas, ds = restate.letterbox_u8(f, 640, 640)
+            out = dg.run(restate.blob_from_bgr(canvas, 1 / 128, 127.5))
+            return restate.scrfd_postprocess([out[n] for n in dg.output_names], 640, 640, ds, 0.5, 0.4, a.faces, "max",
+                                             f.shape[:2])
+
+        def rec(f, k):
+            M = restate.estimate_norm_closed_form(k)
+            crop = cv2.warpAffine(f, M, (112, 112), borderValue=0.0)
+            return rg.run(restate.blob_from_bgr(crop, 1 / 127.5, 127.5))[rg.output_names[0]].reshape(-1)
+        kind = "port"
+    return dict(det=det, rec=rec, gallery=gal, frames=frames, cores=cores, kind=kind)
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = min(a.gallery, 100_000)
+    state = make_cpu_state(a, rows)
+    for _ in range(max(a.warmup, 1)):
+        cpu_reference_step(a, state, 1)
+    t0 = time.perf_counter()
+    faces = 0
+    for _ in range(a.steps):
+        faces += cpu_reference_step(a, state, 1)
+    dt = time.perf_counter() - t0
+    v = faces / dt
+    sample = (f"1 frame {a.width}x{a.height} per step (SCRFD-10G torch-CPU fp32 + {a.faces} ArcFace-R50 faces + "
+              f"cosine top-1 vs {rows} gallery rows), {a.steps} steps")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": workload_config(a, a.gpus),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": state["cores"], "kind": state["kind"], "sample": sample,
+                         "note": "reference CPU path, ORT CPUExecutionProvider substituted by torch-CPU fp32"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from models import SCRFD, ArcFace
+    from scrfd_arcface_facerecognition_b200 import _lib
+    from scrfd_arcface_facerecognition_b200.gallery import Gallery, merge_shard_topk, shard_range
+    from scrfd_arcface_facerecognition_b200.pipeline import FacePipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.gpus > 1 and world != a.gpus:
+        raise SystemExit(f"--gpus {a.gpus} needs torchrun with {a.gpus} ranks (WORLD_SIZE={world})")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, F, H, W = a.frames, a.faces, a.height, a.width
+    det = SCRFD(a.det)
+    rec = ArcFace(a.rec)
+    gal = Gallery(rank=rank, world_size=world)
+    g0, g1 = shard_range(a.gallery, rank, world)
+    gen = torch.Generator(device=dev).manual_seed(2)
+    full_seed_rows = torch.randn((g1 - g0, 512), generator=gen, device=dev)   # each rank draws its own shard
+    gal.set_shard(full_seed_rows, g0)
+    del full_seed_rows
+    pipe = FacePipeline(det, rec, gal if world == 1 else None, max_num=F, similarity_thresh=0.4)
+
+    # synthetic frames: two alternating batches, resident in HBM (398 MB each at the default size)
+    rng = np.random.default_rng(1000 + rank)
+    host = [torch.from_numpy(rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)).pin_memory() for _ in range(2)]
+    resident = [h.to(dev) for h in host]
+
+    def match_sharded(emb):
+        """multi-GPU tail: all ranks see all queries, match their gallery shard, exchange top-1"""
+        allq = [torch.empty_like(emb) for _ in range(world)]
+        dist.all_gather(allq, emb.contiguous())
+        q = torch.cat(allq)
+        s, i = gal.match_local(q, 1, 0.4, strict=True)
+        gs = [torch.empty_like(s) for _ in range(world)]
+        gi = [torch.empty_like(i) for _ in range(world)]
+        dist.all_gather(gs, s.contiguous())
+        dist.all_gather(gi, i.contiguous())
+        ms, mi = merge_shard_topk(torch.stack(gs), torch.stack(gi), 1)
+        n = emb.shape[0]
+        return ms[rank * n:(rank + 1) * n], mi[rank * n:(rank + 1) * n]
+
+    use_graph = not a.no_graph
+    if use_graph:
+        static, outs, graph, kernels_per_step = pipe.capture(B, H, W)
+    else:
+        static = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
+        before = _lib.launch_count()
+        outs = pipe.process(static)
+        kernels_per_step = _lib.launch_count() - before
+
+    def step_resident(i):
+        nonlocal outs
+        static.copy_(resident[i & 1], non_blocking=True)       # device-to-device: inputs already in HBM
+        if use_graph:
+            graph.replay()
+        else:
+            outs = pipe.process(static)
+        if world > 1:
+            return match_sharded(outs["emb"])
+        return outs["match_score"], outs["match_idx"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # validation step: how many face slots are real detections (bench counts only those)
+    s, idx = step_resident(0)
+    torch.cuda.synchronize()
+    counts = outs["counts"].cpu().numpy()
+    faces_per_step = int(counts[:, 0].sum())
+    overflow = int((counts[:, 3] != 0).sum())
+    matched = int((idx >= 0).sum().item())
+
+    for i in range(a.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ms_total = timed(step_resident, a.steps)
+    eager_launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / a.steps
+    value = faces_per_step * world / (ms_step / 1e3)
+
+    # ---- e2e: pinned host frames in, results out, double-buffered copy stream ----------------------
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [torch.empty_like(resident[0]) for _ in range(2)]
+    res_host = {k: torch.empty((B, F), dtype=dt).pin_memory() for k, dt in (("score", torch.float32), ("idx", torch.int64))}
+    det_host = torch.empty((B, F, 5), dtype=torch.float32).pin_memory()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    h2d = B * H * W * 3
+    d2h = B * F * (4 + 8) + B * F * 5 * 4
+
+    def upload(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i & 1])
+            stage[i & 1].copy_(host[i & 1], non_blocking=True)
+            ready[i & 1].record(copy_stream)
+
+    def step_e2e(i):
+        nonlocal outs
+        cur = torch.cuda.current_stream()
+        if i == 0:
+            upload(0)
+        upload(i + 1)                                           # next step's frames ride under this step's compute
+        cur.wait_event(ready[i & 1])
+        static.copy_(stage[i & 1], non_blocking=True)
+        consumed[i & 1].record(cur)
+        if use_graph:
+            graph.replay()
+        else:
+            outs = pipe.process(static)
+        sc, ix = match_sharded(outs["emb"]) if world > 1 else (outs["match_score"], outs["match_idx"])
+        res_host["score"].copy_(sc.reshape(B, F), non_blocking=True)
+        res_host["idx"].copy_(ix.reshape(B, F), non_blocking=True)
+        det_host.copy_(outs["det"], non_blocking=True)
+
+    for e in consumed:
+        e.record(torch.cuda.current_stream())
+    for i in range(max(2, a.warmup)):
+        step_e2e(i)
+    torch.cuda.synchronize()
+    for e in consumed:
+        e.record(torch.cuda.current_stream())
+    ms_e2e = timed(step_e2e, a.steps) / a.steps
+    e2e_value = faces_per_step * world / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel (umma_conv_kernel): per-launch CUDA events, eager pass --------
+    roofline = None
+    if rank == 0:
+        roofline = conv_roofline(a, det, rec, static, pipe, B, F)
+        roofline["share_of_step"] = roofline.pop("conv_ms_per_step") / ms_step if ms_step else None
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp16" if rec._engine.dtype == 0 else "bf16", "data": "synthetic",
+        "config": workload_config(a, world), "roofline": roofline,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e},
+        "gpu_launches": int(kernels_per_step * a.steps + eager_launches) if use_graph else int(eager_launches),
+        "kernels_per_step": int(kernels_per_step), "clocks": clocks,
+        "faces_per_step_per_gpu": faces_per_step, "matched_faces": matched, "decode_overflow_frames": overflow,
+        "match_tflops": 2.0 * faces_per_step * world * a.gallery * 512 / (ms_step / 1e3) / 1e12,
+        "cuda_graph": use_graph,
+    }
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(a)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def conv_roofline(a, det, rec, frames, pipe, B, F):
+    """Time every launch of the tensor-core conv kernel in one eager pass of the two nets (CUDA events on the
+    launching stream) and relate its algorithmic FLOPs to the measured cuBLAS bf16 peak."""
+    import torch
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = json.load(open(peaks_path)).get("bf16_tflops_sustained", 1388.5)
+        src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"
+    else:
+        peak, src = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
+    rows = []
+    for rep in range(3):                                  # the last repetition is the measured one
+        rows = []
+        t_det, t_rec = [], []
+        eng_d = det._engine_for(det.input_size[1], det.input_size[0])
+        eng_d.run(B, timings=t_det)
+        rec._engine.run(B * F, timings=t_rec)
+        torch.cuda.synchronize()
+        for eng, n, tl in ((eng_d, B, t_det), (rec._engine, B * F, t_rec)):
+            for i, kind, e0, e1 in tl:
+                if kind == "conv":
+                    rows.append((eng.op_flops(i, n), e0.elapsed_time(e1)))
+    flops = sum(r[0] for r in rows)
+    ms = sum(r[1] for r in rows)
+    achieved = flops / (ms / 1e3) / 1e12
+    return {"bound": "tensor", "kernel": "umma_conv_kernel<EPI_STORE> (all conv/FC launches of SCRFD-10G + R50)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": src, "launches_per_step": len(rows), "flops_per_step": flops, "conv_ms_per_step": ms}
+
+
+def cpu_baseline(a):
+    rows = min(a.gallery, 100_000)
+    state = make_cpu_state(a, rows)
+    cpu_reference_step(a, state, 1)
+    t0 = time.perf_counter()
+    n_frames, faces = 0, 0
+    while time.perf_counter() - t0 < 12.0 and n_frames < 8:
+        faces += cpu_reference_step(a, state, 1)
+        n_frames += 1
+    dt = time.perf_counter() - t0
+    return {"value": faces / dt, "unit": UNIT, "cores": state["cores"], "kind": state["kind"],
+            "sample": (f"{n_frames} frames {a.width}x{a.height} (SCRFD-10G + {a.faces} R50 faces each, torch-CPU fp32) "
+                       f"+ cosine top-1 vs {rows} gallery rows"),
+            "note": "reference CPU path, ORT CPUExecutionProvider substituted by torch-CPU fp32"}
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -162,17 +162,28 @@ class NetEngine:
             self._bound[n] = self._bind(n)
         return self._bound[n][1][self.plan.input_name]
 
-    def run(self, n: int) -> Dict[str, torch.Tensor]:
-        """Run the net on whatever `input_buffer(n)` holds; returns {graph output name: [n,H,W,Cp] fp32}."""
+    def run(self, n: int, timings: Optional[list] = None) -> Dict[str, torch.Tensor]:
+        """Run the net on whatever `input_buffer(n)` holds; returns {graph output name: [n,H,W,Cp] fp32}.
+        `timings`, when given, receives (op index, kind, start event, end event) per launch (bench roofline)."""
         if n not in self._bound:
             self._bound[n] = self._bind(n)
         bound, tens, _ = self._bound[n]
         sp = stream_ptr()
-        for b in bound:
+        for i, b in enumerate(bound):
+            if timings is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             rc = b.fn(*b.args, sp)
             if rc != 0:
                 _lib.check(rc, b.fn.__name__)
+            if timings is not None:
+                e1.record()
+                timings.append((i, self.plan.ops[i].kind, e0, e1))
         return {name: tens[t] for name, t, _ in self.plan.outputs}
+
+    def op_flops(self, i: int, n: int) -> int:
+        op = self.plan.ops[i]
+        return 2 * op.attrs.get("macs_per_image", 0) * n
 
     def num_kernels(self) -> int:
         return len(self.plan.ops)
