@@ -84,13 +84,12 @@ class NetEngine:
         tens[plan.input_name] = in_buf
 
         def alloc(nbytes: int) -> torch.Tensor:
-            best = None
-            for b in free:
-                if b.numel() >= nbytes and (best is None or b.numel() < best.numel()):
-                    best = b
-            if best is not None:
-                free.remove(best)
-                return best
+            best = -1
+            for j, b in enumerate(free):
+                if b.numel() >= nbytes and (best < 0 or b.numel() < free[best].numel()):
+                    best = j
+            if best >= 0:
+                return free.pop(best)
             b = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             all_bufs.append(b)
             return b

@@ -7,7 +7,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 groups=("$@")
 [ ${#groups[@]} -eq 0 ] && groups=(tma conv layers exact decode match models)
 declare -A sel=(
-  [tma]="tests/test_gpu_kernels.py -k tma"
+  [tma]="tests/test_gpu_kernels.py -k tma_box"
   [conv]="tests/test_gpu_kernels.py -k conv2d"
   [layers]="tests/test_gpu_kernels.py -k 'stem or depthwise or pool'"
   [exact]="tests/test_gpu_kernels.py -k 'letterbox or blob or warp'"
