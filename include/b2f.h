@@ -37,7 +37,8 @@ int b2f_version(void);
 const char* b2f_last_error(void);
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 long long b2f_launch_count(void);
-/* tuning knobs for sweeps: key 0 = smem budget (bytes) for single-N-tile CTAs, 1 = max UMMA N */
+/* tuning knobs for sweeps: key 0 = smem budget (bytes) for single-N-tile CTAs, 1 = max UMMA N,
+ * 2 = persistent conv kernel on/off (off = one CTA per output tile) */
 int b2f_set_tuning(int key, int value);
 
 /* ---- a2: aspect-preserving resize + top-left zero letterbox, uint8 out -------------------------

@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(256)
 stem_conv_kernel(const uint16_t* __restrict__ in, int n, int h, int w, int stride, int ho, int wo,
                  const float* __restrict__ weight /*[9][4][cout_p]*/, const float* __restrict__ bias,
                  const float* __restrict__ slope, int act, int cout_p, int is_bf16, uint16_t* __restrict__ out) {
-  extern __shared__ float s_w[];  // [9*4][cout_p] + bias[cout_p] + slope[cout_p]
+  // each thread: 16 output channels x 2 horizontally adjacent output pixels, weights read as float4 from smem
+  extern __shared__ __align__(16) float s_w[];  // [9*4][cout_p] + bias[cout_p] + slope[cout_p]
   const int wsize = 36 * cout_p;
   for (int i = threadIdx.x; i < wsize; i += blockDim.x) s_w[i] = weight[i];
   for (int i = threadIdx.x; i < cout_p; i += blockDim.x) {
@@ -61,39 +62,71 @@ stem_conv_kernel(const uint16_t* __restrict__ in, int n, int h, int w, int strid
   }
   __syncthreads();
   const int groups = cout_p >> 4;
-  const long long total = (long long)n * ho * wo * groups;
+  const int pairs = (wo + 1) >> 1;
+  const long long total = (long long)n * ho * pairs * groups;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
     const int cg = (int)(t % groups);
-    const long long pix = t / groups;
-    const int ox = (int)(pix % wo), oy = (int)((pix / wo) % ho), b = (int)(pix / ((long long)wo * ho));
-    float acc[16];
+    const long long pr = t / groups;
+    const int px = (int)(pr % pairs), oy = (int)((pr / pairs) % ho), b = (int)(pr / ((long long)pairs * ho));
+    const int ox = px * 2;
+    float acc0[16], acc1[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = s_w[wsize + cg * 16 + i];
+    for (int i = 0; i < 16; ++i) acc0[i] = acc1[i] = s_w[wsize + cg * 16 + i];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int iy = oy * stride + r - 1;
       if (iy < 0 || iy >= h) continue;
+      const uint16_t* row = in + ((size_t)b * h + iy) * w * 4;
+      float v[5][3];                       // up to stride + 3 input columns
+      const int ix0 = ox * stride - 1;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        const int ix = ix0 + c;
+        uint2 q = make_uint2(0u, 0u);
+        if (c < stride + 3 && ix >= 0 && ix < w) q = *reinterpret_cast<const uint2*>(row + (size_t)ix * 4);
+        v[c][0] = h2f((uint16_t)(q.x & 0xFFFF), is_bf16);
+        v[c][1] = h2f((uint16_t)(q.x >> 16), is_bf16);
+        v[c][2] = h2f((uint16_t)(q.y & 0xFFFF), is_bf16);
+      }
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
-        const int ix = ox * stride + s - 1;
-        if (ix < 0 || ix >= w) continue;
-        const uint2 q = *reinterpret_cast<const uint2*>(in + (((size_t)b * h + iy) * w + ix) * 4);
-        const float v0 = h2f((uint16_t)(q.x & 0xFFFF), is_bf16), v1 = h2f((uint16_t)(q.x >> 16), is_bf16),
-                    v2 = h2f((uint16_t)(q.y & 0xFFFF), is_bf16);
         const float* wp = s_w + ((r * 3 + s) * 4) * cout_p + cg * 16;
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          acc[i] = fmaf(v0, wp[i], fmaf(v1, wp[cout_p + i], fmaf(v2, wp[2 * cout_p + i], acc[i])));
+        for (int ci = 0; ci < 3; ++ci) {
+          const float a0 = v[s][ci];
+          const float a1 = stride == 1 ? v[s + 1][ci] : v[s + 2][ci];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wp + ci * cout_p + q4 * 4);
+            acc0[q4 * 4 + 0] = fmaf(a0, w4.x, acc0[q4 * 4 + 0]);
+            acc0[q4 * 4 + 1] = fmaf(a0, w4.y, acc0[q4 * 4 + 1]);
+            acc0[q4 * 4 + 2] = fmaf(a0, w4.z, acc0[q4 * 4 + 2]);
+            acc0[q4 * 4 + 3] = fmaf(a0, w4.w, acc0[q4 * 4 + 3]);
+            acc1[q4 * 4 + 0] = fmaf(a1, w4.x, acc1[q4 * 4 + 0]);
+            acc1[q4 * 4 + 1] = fmaf(a1, w4.y, acc1[q4 * 4 + 1]);
+            acc1[q4 * 4 + 2] = fmaf(a1, w4.z, acc1[q4 * 4 + 2]);
+            acc1[q4 * 4 + 3] = fmaf(a1, w4.w, acc1[q4 * 4 + 3]);
+          }
+        }
       }
     }
+    const float* sl = s_w + wsize + cout_p + cg * 16;
     float o8[8];
-    uint16_t* op = out + (size_t)pix * cout_p + cg * 16;
+    uint16_t* op = out + (((size_t)b * ho + oy) * wo + ox) * cout_p + cg * 16;
 #pragma unroll
     for (int half_i = 0; half_i < 2; ++half_i) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o8[i] = act_f(acc[half_i * 8 + i], act, s_w[wsize + cout_p + cg * 16 + half_i * 8 + i]);
+      for (int i = 0; i < 8; ++i) o8[i] = act_f(acc0[half_i * 8 + i], act, sl[half_i * 8 + i]);
       *reinterpret_cast<uint4*>(op + half_i * 8) = pack8(o8, is_bf16);
+    }
+    if (ox + 1 < wo) {
+#pragma unroll
+      for (int half_i = 0; half_i < 2; ++half_i) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o8[i] = act_f(acc1[half_i * 8 + i], act, sl[half_i * 8 + i]);
+        *reinterpret_cast<uint4*>(op + cout_p + half_i * 8) = pack8(o8, is_bf16);
+      }
     }
   }
 }
@@ -385,7 +418,7 @@ extern "C" int b2f_stem_conv3x3(const void* in, int n, int h, int w, int cin_s, 
   B2F_REQUIRE(cout_p % 16 == 0 && cout_p <= 256, "b2f_stem_conv3x3: cout_p %d unsupported", cout_p);
   B2F_REQUIRE(act != 2 || slope != nullptr, "b2f_stem_conv3x3: PReLU needs slope");
   const int ho = (h + 2 - 3) / stride + 1, wo = (w + 2 - 3) / stride + 1;
-  const long long total = (long long)n * ho * wo * (cout_p / 16);
+  const long long total = (long long)n * ho * ((wo + 1) / 2) * (cout_p / 16);
   const size_t smem = (size_t)(36 + 2) * cout_p * sizeof(float);
   stem_conv_kernel<<<grid_for(total, 256), 256, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint16_t*>(in), n, h, w, stride, ho, wo, weight, bias, slope, act, cout_p,

@@ -9,6 +9,7 @@ namespace b2f {
 std::atomic<long long> g_launches{0};
 extern int g_smem_budget_single;
 extern int g_max_block_n;
+extern int g_persistent;
 }  // namespace b2f
 
 static thread_local char g_err[1024] = "";
@@ -33,6 +34,10 @@ extern "C" int b2f_set_tuning(int key, int value) {
   if (key == 1) {
     B2F_REQUIRE(value >= 16 && value <= 256 && value % 16 == 0, "tuning 1 (max UMMA N) out of range: %d", value);
     b2f::g_max_block_n = value;
+    return 0;
+  }
+  if (key == 2) {
+    b2f::g_persistent = value ? 1 : 0;
     return 0;
   }
   b2f_set_error("unknown tuning key %d", key);

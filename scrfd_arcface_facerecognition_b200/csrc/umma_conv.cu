@@ -93,6 +93,7 @@ struct UmmaParams {
   int n_tiles;              // ceil(cout / block_n)
   int n_per_cta;            // N tiles looped by one CTA (grid.y = ceil(n_tiles / n_per_cta))
   int stages, b_tile_bytes, tmem_cols;
+  int total_tiles, n_acc, acc_stride;   // persistent kernel: tiles = M tiles x N tiles, TMEM accumulator ring
   int is_bf16;
   // EPI_STORE
   void* out;
@@ -465,6 +466,218 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// persistent convolution kernel (EPI_STORE only): one CTA per SM loops over output tiles.
+//   warp 0 = TMA producer (never drains between tiles), warp 1 = MMA issuer over a ring of TMEM
+//   accumulators, warps 2..9 = two epilogue groups that alternate tiles, so the epilogue of tile i
+//   overlaps the MMAs of tile i+1 and barrier / TMEM set-up is paid once per SM instead of per tile.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxAcc = 4;
+constexpr int kPersistThreads = 320;
+
+__device__ __forceinline__ void epilogue_store16(const UmmaParams& p, const uint32_t* r, const float* bias_row, int c,
+                                                 size_t pix, size_t res_pix, int esz) {
+  float f[16];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_row + c) + v);
+    f[4 * v + 0] = __uint_as_float(r[4 * v + 0]) + b4.x;
+    f[4 * v + 1] = __uint_as_float(r[4 * v + 1]) + b4.y;
+    f[4 * v + 2] = __uint_as_float(r[4 * v + 2]) + b4.z;
+    f[4 * v + 3] = __uint_as_float(r[4 * v + 3]) + b4.w;
+  }
+  if (p.res_mode) {
+    float rs[16];
+    load16_as_float(reinterpret_cast<const uint8_t*>(p.residual) + (res_pix * p.cout_p + c) * 2, p.is_bf16, rs);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] += rs[i];
+  }
+  if (p.act == 1) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+  } else if (p.act == 2) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.slope + c) + v);
+      f[4 * v + 0] = f[4 * v + 0] >= 0.f ? f[4 * v + 0] : f[4 * v + 0] * s4.x;
+      f[4 * v + 1] = f[4 * v + 1] >= 0.f ? f[4 * v + 1] : f[4 * v + 1] * s4.y;
+      f[4 * v + 2] = f[4 * v + 2] >= 0.f ? f[4 * v + 2] : f[4 * v + 2] * s4.z;
+      f[4 * v + 3] = f[4 * v + 3] >= 0.f ? f[4 * v + 3] : f[4 * v + 3] * s4.w;
+    }
+  } else if (p.act == 3) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = 1.f / (1.f + expf(-f[i]));
+  }
+  store16(reinterpret_cast<uint8_t*>(p.out) + (pix * p.cout_p + c) * esz, p.out_dtype, f);
+}
+
+__global__ void __launch_bounds__(kPersistThreads, 1)
+umma_conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                            const UmmaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+
+  const int stage_bytes = kATileBytes + p.b_tile_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;
+  uint64_t* tempty_bar = bars + 2 * kMaxStages + kMaxAcc;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kMaxAcc);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int k_iters = p.kh * p.kw * p.cchunks;
+  const uint32_t row_bytes = p.kchunk * 2;
+  const int tiles_xy = p.tiles_x * p.tiles_y;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kMaxAcc; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      const uint32_t tx_bytes = (uint32_t)(p.tw * p.th * p.tn) * row_bytes + (uint32_t)p.block_n * row_bytes;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int nt = t % p.n_tiles;
+        const int m_tile = t / p.n_tiles;
+        const int x0 = (m_tile % p.tiles_x) * p.tw;
+        const int y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.th;
+        const int n0 = (m_tile / tiles_xy) * p.tn;
+        for (int kk = 0; kk < k_iters; ++kk) {
+          const int tap = kk / p.cchunks;
+          const int cc = kk - tap * p.cchunks;
+          const int r = tap / p.kw;
+          const int s = tap - r * p.kw;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = smem + stage * stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          tma_load_4d(a_dst, &tmA, &full_bar[stage], cc * p.kchunk, x0 * p.stride + s - p.pad,
+                      y0 * p.stride + r - p.pad, n0);
+          tma_load_3d(a_dst + kATileBytes, &tmB, &full_bar[stage], cc * p.kchunk, nt * p.block_n, tap);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    const uint32_t idesc = umma_idesc(128, (uint32_t)p.block_n, (uint32_t)p.is_bf16);
+    const int ksteps = p.kchunk >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const int acc = it % p.n_acc;
+      const uint32_t acc_phase = (uint32_t)(it / p.n_acc) & 1u;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+      for (int kk = 0; kk < k_iters; ++kk) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          const uint64_t da = umma_smem_desc(a_addr, row_bytes);
+          const uint64_t db = umma_smem_desc(a_addr + kATileBytes, row_bytes);
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kk | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (kk == k_iters - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue: two groups of four warps ================================
+    const int group = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int lx = m % p.tw;
+    const int ly = (m / p.tw) % p.th;
+    const int lz = m / (p.tw * p.th);
+    const int esz = p.out_dtype == 2 ? 4 : 2;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      if ((it & 1) != group) continue;
+      const int nt = t % p.n_tiles;
+      const int m_tile = t / p.n_tiles;
+      const int ox = (m_tile % p.tiles_x) * p.tw + lx;
+      const int oy = ((m_tile / p.tiles_x) % p.tiles_y) * p.th + ly;
+      const int on = (m_tile / tiles_xy) * p.tn + lz;
+      const bool valid = (lz < p.tn) && ox < p.Wo && oy < p.Ho && on < p.N;
+      int cls = 0;
+      if (p.bias_classes == 9) {
+        const int iy = oy * p.stride - p.pad, ix = ox * p.stride - p.pad;
+        const int cy = iy < 0 ? 0 : (iy + p.kh - 1 >= p.H ? 2 : 1);
+        const int cx = ix < 0 ? 0 : (ix + p.kw - 1 >= p.W ? 2 : 1);
+        cls = cy * 3 + cx;
+      }
+      const float* bias_row = p.bias + (size_t)cls * p.cout_p;
+      const size_t pix = ((size_t)on * p.Ho + oy) * p.Wo + ox;
+      size_t res_pix = pix;
+      if (p.res_mode == 2) {
+        const int ry = min(oy >> 1, p.res_h - 1), rx = min(ox >> 1, p.res_w - 1);
+        res_pix = ((size_t)on * p.res_h + ry) * p.res_w + rx;
+      }
+      const int acc = it % p.n_acc;
+      const uint32_t acc_phase = (uint32_t)(it / p.n_acc) & 1u;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+      const int cbase = nt * p.block_n;
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_addr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (valid) {
+          epilogue_store16(p, r, bias_row, cbase + c0, pix, res_pix, esz);
+          if (c0 + 16 < p.block_n) epilogue_store16(p, r + 16, bias_row, cbase + c0 + 16, pix, res_pix, esz);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host-side planning
 // ------------------------------------------------------------------------------------------
@@ -521,6 +734,39 @@ static int launch_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaParam
   B2F_CHECK_CUDA(attr_rc);
   B2F_REQUIRE(smem <= 227 * 1024, "umma kernel: %zu bytes of shared memory requested", smem);
   umma_conv_kernel<EPI><<<dim3(m_tiles, grid_y), 192, smem, stream>>>(tmA, tmB, p);
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
+
+int g_persistent = 1;
+int g_num_sms = 0;
+
+static int launch_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaParams& p, int m_tiles,
+                             cudaStream_t stream) {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    B2F_CHECK_CUDA(cudaGetDevice(&dev));
+    B2F_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int stage_bytes = kATileBytes + p.b_tile_bytes;
+  int stages = (g_smem_budget_loop - 2048) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  p.total_tiles = m_tiles * p.n_tiles;
+  p.acc_stride = (p.block_n + 31) & ~31;
+  p.n_acc = (512 / p.acc_stride) >= 4 ? 4 : 2;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  static std::once_flag once;
+  static cudaError_t attr_rc = cudaSuccess;
+  std::call_once(once, [] {
+    attr_rc = cudaFuncSetAttribute(umma_conv_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024);
+  });
+  B2F_CHECK_CUDA(attr_rc);
+  const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+  umma_conv_persistent_kernel<<<grid, kPersistThreads, smem, stream>>>(tmA, tmB, p);
   g_launches.fetch_add(1);
   B2F_LAUNCH_CHECK();
   return 0;
@@ -596,6 +842,7 @@ extern "C" int b2f_conv2d(const b2f_conv_desc* d, void* stream_) {
     if (rc) return rc;
   }
   const int m_tiles = p.tiles_x * p.tiles_y * tiles_z;
+  if (g_persistent) return launch_persistent(tmA, tmB, p, m_tiles, stream);
   return launch_umma<EPI_STORE>(tmA, tmB, p, m_tiles, p.n_tiles, stream);
 }
 

@@ -90,6 +90,12 @@ class Gallery:
         self.add(embeddings)
         self.idx_base = int(idx_base)
 
+    def replace_rows(self, rows: torch.Tensor, embeddings: torch.Tensor) -> None:
+        """Overwrite local rows (int64 indices into this shard) with new embeddings (upsert of existing ids)."""
+        f32, h16 = self._normalise(embeddings)
+        self.f32[rows] = f32
+        self.h16[rows] = h16
+
     def remove(self, row: int) -> None:
         keep = torch.ones(len(self), dtype=torch.bool, device=self.device)
         keep[row] = False
