@@ -117,6 +117,7 @@ typedef struct b2f_conv_desc {
   int res_mode;             /* 0 none, 1 same-size residual, 2 residual is a (res_h,res_w) map upsampled 2x nearest */
   int res_h, res_w;
   int force_kchunk;         /* 0 = auto (64/32/16) */
+  int sig_hi;               /* act == SIGMOID: apply to channels [0, sig_hi) only; 0 = all channels */
   const void* in;
   const void* weight;
   const float* bias;        /* [bias_classes][cout_p] */
@@ -130,6 +131,9 @@ int b2f_conv2d(const b2f_conv_desc* desc, void* stream);
 int b2f_stem_conv3x3(const void* in, int n, int h, int w, int cin_s /*stored channels*/, int stride,
                      const float* weight, const float* bias, const float* slope, int act, int cout_p,
                      int dtype, void* out, void* stream);
+/* 3x3 pad-1 patches of a 4-channel (RGB0) NHWC image -> [n][ho][wo][32] with k = tap*3 + channel (27 used):
+ * turns the first layer into a 1x1 convolution for the tensor-core kernel */
+int b2f_im2col3x3(const void* in, int n, int h, int w, int stride, int ho, int wo, int dtype, void* out, void* stream);
 /* depthwise kxk (+bias, activation). weight [k*k][c_p] f32 */
 int b2f_dwconv(const void* in, int n, int h, int w, int c_p, int k, int stride, int pad, const float* weight,
                const float* bias, const float* slope, int act, int dtype, void* out, void* stream);

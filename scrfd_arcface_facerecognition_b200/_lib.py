@@ -64,6 +64,7 @@ class ConvDesc(C.Structure):
                 ("kh", C.c_int), ("kw", C.c_int), ("stride", C.c_int), ("pad", C.c_int),
                 ("dtype", C.c_int), ("out_dtype", C.c_int), ("act", C.c_int), ("bias_classes", C.c_int),
                 ("res_mode", C.c_int), ("res_h", C.c_int), ("res_w", C.c_int), ("force_kchunk", C.c_int),
+                ("sig_hi", C.c_int),
                 ("in_", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p), ("slope", C.c_void_p),
                 ("residual", C.c_void_p), ("out", C.c_void_p)]
 
@@ -90,6 +91,7 @@ SIGNATURES = {
     "b2f_norm_crop": [_vp, _i, _i, _vp, _vp, _i, _i, _f, _f, _vp, _i, _i, _vp, _vp, _vp],
     "b2f_conv2d": [C.POINTER(ConvDesc), _vp],
     "b2f_stem_conv3x3": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "b2f_im2col3x3": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "b2f_dwconv": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp],
     "b2f_pool": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "b2f_eltwise": [_vp, _vp, _ll, _i, _vp, _vp, _vp, _i, _i, _vp, _vp],

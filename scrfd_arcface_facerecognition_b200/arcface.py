@@ -54,9 +54,7 @@ class ArcFace:
 
     # ------------------------------------------------------------------------------------------
     def _embed_loaded(self, n: int) -> torch.Tensor:
-        out = self._engine.run(n)[self.output_names[0]]
-        dim = self._engine.plan.outputs[0][2]
-        return out.reshape(n, -1)[:, :dim]
+        return self._engine.run(n)[self.output_names[0]].reshape(n, -1)
 
     def get_feat(self, images) -> np.ndarray:
         """(B,512) float32 embeddings of already-aligned uint8 BGR crops (reference models/arcface.py:39-52)."""

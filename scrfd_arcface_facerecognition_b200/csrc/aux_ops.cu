@@ -131,6 +131,41 @@ stem_conv_kernel(const uint16_t* __restrict__ in, int n, int h, int w, int strid
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// 3x3 pad-1 patch extraction for the first layer: [n][h][w][4] -> [n][ho][wo][32], k = tap*3 + channel
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+im2col3x3_kernel(const uint16_t* __restrict__ in, int n, int h, int w, int stride, int ho, int wo,
+                 uint16_t* __restrict__ out) {
+  const long long total = (long long)n * ho * wo;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(t % wo), oy = (int)((t / wo) % ho), b = (int)(t / ((long long)wo * ho));
+    uint16_t v[32];
+#pragma unroll
+    for (int i = 27; i < 32; ++i) v[i] = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = oy * stride + r - 1;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int ix = ox * stride + s - 1;
+        uint2 q = make_uint2(0u, 0u);
+        if (iy >= 0 && iy < h && ix >= 0 && ix < w)
+          q = __ldg(reinterpret_cast<const uint2*>(in + (((size_t)b * h + iy) * w + ix) * 4));
+        const int k = (r * 3 + s) * 3;
+        v[k] = (uint16_t)(q.x & 0xFFFF), v[k + 1] = (uint16_t)(q.x >> 16), v[k + 2] = (uint16_t)(q.y & 0xFFFF);
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + (size_t)t * 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      o[j] = make_uint4(v[8 * j] | ((uint32_t)v[8 * j + 1] << 16), v[8 * j + 2] | ((uint32_t)v[8 * j + 3] << 16),
+                        v[8 * j + 4] | ((uint32_t)v[8 * j + 5] << 16), v[8 * j + 6] | ((uint32_t)v[8 * j + 7] << 16));
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // depthwise k x k conv, 8 channels per thread
 // ------------------------------------------------------------------------------------------
@@ -423,6 +458,20 @@ extern "C" int b2f_stem_conv3x3(const void* in, int n, int h, int w, int cin_s, 
   stem_conv_kernel<<<grid_for(total, 256), 256, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint16_t*>(in), n, h, w, stride, ho, wo, weight, bias, slope, act, cout_p,
       dtype == B2F_BF16, reinterpret_cast<uint16_t*>(out));
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
+
+
+extern "C" int b2f_im2col3x3(const void* in, int n, int h, int w, int stride, int ho, int wo, int dtype, void* out,
+                             void* stream) {
+  (void)dtype;  // a pure 16-bit move: fp16 and bf16 are handled alike
+  B2F_REQUIRE(ho == (h + 2 - 3) / stride + 1 && wo == (w + 2 - 3) / stride + 1, "b2f_im2col3x3: output size mismatch");
+  const long long total = (long long)n * ho * wo;
+  if (total <= 0) return 0;
+  im2col3x3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint16_t*>(in), n, h, w, stride, ho, wo, reinterpret_cast<uint16_t*>(out));
   g_launches.fetch_add(1);
   B2F_LAUNCH_CHECK();
   return 0;

@@ -10,6 +10,7 @@ std::atomic<long long> g_launches{0};
 extern int g_smem_budget_single;
 extern int g_max_block_n;
 extern int g_persistent;
+extern int g_vhalo;
 }  // namespace b2f
 
 static thread_local char g_err[1024] = "";
@@ -38,6 +39,10 @@ extern "C" int b2f_set_tuning(int key, int value) {
   }
   if (key == 2) {
     b2f::g_persistent = value ? 1 : 0;
+    return 0;
+  }
+  if (key == 3) {
+    b2f::g_vhalo = value ? 1 : 0;
     return 0;
   }
   b2f_set_error("unknown tuning key %d", key);

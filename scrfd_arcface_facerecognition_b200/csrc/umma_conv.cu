@@ -94,6 +94,7 @@ struct UmmaParams {
   int n_per_cta;            // N tiles looped by one CTA (grid.y = ceil(n_tiles / n_per_cta))
   int stages, b_tile_bytes, tmem_cols;
   int total_tiles, n_acc, acc_stride;   // persistent kernel: tiles = M tiles x N tiles, TMEM accumulator ring
+  int a_stage_bytes, stages_a, stages_b, b_resident;   // vertical-halo kernel
   int is_bf16;
   // EPI_STORE
   void* out;
@@ -102,6 +103,7 @@ struct UmmaParams {
   int bias_classes;         // 1 or 9 (3x3 border classes: which taps fall inside the image)
   const float* slope;       // PReLU slope [cout_p] (act == 2)
   int act;                  // 0 none, 1 relu, 2 prelu, 3 sigmoid
+  int sig_hi;               // sigmoid only on channels [0, sig_hi); 0 = all
   const void* residual;     // same dtype as activations
   int res_mode;             // 0 none, 1 same-size, 2 nearest 2x upsample of a (res_h,res_w) map
   int res_h, res_w;
@@ -172,6 +174,22 @@ __device__ __forceinline__ void store16(void* p, int dtype, const float (&f)[16]
   uint4* q = reinterpret_cast<uint4*>(p);
   q[0] = make_uint4(w[0], w[1], w[2], w[3]);
   q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+
+// K-steps of one pipeline stage, fully unrolled (the issuing thread's instruction stream is the critical path
+// for narrow tiles: every extra instruction per tcgen05.mma shows up as tensor-pipe idle time)
+template <int KSTEPS>
+__device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t first_acc) {
+#pragma unroll
+  for (int k = 0; k < KSTEPS; ++k)
+    umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, k == 0 ? first_acc : 1u);
+}
+__device__ __forceinline__ void issue_stage_rt(int ksteps, uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc,
+                                               uint32_t first_acc) {
+  if (ksteps == 4) issue_stage<4>(d_tmem, da, db, idesc, first_acc);
+  else if (ksteps == 2) issue_stage<2>(d_tmem, da, db, idesc, first_acc);
+  else issue_stage<1>(d_tmem, da, db, idesc, first_acc);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -271,18 +289,15 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int kk = 0; kk < k_iters; ++kk) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        {
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-          const uint32_t b_addr = a_addr + kATileBytes;
           const uint64_t da = umma_smem_desc(a_addr, row_bytes);
-          const uint64_t db = umma_smem_desc(b_addr, row_bytes);
-          const int ksteps = p.kchunk >> 4;
-          for (int k = 0; k < ksteps; ++k) {
-            // advance 16 elements (32 B) along K inside the swizzle span: +2 in the (addr >> 4) field
-            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kk | k) != 0);
+          const uint64_t db = umma_smem_desc(a_addr + kATileBytes, row_bytes);
+          if (elect_one()) {
+            issue_stage_rt(p.kchunk >> 4, d_tmem, da, db, idesc, kk != 0);
+            umma_commit(&empty_bar[stage]);           // frees the smem slot when these MMAs retire
+            if (kk == k_iters - 1) umma_commit(&tfull_bar[acc]);
           }
-          umma_commit(&empty_bar[stage]);           // frees the smem slot when these MMAs retire
-          if (kk == k_iters - 1) umma_commit(&tfull_bar[acc]);
         }
         __syncwarp();
         if (++stage == p.stages) {
@@ -343,7 +358,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             if (p.act) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] = act_apply(f[i], p.act, p.act == 2 ? __ldg(p.slope + c + i) : 0.f);
+              for (int i = 0; i < 16; ++i)
+                if (p.act != 3 || p.sig_hi == 0 || c + i < p.sig_hi)
+                  f[i] = act_apply(f[i], p.act, p.act == 2 ? __ldg(p.slope + c + i) : 0.f);
             }
             store16(reinterpret_cast<uint8_t*>(p.out) + (pix * p.cout_p + c) * esz, p.out_dtype, f);
           }
@@ -474,14 +491,16 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 //   overlaps the MMAs of tile i+1 and barrier / TMEM set-up is paid once per SM instead of per tile.
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxAcc = 4;
-constexpr int kPersistThreads = 320;
+constexpr int kEpiGroups = 4;
+constexpr int kPersistThreads = 64 + kEpiGroups * 128;   // producer warp, MMA warp, 16 epilogue warps
+constexpr int kEpiSmemBytes = 24 * 1024;                 // bias table [<=9][cout_p] + slopes [cout_p], cout_p <= 512
 
-__device__ __forceinline__ void epilogue_store16(const UmmaParams& p, const uint32_t* r, const float* bias_row, int c,
-                                                 size_t pix, size_t res_pix, int esz) {
+__device__ __forceinline__ void epilogue_store16(const UmmaParams& p, const uint32_t* r, const float* bias_row,
+                                                 const float* s_slope, int c, size_t pix, size_t res_pix, int esz) {
   float f[16];
 #pragma unroll
   for (int v = 0; v < 4; ++v) {
-    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_row + c) + v);
+    const float4 b4 = *(reinterpret_cast<const float4*>(bias_row + c) + v);     // shared memory
     f[4 * v + 0] = __uint_as_float(r[4 * v + 0]) + b4.x;
     f[4 * v + 1] = __uint_as_float(r[4 * v + 1]) + b4.y;
     f[4 * v + 2] = __uint_as_float(r[4 * v + 2]) + b4.z;
@@ -499,7 +518,7 @@ __device__ __forceinline__ void epilogue_store16(const UmmaParams& p, const uint
   } else if (p.act == 2) {
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
-      const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.slope + c) + v);
+      const float4 s4 = *(reinterpret_cast<const float4*>(s_slope + c) + v);        // shared memory
       f[4 * v + 0] = f[4 * v + 0] >= 0.f ? f[4 * v + 0] : f[4 * v + 0] * s4.x;
       f[4 * v + 1] = f[4 * v + 1] >= 0.f ? f[4 * v + 1] : f[4 * v + 1] * s4.y;
       f[4 * v + 2] = f[4 * v + 2] >= 0.f ? f[4 * v + 2] : f[4 * v + 2] * s4.z;
@@ -507,9 +526,74 @@ __device__ __forceinline__ void epilogue_store16(const UmmaParams& p, const uint
     }
   } else if (p.act == 3) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = 1.f / (1.f + expf(-f[i]));
+    for (int i = 0; i < 16; ++i)
+      if (p.sig_hi == 0 || c + i < p.sig_hi) f[i] = 1.f / (1.f + expf(-f[i]));
   }
   store16(reinterpret_cast<uint8_t*>(p.out) + (pix * p.cout_p + c) * esz, p.out_dtype, f);
+}
+
+
+// epilogue of the persistent kernels: four groups of four warps.  With four TMEM accumulators each group owns
+// every fourth tile; with two (N > 128) a pair of groups shares a tile and splits its columns.  Bias table and
+// PReLU slopes are staged in shared memory once per CTA.  Each thread owns one output pixel (TMEM lane).
+__device__ __forceinline__ void persistent_epilogue(const UmmaParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
+                                                    uint64_t* tempty_bar, const float* s_bias, const float* s_slope,
+                                                    int warp, int lane) {
+  const int tiles_xy = p.tiles_x * p.tiles_y;
+  const int group = (warp - 2) >> 2;                 // 0..3
+  const int split = kEpiGroups / p.n_acc;            // groups per tile: 1 or 2
+  const int my_acc_slot = group / split;             // which tile residue (it % n_acc) this group serves
+  const int col_part = group % split;
+  const int q = warp & 3;
+  const int m = q * 32 + lane;
+  const int lx = m % p.tw;
+  const int ly = (m / p.tw) % p.th;
+  const int lz = m / (p.tw * p.th);
+  const int esz = p.out_dtype == 2 ? 4 : 2;
+  int it = 0;
+  for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    const int acc = it % p.n_acc;
+    if (acc != my_acc_slot) continue;
+    const int nt = t % p.n_tiles;
+    const int m_tile = t / p.n_tiles;
+    const int ox = (m_tile % p.tiles_x) * p.tw + lx;
+    const int oy = ((m_tile / p.tiles_x) % p.tiles_y) * p.th + ly;
+    const int on = (m_tile / tiles_xy) * p.tn + lz;
+    const bool valid = (lz < p.tn) && ox < p.Wo && oy < p.Ho && on < p.N;
+    int cls = 0;
+    if (p.bias_classes == 9) {
+      const int iy = oy * p.stride - p.pad, ix = ox * p.stride - p.pad;
+      const int cy = iy < 0 ? 0 : (iy + p.kh - 1 >= p.H ? 2 : 1);
+      const int cx = ix < 0 ? 0 : (ix + p.kw - 1 >= p.W ? 2 : 1);
+      cls = cy * 3 + cx;
+    }
+    const float* bias_row = s_bias + (size_t)cls * p.cout_p;
+    const size_t pix = ((size_t)on * p.Ho + oy) * p.Wo + ox;
+    size_t res_pix = pix;
+    if (p.res_mode == 2) {
+      const int ry = min(oy >> 1, p.res_h - 1), rx = min(ox >> 1, p.res_w - 1);
+      res_pix = ((size_t)on * p.res_h + ry) * p.res_w + rx;
+    }
+    const uint32_t acc_phase = (uint32_t)(it / p.n_acc) & 1u;
+    mbar_wait(&tfull_bar[acc], acc_phase);
+    tc_fence_after();
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+    const int cbase = nt * p.block_n;
+    const int c_begin = col_part * 128;                                   // split == 2 only when block_n > 128
+    const int c_end = split == 1 ? p.block_n : min(p.block_n, c_begin + 128);
+    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(t_addr + (uint32_t)c0, r);
+      tmem_ld_wait();
+      if (valid) {
+        epilogue_store16(p, r, bias_row, s_slope, cbase + c0, pix, res_pix, esz);
+        if (c0 + 16 < c_end) epilogue_store16(p, r + 16, bias_row, s_slope, cbase + c0 + 16, pix, res_pix, esz);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+  }
 }
 
 __global__ void __launch_bounds__(kPersistThreads, 1)
@@ -526,6 +610,7 @@ umma_conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   uint64_t* tfull_bar = bars + 2 * kMaxStages;
   uint64_t* tempty_bar = bars + 2 * kMaxStages + kMaxAcc;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kMaxAcc);
+  uint8_t* epi_smem = reinterpret_cast<uint8_t*>(bars) + 512;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -542,7 +627,7 @@ umma_conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     }
     for (int s = 0; s < kMaxAcc; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], 4 * (kEpiGroups / p.n_acc));
     }
     fence_barrier_init();
   }
@@ -550,6 +635,11 @@ umma_conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  // bias table and PReLU slopes -> shared memory (read by every epilogue thread for every tile)
+  float* s_bias = reinterpret_cast<float*>(epi_smem);
+  float* s_slope = s_bias + p.bias_classes * p.cout_p;
+  for (int i = threadIdx.x; i < p.bias_classes * p.cout_p; i += blockDim.x) s_bias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.cout_p; i += blockDim.x) s_slope[i] = p.act == 2 ? p.slope[i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -601,14 +691,15 @@ umma_conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       for (int kk = 0; kk < k_iters; ++kk) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        {
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
           const uint64_t da = umma_smem_desc(a_addr, row_bytes);
           const uint64_t db = umma_smem_desc(a_addr + kATileBytes, row_bytes);
-          for (int k = 0; k < ksteps; ++k)
-            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kk | k) != 0);
-          umma_commit(&empty_bar[stage]);
-          if (kk == k_iters - 1) umma_commit(&tfull_bar[acc]);
+          if (elect_one()) {
+            issue_stage_rt(ksteps, d_tmem, da, db, idesc, kk != 0);
+            umma_commit(&empty_bar[stage]);
+            if (kk == k_iters - 1) umma_commit(&tfull_bar[acc]);
+          }
         }
         __syncwarp();
         if (++stage == p.stages) {
@@ -618,56 +709,174 @@ umma_conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       }
     }
   } else {
-    // ================================ epilogue: two groups of four warps ================================
-    const int group = (warp - 2) >> 2;
-    const int q = warp & 3;
-    const int m = q * 32 + lane;
-    const int lx = m % p.tw;
-    const int ly = (m / p.tw) % p.th;
-    const int lz = m / (p.tw * p.th);
-    const int esz = p.out_dtype == 2 ? 4 : 2;
-    int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-      if ((it & 1) != group) continue;
-      const int nt = t % p.n_tiles;
-      const int m_tile = t / p.n_tiles;
-      const int ox = (m_tile % p.tiles_x) * p.tw + lx;
-      const int oy = ((m_tile / p.tiles_x) % p.tiles_y) * p.th + ly;
-      const int on = (m_tile / tiles_xy) * p.tn + lz;
-      const bool valid = (lz < p.tn) && ox < p.Wo && oy < p.Ho && on < p.N;
-      int cls = 0;
-      if (p.bias_classes == 9) {
-        const int iy = oy * p.stride - p.pad, ix = ox * p.stride - p.pad;
-        const int cy = iy < 0 ? 0 : (iy + p.kh - 1 >= p.H ? 2 : 1);
-        const int cx = ix < 0 ? 0 : (ix + p.kw - 1 >= p.W ? 2 : 1);
-        cls = cy * 3 + cx;
+    persistent_epilogue(p, tmem_base, tfull_bar, tempty_bar, s_bias, s_slope, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// persistent 3x3 / stride-1 kernel with vertical-halo reuse of the A operand and optional resident weights.
+//   For every input-channel chunk and horizontal tap s, ONE box of (th+2) x tw pixels is fetched; the three
+//   vertical taps r read it at row offsets r*tw (tw % 8 == 0 keeps every 8-row swizzle atom aligned, so the
+//   UMMA descriptor only changes its start address).  A traffic drops from 9 to 3*(th+2)/th tile loads.
+//   When all 9*cchunks weight tiles fit in shared memory they are loaded once per CTA (b_resident).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPersistThreads, 1)
+umma_conv_vhalo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const UmmaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+
+  uint8_t* a_ring = smem;
+  uint8_t* b_base = smem + p.stages_a * p.a_stage_bytes;
+  const int b_slots = p.b_resident ? 9 * p.cchunks : p.stages_b;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)b_slots * p.b_tile_bytes);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = bars + kMaxStages;
+  uint64_t* fullB = bars + 2 * kMaxStages;
+  uint64_t* emptyB = bars + 3 * kMaxStages;
+  uint64_t* tfull_bar = bars + 4 * kMaxStages;
+  uint64_t* tempty_bar = bars + 4 * kMaxStages + kMaxAcc;
+  uint64_t* bres_bar = bars + 4 * kMaxStages + 2 * kMaxAcc;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
+  uint8_t* epi_smem = reinterpret_cast<uint8_t*>(bars) + 512;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t row_bytes = p.kchunk * 2;
+  const int tiles_xy = p.tiles_x * p.tiles_y;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kMaxStages; ++s) {
+      mbar_init(&fullA[s], 1);
+      mbar_init(&emptyA[s], 1);
+      mbar_init(&fullB[s], 1);
+      mbar_init(&emptyB[s], 1);
+    }
+    for (int s = 0; s < kMaxAcc; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4 * (kEpiGroups / p.n_acc));
+    }
+    mbar_init(bres_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  // bias table and PReLU slopes -> shared memory (read by every epilogue thread for every tile)
+  float* s_bias = reinterpret_cast<float*>(epi_smem);
+  float* s_slope = s_bias + p.bias_classes * p.cout_p;
+  for (int i = threadIdx.x; i < p.bias_classes * p.cout_p; i += blockDim.x) s_bias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.cout_p; i += blockDim.x) s_slope[i] = p.act == 2 ? p.slope[i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      const uint32_t a_bytes = (uint32_t)((p.th + 2) * p.tw) * row_bytes;
+      const uint32_t b_bytes = (uint32_t)p.block_n * row_bytes;
+      if (p.b_resident) {
+        mbar_arrive_expect_tx(bres_bar, b_bytes * 9u * (uint32_t)p.cchunks);
+        for (int cc = 0; cc < p.cchunks; ++cc)
+          for (int s = 0; s < 3; ++s)
+            for (int r = 0; r < 3; ++r)
+              tma_load_3d(b_base + (size_t)((cc * 3 + s) * 3 + r) * p.b_tile_bytes, &tmB, bres_bar, cc * p.kchunk, 0,
+                          r * 3 + s);
       }
-      const float* bias_row = p.bias + (size_t)cls * p.cout_p;
-      const size_t pix = ((size_t)on * p.Ho + oy) * p.Wo + ox;
-      size_t res_pix = pix;
-      if (p.res_mode == 2) {
-        const int ry = min(oy >> 1, p.res_h - 1), rx = min(ox >> 1, p.res_w - 1);
-        res_pix = ((size_t)on * p.res_h + ry) * p.res_w + rx;
-      }
-      const int acc = it % p.n_acc;
-      const uint32_t acc_phase = (uint32_t)(it / p.n_acc) & 1u;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
-      const int cbase = nt * p.block_n;
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(t_addr + (uint32_t)c0, r);
-        tmem_ld_wait();
-        if (valid) {
-          epilogue_store16(p, r, bias_row, cbase + c0, pix, res_pix, esz);
-          if (c0 + 16 < p.block_n) epilogue_store16(p, r + 16, bias_row, cbase + c0 + 16, pix, res_pix, esz);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int nt = t % p.n_tiles;
+        const int m_tile = t / p.n_tiles;
+        const int x0 = (m_tile % p.tiles_x) * p.tw;
+        const int y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.th;
+        const int n0 = m_tile / tiles_xy;
+        for (int cc = 0; cc < p.cchunks; ++cc) {
+          for (int s = 0; s < 3; ++s) {
+            mbar_wait(&emptyA[sa], pa ^ 1);
+            mbar_arrive_expect_tx(&fullA[sa], a_bytes);
+            tma_load_4d(a_ring + (size_t)sa * p.a_stage_bytes, &tmA, &fullA[sa], cc * p.kchunk, x0 + s - 1, y0 - 1, n0);
+            if (++sa == p.stages_a) sa = 0, pa ^= 1;
+            if (!p.b_resident) {
+              for (int r = 0; r < 3; ++r) {
+                mbar_wait(&emptyB[sb], pb ^ 1);
+                mbar_arrive_expect_tx(&fullB[sb], b_bytes);
+                tma_load_3d(b_base + (size_t)sb * p.b_tile_bytes, &tmB, &fullB[sb], cc * p.kchunk, nt * p.block_n,
+                            r * 3 + s);
+                if (++sb == p.stages_b) sb = 0, pb ^= 1;
+              }
+            }
+          }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    const uint32_t idesc = umma_idesc(128, (uint32_t)p.block_n, (uint32_t)p.is_bf16);
+    const int ksteps = p.kchunk >> 4;
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    int it = 0;
+    if (p.b_resident) {
+      mbar_wait(bres_bar, 0);
+      tc_fence_after();
+    }
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const int acc = it % p.n_acc;
+      const uint32_t acc_phase = (uint32_t)(it / p.n_acc) & 1u;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+      uint32_t accumulate = 0;
+      for (int cc = 0; cc < p.cchunks; ++cc) {
+        for (int s = 0; s < 3; ++s) {
+          mbar_wait(&fullA[sa], pa);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(a_ring + (size_t)sa * p.a_stage_bytes);
+          for (int r = 0; r < 3; ++r) {
+            uint32_t b_addr;
+            if (p.b_resident) {
+              b_addr = smem_u32(b_base + (size_t)((cc * 3 + s) * 3 + r) * p.b_tile_bytes);
+            } else {
+              mbar_wait(&fullB[sb], pb);
+              tc_fence_after();
+              b_addr = smem_u32(b_base + (size_t)sb * p.b_tile_bytes);
+            }
+            {
+              const uint64_t da = umma_smem_desc(a_addr + (uint32_t)(r * p.tw) * row_bytes, row_bytes);
+              const uint64_t db = umma_smem_desc(b_addr, row_bytes);
+              if (elect_one()) {
+                issue_stage_rt(ksteps, d_tmem, da, db, idesc, accumulate);
+                if (!p.b_resident) umma_commit(&emptyB[sb]);
+              }
+              accumulate = 1;
+            }
+            if (!p.b_resident) {
+              if (++sb == p.stages_b) sb = 0, pb ^= 1;
+            }
+          }
+          if (elect_one()) umma_commit(&emptyA[sa]);
+          if (++sa == p.stages_a) sa = 0, pa ^= 1;
+        }
+      }
+      if (elect_one()) umma_commit(&tfull_bar[acc]);
+      __syncwarp();
+    }
+  } else {
+    persistent_epilogue(p, tmem_base, tfull_bar, tempty_bar, s_bias, s_slope, warp, lane);
   }
 
   tc_fence_before();
@@ -750,14 +959,17 @@ static int launch_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, Umm
     B2F_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int stage_bytes = kATileBytes + p.b_tile_bytes;
-  int stages = (g_smem_budget_loop - 2048) / stage_bytes;
+  int stages = (226 * 1024 - 1024 - 512 - kEpiSmemBytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   p.stages = stages;
   p.total_tiles = m_tiles * p.n_tiles;
   p.acc_stride = (p.block_n + 31) & ~31;
   p.n_acc = (512 / p.acc_stride) >= 4 ? 4 : 2;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  size_t smem = (size_t)stages * stage_bytes + 1024 + 512 + kEpiSmemBytes;
+  if (smem < 120 * 1024) smem = 120 * 1024;     // one CTA per SM: it owns all 512 TMEM columns
+  B2F_REQUIRE((size_t)(p.bias_classes + 1) * p.cout_p * 4 <= (size_t)kEpiSmemBytes,
+              "conv: bias table of %d x %d floats does not fit the epilogue staging area", p.bias_classes + 1, p.cout_p);
   static std::once_flag once;
   static cudaError_t attr_rc = cudaSuccess;
   std::call_once(once, [] {
@@ -767,6 +979,51 @@ static int launch_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, Umm
   B2F_CHECK_CUDA(attr_rc);
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   umma_conv_persistent_kernel<<<grid, kPersistThreads, smem, stream>>>(tmA, tmB, p);
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
+
+int g_vhalo = 1;
+
+static int launch_vhalo(const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaParams& p, int m_tiles,
+                        cudaStream_t stream) {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    B2F_CHECK_CUDA(cudaGetDevice(&dev));
+    B2F_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int row_bytes = p.kchunk * 2;
+  p.a_stage_bytes = (((p.th + 2) * p.tw * row_bytes) + 1023) & ~1023;
+  const int budget = 226 * 1024 - 1024 - 512 - kEpiSmemBytes;
+  int b_bytes_total;
+  if (p.b_resident) {
+    b_bytes_total = 9 * p.cchunks * p.b_tile_bytes;
+    p.stages_b = 0;
+  } else {
+    p.stages_b = 6;
+    while (p.stages_b > 3 && p.stages_b * p.b_tile_bytes > budget / 2) --p.stages_b;
+    b_bytes_total = p.stages_b * p.b_tile_bytes;
+  }
+  p.stages_a = (budget - b_bytes_total) / p.a_stage_bytes;
+  if (p.stages_a > kMaxStages) p.stages_a = kMaxStages;
+  B2F_REQUIRE(p.stages_a >= 2, "vhalo conv: not enough shared memory for two A stages");
+  p.total_tiles = m_tiles * p.n_tiles;
+  p.acc_stride = (p.block_n + 31) & ~31;
+  p.n_acc = (512 / p.acc_stride) >= 4 ? 4 : 2;
+  size_t smem = (size_t)p.stages_a * p.a_stage_bytes + b_bytes_total + 1024 + 512 + kEpiSmemBytes;
+  if (smem < 120 * 1024) smem = 120 * 1024;     // keep one CTA per SM: every CTA owns all 512 TMEM columns
+  B2F_REQUIRE((size_t)(p.bias_classes + 1) * p.cout_p * 4 <= (size_t)kEpiSmemBytes,
+              "conv: bias table of %d x %d floats does not fit the epilogue staging area", p.bias_classes + 1, p.cout_p);
+  static std::once_flag once;
+  static cudaError_t attr_rc = cudaSuccess;
+  std::call_once(once, [] {
+    attr_rc = cudaFuncSetAttribute(umma_conv_vhalo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  B2F_CHECK_CUDA(attr_rc);
+  B2F_REQUIRE(smem <= 227 * 1024, "vhalo conv: %zu bytes of shared memory requested", smem);
+  const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+  umma_conv_vhalo_kernel<<<grid, kPersistThreads, smem, stream>>>(tmA, tmB, p);
   g_launches.fetch_add(1);
   B2F_LAUNCH_CHECK();
   return 0;
@@ -819,13 +1076,52 @@ extern "C" int b2f_conv2d(const b2f_conv_desc* d, void* stream_) {
   p.is_bf16 = d->dtype == 1;
   p.out = d->out, p.out_dtype = d->out_dtype;
   p.bias = d->bias, p.bias_classes = d->bias_classes;
-  p.slope = d->slope, p.act = d->act;
+  p.slope = d->slope, p.act = d->act, p.sig_hi = d->sig_hi;
   B2F_REQUIRE(d->act != 2 || d->slope != nullptr, "b2f_conv2d: PReLU needs a slope vector");
   p.residual = d->residual, p.res_mode = d->residual ? d->res_mode : 0;
   p.res_h = d->res_h, p.res_w = d->res_w;
 
+  // ---- vertical-halo variant: 3x3 / stride 1 / pad 1 on maps wide enough for 8-pixel-aligned tiles ----------
+  bool vhalo = false;
+  if (g_persistent && g_vhalo && d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && Wo >= 8 && Ho >= 2) {
+    // per-tile time model (cycles): tensor pipe = N/2 per 128xNx16 MMA; L2->SM fabric ~37 B/clk/SM (measured:
+    // ~10.4 TB/s over 148 SMs on the 256-channel layers, which is what bounds them)
+    const double kFabric = 37.0;
+    const double row_b = p.kchunk * 2.0;
+    const double mma = 9.0 * p.cchunks * (p.kchunk / 16) * (p.block_n / 2.0);
+    const double def_tiles = (double)p.tiles_x * p.tiles_y * tiles_z * p.n_tiles;
+    const double def_bytes = 9.0 * p.cchunks * (p.tw * p.th * p.tn + p.block_n) * row_b;
+    const double def_time = def_tiles * (mma > def_bytes / kFabric ? mma : def_bytes / kFabric);
+    const bool can_res = p.n_tiles == 1 && 9 * p.cchunks * p.b_tile_bytes <= 100 * 1024;
+    double best = -1;
+    int btw = 0;
+    for (int tw = 8; tw <= 128; tw <<= 1) {
+      const int th = 128 / tw;
+      if (tw > ((Wo + 7) & ~7)) continue;
+      const double tiles = (double)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * d->n * p.n_tiles;
+      const double bytes = p.cchunks * (3.0 * (th + 2) * tw + (can_res ? 0.0 : 9.0 * p.block_n)) * row_b;
+      const double t = tiles * (mma > bytes / kFabric ? mma : bytes / kFabric);
+      if (best < 0 || t < best) best = t, btw = tw;
+    }
+    if (best >= 0 && best < 0.9 * def_time) {
+      vhalo = true;
+      p.tw = btw, p.th = 128 / btw, p.tn = 1;
+      p.tiles_x = (Wo + p.tw - 1) / p.tw;
+      p.tiles_y = (Ho + p.th - 1) / p.th;
+      p.b_resident = can_res ? 1 : 0;
+    }
+  }
+  const int tiles_z_final = vhalo ? d->n : tiles_z;
+
   CUtensorMap tmA, tmB;
-  {
+  if (vhalo) {
+    uint64_t dims[4] = {(uint64_t)d->cin_p, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
+    uint64_t str[3] = {(uint64_t)d->cin_p * 2, (uint64_t)d->w * d->cin_p * 2, (uint64_t)d->h * d->w * d->cin_p * 2};
+    uint32_t box[4] = {(uint32_t)p.kchunk, (uint32_t)p.tw, (uint32_t)(p.th + 2), 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    int rc = make_tmap(&tmA, d->in, 4, dims, str, box, es, p.kchunk * 2, p.is_bf16);
+    if (rc) return rc;
+  } else {
     uint64_t dims[4] = {(uint64_t)d->cin_p, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
     uint64_t str[3] = {(uint64_t)d->cin_p * 2, (uint64_t)d->w * d->cin_p * 2, (uint64_t)d->h * d->w * d->cin_p * 2};
     uint32_t box[4] = {(uint32_t)p.kchunk, (uint32_t)(p.tw * d->stride), (uint32_t)(p.th * d->stride), (uint32_t)p.tn};
@@ -841,7 +1137,8 @@ extern "C" int b2f_conv2d(const b2f_conv_desc* d, void* stream_) {
     int rc = make_tmap(&tmB, d->weight, 3, dims, str, box, es, p.kchunk * 2, p.is_bf16);
     if (rc) return rc;
   }
-  const int m_tiles = p.tiles_x * p.tiles_y * tiles_z;
+  const int m_tiles = p.tiles_x * p.tiles_y * tiles_z_final;
+  if (vhalo) return launch_vhalo(tmA, tmB, p, m_tiles, stream);
   if (g_persistent) return launch_persistent(tmA, tmB, p, m_tiles, stream);
   return launch_umma<EPI_STORE>(tmA, tmB, p, m_tiles, p.n_tiles, stream);
 }

@@ -69,7 +69,7 @@ class NetEngine:
             self._last_use[op.src] = i
             if op.residual:
                 self._last_use[op.residual] = i
-        self._out_tensors = {t for _, t, _ in plan.outputs}
+        self._out_tensors = {o[1] for o in plan.outputs}
 
     # ------------------------------------------------------------------------------------------
     def _bind(self, n: int):
@@ -122,6 +122,7 @@ class NetEngine:
             d.dtype = self.dtype
             d.out_dtype = F32 if spec_out.f32 else self.dtype
             d.act = op.act
+            d.sig_hi = a.get("sig_hi", 0)
             d.bias_classes = a["bias_classes"]
             d.res_mode = op.res_mode if res is not None else 0
             if res is not None:
@@ -133,6 +134,10 @@ class NetEngine:
             d.residual = _ptr(res)
             d.out = dst.data_ptr()
             return _Bound(lib.b2f_conv2d, (C.byref(d),), (d, src, dst, res))
+        if op.kind == "im2col":
+            return _Bound(lib.b2f_im2col3x3,
+                          (src.data_ptr(), n, a["h"], a["w"], a["stride"], a["ho"], a["wo"], self.dtype, dst.data_ptr()),
+                          (src, dst))
         if op.kind == "stem":
             return _Bound(lib.b2f_stem_conv3x3,
                           (src.data_ptr(), n, a["h"], a["w"], 4, a["stride"], w["weight"].data_ptr(),
@@ -162,7 +167,7 @@ class NetEngine:
         return self._bound[n][1][self.plan.input_name]
 
     def run(self, n: int, timings: Optional[list] = None) -> Dict[str, torch.Tensor]:
-        """Run the net on whatever `input_buffer(n)` holds; returns {graph output name: [n,H,W,Cp] fp32}.
+        """Run the net on whatever `input_buffer(n)` holds; returns {graph output name: [n,H,W,C] fp32 view}.
         `timings`, when given, receives (op index, kind, start event, end event) per launch (bench roofline)."""
         if n not in self._bound:
             self._bound[n] = self._bind(n)
@@ -178,7 +183,7 @@ class NetEngine:
             if timings is not None:
                 e1.record()
                 timings.append((i, self.plan.ops[i].kind, e0, e1))
-        return {name: tens[t] for name, t, _ in self.plan.outputs}
+        return {name: tens[t][..., off:off + c] for name, t, c, off in self.plan.outputs}
 
     def op_flops(self, i: int, n: int) -> int:
         op = self.plan.ops[i]

@@ -27,8 +27,13 @@ ACT_NONE, ACT_RELU, ACT_PRELU, ACT_SIGMOID = 0, 1, 2, 3
 _ACT = {"Relu": ACT_RELU, "PRelu": ACT_PRELU, "Sigmoid": ACT_SIGMOID}
 
 
-def pad16(c: int) -> int:
-    return (c + 15) // 16 * 16
+def pad_ch(c: int) -> int:
+    """Stored channel count: 16 for tiny tensors, else a multiple of 32 so the K pipeline never drops to
+    16-element (32-byte) chunks -- 28->32, 56->64, 80->96, 88->96, 224 stays."""
+    return 16 if c <= 16 else (c + 31) // 32 * 32
+
+
+pad16 = pad_ch      # historical name
 
 
 @dataclass
@@ -60,7 +65,7 @@ class Plan:
     in_hw: Tuple[int, int]
     ops: List[FusedOp]
     tensors: Dict[str, TensorSpec]
-    outputs: List[Tuple[str, str, int]]      # (graph output name, tensor name, channels used)
+    outputs: List[Tuple[str, str, int, int]]  # (graph output name, tensor name, channels used, channel offset)
 
     def conv_flops(self, n: int = 1) -> int:
         total = 0
@@ -125,7 +130,7 @@ def _infer_shapes(g: Graph, in_hw: Tuple[int, int]) -> Dict[str, Tuple[int, ...]
     return shapes
 
 
-def compile_graph(g: Graph, in_hw: Tuple[int, int]) -> Plan:
+def compile_graph(g: Graph, in_hw: Tuple[int, int], stem_im2col: bool = True, merge_heads: bool = True) -> Plan:
     nodes = g.nodes
     init = g.initializers
     shapes = _infer_shapes(g, in_hw)
@@ -379,6 +384,69 @@ def compile_graph(g: Graph, in_hw: Tuple[int, int]) -> Plan:
         else:
             raise NotImplementedError(f"ONNX op {t} ({n.name}) is not supported by the B200 engine")
 
+    out_names = {resolve(o.name) for o in g.outputs}
+    view: Dict[str, Tuple[str, int]] = {}          # output tensor -> (merged tensor, channel offset)
+    extra_specs: Dict[str, TensorSpec] = {}
+
+    # ---- first layer on the tensor cores: 3x3 patches -> 27(+5) channels, then a 1x1 convolution -------------
+    if stem_im2col:
+        new_ops: List[FusedOp] = []
+        for op in ops:
+            if op.kind != "stem":
+                new_ops.append(op)
+                continue
+            a = op.attrs
+            mid = op.dst + "__patches"
+            new_ops.append(FusedOp("im2col", op.src, mid, attrs=dict(h=a["h"], w=a["w"], ho=a["ho"], wo=a["wo"],
+                                                                     stride=a["stride"]), order=op.order))
+            extra_specs[mid] = TensorSpec(mid, 27, a["ho"], a["wo"], 32)
+            cout, cout_p = a["cout"], pad_ch(a["cout"])
+            wk = op.arrays["weight"]                                    # (9, 4, cout_p) fp32
+            w2 = np.zeros((1, cout_p, 32), np.float32)
+            w2[0, :, :27] = wk[:, :3, :].reshape(27, cout_p).T           # k = tap*3 + ci
+            arrays = dict(weight=w2, bias=op.arrays["bias"][None, :].copy())
+            if "slope" in op.arrays:
+                arrays["slope"] = op.arrays["slope"]
+            attrs = dict(cin=27, cout=cout, kh=1, kw=1, stride=1, pad=0, h=a["ho"], w=a["wo"], ho=a["ho"], wo=a["wo"],
+                         macs_per_image=a["macs_per_image"], bias_classes=1)
+            new_ops.append(FusedOp("conv", mid, op.dst, None, 0, op.act, attrs, arrays, op.order))
+        ops = new_ops
+
+    # ---- sibling head convolutions (same input, same geometry, all graph outputs) become one launch ----------
+    if merge_heads:
+        groups: Dict[Tuple, List[FusedOp]] = {}
+        for op in ops:
+            a = op.attrs
+            if op.kind == "conv" and op.dst in out_names and op.residual is None and a["bias_classes"] == 1 \
+                    and op.act in (ACT_NONE, ACT_SIGMOID):
+                groups.setdefault((op.src, a["kh"], a["kw"], a["stride"], a["pad"]), []).append(op)
+        for key, members in groups.items():
+            if len(members) < 2:
+                continue
+            members.sort(key=lambda o: (o.act != ACT_SIGMOID, o.order))   # sigmoid channels first
+            couts = [m.attrs["cout"] for m in members]
+            total = sum(couts)
+            cin = members[0].attrs["cin"]
+            cin_p = members[0].arrays["weight"].shape[2]
+            taps = members[0].arrays["weight"].shape[0]
+            wk = np.zeros((taps, pad_ch(total), cin_p), np.float32)
+            bias = np.zeros((1, pad_ch(total)), np.float32)
+            name = "+".join(m.dst for m in members)
+            off = 0
+            sig_hi = 0
+            for m_op, c in zip(members, couts):
+                wk[:, off:off + c, :] = m_op.arrays["weight"][:, :c, :]
+                bias[0, off:off + c] = m_op.arrays["bias"][0, :c]
+                view[m_op.dst] = (name, off)
+                if m_op.act == ACT_SIGMOID:
+                    sig_hi = off + c
+                off += c
+            a0 = dict(members[0].attrs)
+            a0.update(cout=total, macs_per_image=sum(m.attrs["macs_per_image"] for m in members), sig_hi=sig_hi)
+            merged = FusedOp("conv", members[0].src, name, None, 0, ACT_SIGMOID if sig_hi else ACT_NONE, a0,
+                             dict(weight=wk, bias=bias), min(m.order for m in members))
+            ops = [o for o in ops if o not in members] + [merged]
+
     # ---- topological order over fused ops ------------------------------------------------------------
     inp = g.real_inputs()[0].name
     produced_by = {op.dst: op for op in ops}
@@ -399,19 +467,26 @@ def compile_graph(g: Graph, in_hw: Tuple[int, int]) -> Plan:
             raise RuntimeError(f"graph compile: unresolved tensors {sorted(missing)[:5]}")
 
     # ---- tensor table ----------------------------------------------------------------------------------
-    out_tensors = {resolve(o.name) for o in g.outputs}
+    out_tensors = {view.get(t, (t, 0))[0] for t in out_names}
     tensors: Dict[str, TensorSpec] = {inp: TensorSpec(inp, 3, in_hw[0], in_hw[1], 4)}
     for op in ordered:
-        shp = shapes[op.dst]
-        if len(shp) == 1:
-            c, h, w = shp[0], 1, 1
+        if op.dst in extra_specs:
+            tensors[op.dst] = extra_specs[op.dst]
+            continue
+        a = op.attrs
+        if op.kind in ("conv", "dwconv", "stem"):
+            c, h, w = a["cout"], a["ho"], a["wo"]
+        elif op.kind == "pool":
+            c, h, w = a["c"], a["ho"], a["wo"]
         else:
-            c, h, w = shp
-        tensors[op.dst] = TensorSpec(op.dst, c, h, w, pad16(c), f32=op.dst in out_tensors)
+            c, h, w = a["c"], a["h"], a["w"]
+        tensors[op.dst] = TensorSpec(op.dst, c, h, w, pad_ch(c), f32=op.dst in out_tensors)
         if op.dst in out_tensors and op.kind != "conv":
             raise NotImplementedError("graph outputs must be produced by a tensor-core convolution / Gemm")
     outputs = []
     for o in g.outputs:
         tname = resolve(o.name)
-        outputs.append((o.name, tname, tensors[tname].c))
+        shp = shapes[tname]
+        base, off = view.get(tname, (tname, 0))
+        outputs.append((o.name, base, shp[0], off))
     return Plan(inp, in_hw, ordered, tensors, outputs)

@@ -113,7 +113,7 @@ class SCRFD:
         for i in range(3):
             s, b, k = (outs[self.output_names[i + j * self.fmc]] for j in range(3))
             lv.score[i], lv.bbox[i], lv.kps[i] = s.data_ptr(), b.data_ptr(), k.data_ptr()
-            lv.score_ps[i], lv.bbox_ps[i], lv.kps_ps[i] = s.shape[-1], b.shape[-1], k.shape[-1]
+            lv.score_ps[i], lv.bbox_ps[i], lv.kps_ps[i] = s.stride(-2), b.stride(-2), k.stride(-2)
         return lv
 
     def _total_anchors(self, h: int, w: int) -> int:

@@ -35,7 +35,12 @@ def run_plan(plan: Plan, x_nchw: np.ndarray, quantize=None):
         a = op.attrs
         x = env[op.src]
         slope = torch.from_numpy(op.arrays["slope"]) if "slope" in op.arrays else None
-        if op.kind in ("conv", "stem", "dwconv"):
+        if op.kind == "im2col":
+            n_, c_, h_, w_ = x.shape
+            cols = F.unfold(x, 3, padding=1, stride=a["stride"])                   # (N, C*9, L), channel-major
+            cols = cols.view(n_, c_, 9, a["ho"], a["wo"]).permute(0, 2, 1, 3, 4)     # -> tap-major: k = tap*3 + ci
+            y = cols.reshape(n_, 9 * c_, a["ho"], a["wo"])
+        elif op.kind in ("conv", "stem", "dwconv"):
             cout = a["cout"]
             if op.kind == "conv":
                 wk = op.arrays["weight"]                                   # (taps, cout_p, cin_p)
@@ -66,7 +71,10 @@ def run_plan(plan: Plan, x_nchw: np.ndarray, quantize=None):
                 if op.res_mode == 2:
                     r = r.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
                 y = y + r
-            y = _act(y, op.act, slope[:cout] if slope is not None else None)
+            if op.act == ACT_SIGMOID and a.get("sig_hi", 0):
+                y = torch.cat([torch.sigmoid(y[:, :a["sig_hi"]]), y[:, a["sig_hi"]:]], dim=1)
+            else:
+                y = _act(y, op.act, slope[:cout] if slope is not None else None)
         elif op.kind == "pool":
             if a["mode"] == 0:
                 y = F.max_pool2d(x, a["k"], a["stride"], a["pad"])
@@ -88,4 +96,4 @@ def run_plan(plan: Plan, x_nchw: np.ndarray, quantize=None):
         if y.dim() == 2:
             y = y.view(y.shape[0], -1, 1, 1)
         env[op.dst] = y if spec.f32 else qz(y)
-    return {name: env[t].permute(0, 2, 3, 1).contiguous().numpy() for name, t, c in plan.outputs}
+    return {name: env[t][:, off:off + c].permute(0, 2, 3, 1).contiguous().numpy() for name, t, c, off in plan.outputs}

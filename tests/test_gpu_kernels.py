@@ -217,6 +217,30 @@ def test_conv2d_epilogue_variants(lib):
     assert (got - ref).abs().max().item() <= 2e-3 * scale
 
 
+@pytest.mark.parametrize("case", [(2, 64, 64, 64, 64), (2, 48, 80, 96, 96), (1, 32, 32, 128, 128), (3, 24, 40, 32, 32),
+                                  (2, 56, 56, 64, 128), (2, 20, 20, 224, 224), (1, 33, 47, 64, 32)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_conv_kernel_variants_agree(lib, case):
+    """per-tile kernel, persistent kernel and vertical-halo kernel (resident / streamed weights) on 3x3 s1 convs"""
+    n, h, w, cin, cout = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = _q(torch.randn((n, cin, h, w), generator=g))
+    wt = _q(torch.randn((cout, cin, 3, 3), generator=g) * (2.0 / (cin * 9)) ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.1
+    res = _q(torch.randn((n, cout, h, w), generator=g))
+    ref = torch.relu(F.conv2d(x, wt, b, 1, 1) + res)
+    try:
+        for persistent, vhalo in ((0, 0), (1, 0), (1, 1)):
+            _lib.check(lib.b2f_set_tuning(2, persistent))
+            _lib.check(lib.b2f_set_tuning(3, vhalo))
+            out = run_conv(lib, x, wt, b, 1, 1, act=1, residual=res, res_mode=1, out_f32=True)
+            err = (out - ref).abs().max().item()
+            assert err <= 2e-3 * max(1.0, ref.abs().max().item()), f"persistent={persistent} vhalo={vhalo}: {err}"
+    finally:
+        _lib.check(lib.b2f_set_tuning(2, 1))
+        _lib.check(lib.b2f_set_tuning(3, 1))
+
+
 # =============================================================================================
 # CUDA-core layers
 # =============================================================================================
@@ -271,6 +295,19 @@ def test_depthwise_conv(lib, k, stride, pad):
     want = torch.relu(F.conv2d(x, wt, b, stride, pad, groups=c))
     got = out.float().cpu()[..., :c].permute(0, 3, 1, 2)
     assert (got - want).abs().max().item() <= 3e-3 * max(1.0, want.abs().max().item())
+
+
+def test_im2col3x3(lib):
+    g = torch.Generator().manual_seed(11)
+    for stride in (1, 2):
+        x = _q(torch.rand((2, 3, 21, 30), generator=g) * 2 - 1)
+        xin = _nhwc16(x, 4)
+        ho, wo = (21 + 2 - 3) // stride + 1, (30 + 2 - 3) // stride + 1
+        out = torch.empty((2, ho, wo, 32), dtype=torch.float16, device="cuda")
+        _lib.check(lib.b2f_im2col3x3(xin.data_ptr(), 2, 21, 30, stride, ho, wo, 0, out.data_ptr(), sp()))
+        cols = F.unfold(x, 3, padding=1, stride=stride).view(2, 3, 9, ho, wo).permute(0, 3, 4, 2, 1).reshape(2, ho, wo, 27)
+        got = out.float().cpu()
+        assert torch.equal(got[..., :27], cols) and (got[..., 27:] == 0).all()
 
 
 def test_pool_and_eltwise(lib):

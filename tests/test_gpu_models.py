@@ -53,12 +53,12 @@ def test_detector_heads_match_oracle(key, hw):
     frames = np.stack([inputs.frame(50, hw[0], hw[1]), inputs.smooth_frame(51, hw[0], hw[1])])
     eng, outs, ref = _engine_outputs(key, hw, frames, 127.5, 1 / 128)
     worst = {}
-    for name, tname, c in eng.plan.outputs:
-        got = outs[name][..., :c].reshape(2, -1, c).cpu().numpy()
+    for name, tname, c, off in eng.plan.outputs:
+        got = outs[name].reshape(2, -1, c).cpu().numpy()
         want = ref[name].reshape(2, got.shape[1], c)       # (2*H*W*2, k) -> per frame, per pixel, 2 anchors x k
         worst[name] = float(np.abs(got - want).max())
     print(key, {k: f"{v:.2e}" for k, v in worst.items()})
-    names = [n for n, _, _ in eng.plan.outputs]
+    names = [o[0] for o in eng.plan.outputs]
     # scores are probabilities; bbox / kps are in stride units (x8..32 px): fp16 activations vs fp32 oracle
     assert max(worst[n] for n in names[:3]) <= 2e-2
     assert max(worst[n] for n in names[3:]) <= 6e-2

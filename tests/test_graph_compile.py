@@ -22,7 +22,7 @@ def _check(key, hw, n=1, tol=2e-5):
     out = plan_sim.run_plan(plan, x)
     for name in tg.output_names:
         r = ref[name]
-        o = out[name][..., :plan.tensors[dict((a, b) for a, b, _ in plan.outputs)[name]].c]
+        o = out[name]
         np.testing.assert_allclose(o.reshape(r.shape), r, rtol=0, atol=tol * max(1.0, np.abs(r).max()))
     return plan
 
@@ -30,7 +30,8 @@ def _check(key, hw, n=1, tol=2e-5):
 def test_scrfd_500m_plan_matches_oracle():
     plan = _check("scrfd_500m", (160, 160))
     kinds = {o.kind for o in plan.ops}
-    assert kinds == {"stem", "conv", "dwconv"}
+    assert kinds == {"im2col", "conv", "dwconv"}
+    assert sum(o.attrs.get("sig_hi", 0) == 2 for o in plan.ops) == 3            # one merged head conv per level
 
 
 def test_scrfd_2p5g_plan_matches_oracle():
@@ -47,14 +48,27 @@ def test_arcface_mbf_plan_matches_oracle():
 def test_arcface_r50_plan_matches_oracle_and_uses_border_tables():
     plan = _check("arcface_r50", (112, 112), n=1)
     assert sum(o.attrs.get("bias_classes") == 9 for o in plan.ops) == 24        # one pre-BN per IBasicBlock
-    assert all(o.kind in ("conv", "stem") for o in plan.ops) and len(plan.ops) == 54
+    assert all(o.kind in ("conv", "im2col") for o in plan.ops) and len(plan.ops) == 55
     assert abs(plan.conv_flops() / 1e9 - 12.62) < 0.01                            # SURVEY 8d per-face figure
+
+
+def test_unfused_variants_still_match_oracle():
+    g = archs.build_arch("scrfd_500m")
+    x = restate.blob_from_bgr(inputs.frame(50, 96, 128)[None], 1 / 128, 127.5)
+    ref = TorchGraph(g).run(x)
+    plan = graph.compile_graph(g, (96, 128), stem_im2col=False, merge_heads=False)
+    assert {o.kind for o in plan.ops} == {"stem", "conv", "dwconv"}
+    out = plan_sim.run_plan(plan, x)
+    for name, r in ref.items():
+        np.testing.assert_allclose(out[name].reshape(r.shape), r, rtol=0, atol=2e-5 * max(1.0, np.abs(r).max()))
 
 
 def test_scrfd_10g_flops():
     plan = graph.compile_graph(archs.build_arch("scrfd_10g"), (640, 640))
+    assert [t.cp for t in plan.tensors.values() if t.c in (28, 56, 80, 88, 224)] and \
+        {t.c: t.cp for t in plan.tensors.values()}.get(80) == 96
     assert abs(plan.conv_flops() / 1e9 - 26.68) < 0.01                            # SURVEY 8d per-frame figure
-    assert [c for _, _, c in plan.outputs] == [2, 2, 2, 8, 8, 8, 20, 20, 20]
+    assert [o[2] for o in plan.outputs] == [2, 2, 2, 8, 8, 8, 20, 20, 20]
 
 
 def test_fp16_activations_keep_embedding_cosine():

@@ -8,8 +8,8 @@ groups=("$@")
 [ ${#groups[@]} -eq 0 ] && groups=(tma conv layers exact decode match models)
 declare -A sel=(
   [tma]="tests/test_gpu_kernels.py -k tma_box"
-  [conv]="tests/test_gpu_kernels.py -k conv2d"
-  [layers]="tests/test_gpu_kernels.py -k 'stem or depthwise or pool'"
+  [conv]="tests/test_gpu_kernels.py -k 'conv2d or conv_kernel_variants'"
+  [layers]="tests/test_gpu_kernels.py -k 'stem or depthwise or pool or im2col'"
   [exact]="tests/test_gpu_kernels.py -k 'letterbox or blob or warp'"
   [decode]="tests/test_gpu_kernels.py -k 'decode or forward_view'"
   [match]="tests/test_gpu_kernels.py -k 'l2norm or match or duplicate'"
