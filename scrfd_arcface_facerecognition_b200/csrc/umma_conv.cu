@@ -648,29 +648,34 @@ umma_conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)(p.tw * p.th * p.tn) * row_bytes + (uint32_t)p.block_n * row_bytes;
+      // every parameter the loop needs lives in a register: the single issuing thread is a critical path
+      const int tw = p.tw, th = p.th, tn = p.tn, tiles_x = p.tiles_x, tiles_y = p.tiles_y, n_tiles = p.n_tiles;
+      const int kh = p.kh, kw = p.kw, cchunks = p.cchunks, kchunk = p.kchunk, stride = p.stride, pad = p.pad;
+      const int block_n = p.block_n, stages = p.stages, total = p.total_tiles;
+      const uint32_t tx_bytes = (uint32_t)(tw * th * tn) * row_bytes + (uint32_t)block_n * row_bytes;
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int nt = t % p.n_tiles;
-        const int m_tile = t / p.n_tiles;
-        const int x0 = (m_tile % p.tiles_x) * p.tw;
-        const int y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.th;
-        const int n0 = (m_tile / tiles_xy) * p.tn;
-        for (int kk = 0; kk < k_iters; ++kk) {
-          const int tap = kk / p.cchunks;
-          const int cc = kk - tap * p.cchunks;
-          const int r = tap / p.kw;
-          const int s = tap - r * p.kw;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* a_dst = smem + stage * stage_bytes;
-          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-          tma_load_4d(a_dst, &tmA, &full_bar[stage], cc * p.kchunk, x0 * p.stride + s - p.pad,
-                      y0 * p.stride + r - p.pad, n0);
-          tma_load_3d(a_dst + kATileBytes, &tmB, &full_bar[stage], cc * p.kchunk, nt * p.block_n, tap);
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int nt = t % n_tiles;
+        const int m_tile = t / n_tiles;
+        const int x0 = (m_tile % tiles_x) * tw * stride - pad;
+        const int y0 = ((m_tile / tiles_x) % tiles_y) * th * stride - pad;
+        const int n0 = (m_tile / tiles_xy) * tn;
+        const int nrow = nt * block_n;
+        int tap = 0;
+        for (int r = 0; r < kh; ++r) {
+          for (int sx = 0; sx < kw; ++sx, ++tap) {
+            for (int cc = 0; cc < cchunks; ++cc) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* a_dst = smem + stage * stage_bytes;
+              mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+              tma_load_4d(a_dst, &tmA, &full_bar[stage], cc * kchunk, x0 + sx, y0 + r, n0);
+              tma_load_3d(a_dst + kATileBytes, &tmB, &full_bar[stage], cc * kchunk, nrow, tap);
+              if (++stage == stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
           }
         }
       }
@@ -678,34 +683,36 @@ umma_conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     const uint32_t idesc = umma_idesc(128, (uint32_t)p.block_n, (uint32_t)p.is_bf16);
-    const int ksteps = p.kchunk >> 4;
+    const int ksteps = p.kchunk >> 4, stages = p.stages, total = p.total_tiles, n_acc = p.n_acc;
+    const uint32_t acc_stride = (uint32_t)p.acc_stride;
+    const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem), row_bytes);
+    const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem) + kATileBytes, row_bytes);
+    const uint64_t stage_inc = (uint64_t)(stage_bytes >> 4);
     int stage = 0;
     uint32_t phase = 0;
-    int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-      const int acc = it % p.n_acc;
-      const uint32_t acc_phase = (uint32_t)(it / p.n_acc) & 1u;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
       for (int kk = 0; kk < k_iters; ++kk) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        {
-          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-          const uint64_t da = umma_smem_desc(a_addr, row_bytes);
-          const uint64_t db = umma_smem_desc(a_addr + kATileBytes, row_bytes);
-          if (elect_one()) {
-            issue_stage_rt(ksteps, d_tmem, da, db, idesc, kk != 0);
-            umma_commit(&empty_bar[stage]);
-            if (kk == k_iters - 1) umma_commit(&tfull_bar[acc]);
-          }
+        if (elect_one()) {
+          const uint64_t off = stage_inc * (uint64_t)stage;
+          issue_stage_rt(ksteps, d_tmem, a_desc0 + off, b_desc0 + off, idesc, kk != 0);
+          umma_commit(&empty_bar[stage]);
+          if (kk == k_iters - 1) umma_commit(&tfull_bar[acc]);
         }
-        __syncwarp();
-        if (++stage == p.stages) {
+        if (++stage == stages) {
           stage = 0;
           phase ^= 1;
         }
+      }
+      if (++acc == n_acc) {
+        acc = 0;
+        acc_phase ^= 1;
       }
     }
   } else {
@@ -786,37 +793,42 @@ umma_conv_vhalo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      const uint32_t a_bytes = (uint32_t)((p.th + 2) * p.tw) * row_bytes;
-      const uint32_t b_bytes = (uint32_t)p.block_n * row_bytes;
-      if (p.b_resident) {
-        mbar_arrive_expect_tx(bres_bar, b_bytes * 9u * (uint32_t)p.cchunks);
-        for (int cc = 0; cc < p.cchunks; ++cc)
-          for (int s = 0; s < 3; ++s)
-            for (int r = 0; r < 3; ++r)
-              tma_load_3d(b_base + (size_t)((cc * 3 + s) * 3 + r) * p.b_tile_bytes, &tmB, bres_bar, cc * p.kchunk, 0,
-                          r * 3 + s);
+      const int tw = p.tw, th = p.th, tiles_x = p.tiles_x, tiles_y = p.tiles_y, n_tiles = p.n_tiles;
+      const int cchunks = p.cchunks, kchunk = p.kchunk, block_n = p.block_n, total = p.total_tiles;
+      const int stages_a = p.stages_a, stages_b = p.stages_b, a_stage_bytes = p.a_stage_bytes;
+      const int b_tile_bytes = p.b_tile_bytes;
+      const bool resident = p.b_resident != 0;
+      const uint32_t a_bytes = (uint32_t)((th + 2) * tw) * row_bytes;
+      const uint32_t b_bytes = (uint32_t)block_n * row_bytes;
+      if (resident) {
+        mbar_arrive_expect_tx(bres_bar, b_bytes * 9u * (uint32_t)cchunks);
+        uint8_t* dst = b_base;
+        for (int cc = 0; cc < cchunks; ++cc)
+          for (int sx = 0; sx < 3; ++sx)
+            for (int r = 0; r < 3; ++r, dst += b_tile_bytes)
+              tma_load_3d(dst, &tmB, bres_bar, cc * kchunk, 0, r * 3 + sx);
       }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int nt = t % p.n_tiles;
-        const int m_tile = t / p.n_tiles;
-        const int x0 = (m_tile % p.tiles_x) * p.tw;
-        const int y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.th;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int nt = t % n_tiles;
+        const int m_tile = t / n_tiles;
+        const int x0 = (m_tile % tiles_x) * tw - 1;
+        const int y0 = ((m_tile / tiles_x) % tiles_y) * th - 1;
         const int n0 = m_tile / tiles_xy;
-        for (int cc = 0; cc < p.cchunks; ++cc) {
-          for (int s = 0; s < 3; ++s) {
+        const int nrow = nt * block_n;
+        for (int cc = 0; cc < cchunks; ++cc) {
+          for (int sx = 0; sx < 3; ++sx) {
             mbar_wait(&emptyA[sa], pa ^ 1);
             mbar_arrive_expect_tx(&fullA[sa], a_bytes);
-            tma_load_4d(a_ring + (size_t)sa * p.a_stage_bytes, &tmA, &fullA[sa], cc * p.kchunk, x0 + s - 1, y0 - 1, n0);
-            if (++sa == p.stages_a) sa = 0, pa ^= 1;
-            if (!p.b_resident) {
+            tma_load_4d(a_ring + (size_t)sa * a_stage_bytes, &tmA, &fullA[sa], cc * kchunk, x0 + sx, y0, n0);
+            if (++sa == stages_a) sa = 0, pa ^= 1;
+            if (!resident) {
               for (int r = 0; r < 3; ++r) {
                 mbar_wait(&emptyB[sb], pb ^ 1);
                 mbar_arrive_expect_tx(&fullB[sb], b_bytes);
-                tma_load_3d(b_base + (size_t)sb * p.b_tile_bytes, &tmB, &fullB[sb], cc * p.kchunk, nt * p.block_n,
-                            r * 3 + s);
-                if (++sb == p.stages_b) sb = 0, pb ^= 1;
+                tma_load_3d(b_base + (size_t)sb * b_tile_bytes, &tmB, &fullB[sb], cc * kchunk, nrow, r * 3 + sx);
+                if (++sb == stages_b) sb = 0, pb ^= 1;
               }
             }
           }
@@ -826,54 +838,62 @@ umma_conv_vhalo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     const uint32_t idesc = umma_idesc(128, (uint32_t)p.block_n, (uint32_t)p.is_bf16);
-    const int ksteps = p.kchunk >> 4;
+    const int ksteps = p.kchunk >> 4, total = p.total_tiles, n_acc = p.n_acc, groups = 3 * p.cchunks;
+    const int stages_a = p.stages_a, stages_b = p.stages_b;
+    const bool resident = p.b_resident != 0;
+    const uint32_t acc_stride = (uint32_t)p.acc_stride;
+    const uint64_t a_desc0 = umma_smem_desc(smem_u32(a_ring), row_bytes);
+    const uint64_t b_desc0 = umma_smem_desc(smem_u32(b_base), row_bytes);
+    const uint64_t a_inc = (uint64_t)(p.a_stage_bytes >> 4), b_inc = (uint64_t)(p.b_tile_bytes >> 4);
+    const uint64_t r_inc = (uint64_t)(((uint32_t)p.tw * row_bytes) >> 4);       // one tile row of the halo box
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
-    int it = 0;
-    if (p.b_resident) {
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    if (resident) {
       mbar_wait(bres_bar, 0);
       tc_fence_after();
     }
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-      const int acc = it % p.n_acc;
-      const uint32_t acc_phase = (uint32_t)(it / p.n_acc) & 1u;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
-      uint32_t accumulate = 0;
-      for (int cc = 0; cc < p.cchunks; ++cc) {
-        for (int s = 0; s < 3; ++s) {
-          mbar_wait(&fullA[sa], pa);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(a_ring + (size_t)sa * p.a_stage_bytes);
-          for (int r = 0; r < 3; ++r) {
-            uint32_t b_addr;
-            if (p.b_resident) {
-              b_addr = smem_u32(b_base + (size_t)((cc * 3 + s) * 3 + r) * p.b_tile_bytes);
-            } else {
-              mbar_wait(&fullB[sb], pb);
-              tc_fence_after();
-              b_addr = smem_u32(b_base + (size_t)sb * p.b_tile_bytes);
-            }
-            {
-              const uint64_t da = umma_smem_desc(a_addr + (uint32_t)(r * p.tw) * row_bytes, row_bytes);
-              const uint64_t db = umma_smem_desc(b_addr, row_bytes);
-              if (elect_one()) {
-                issue_stage_rt(ksteps, d_tmem, da, db, idesc, accumulate);
-                if (!p.b_resident) umma_commit(&emptyB[sb]);
-              }
-              accumulate = 1;
-            }
-            if (!p.b_resident) {
-              if (++sb == p.stages_b) sb = 0, pb ^= 1;
-            }
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
+      uint64_t bd = b_desc0;
+      for (int g = 0; g < groups; ++g) {                 // one (channel chunk, horizontal tap) group = one A box
+        mbar_wait(&fullA[sa], pa);
+        tc_fence_after();
+        const uint64_t ad = a_desc0 + a_inc * (uint64_t)sa;
+        if (resident) {
+          if (elect_one()) {
+            issue_stage_rt(ksteps, d_tmem, ad, bd, idesc, g != 0);
+            issue_stage_rt(ksteps, d_tmem, ad + r_inc, bd + b_inc, idesc, 1u);
+            issue_stage_rt(ksteps, d_tmem, ad + 2 * r_inc, bd + 2 * b_inc, idesc, 1u);
+            umma_commit(&emptyA[sa]);
+            if (g == groups - 1) umma_commit(&tfull_bar[acc]);
           }
-          if (elect_one()) umma_commit(&emptyA[sa]);
-          if (++sa == p.stages_a) sa = 0, pa ^= 1;
+          bd += 3 * b_inc;
+        } else {
+          for (int r = 0; r < 3; ++r) {
+            mbar_wait(&fullB[sb], pb);
+            tc_fence_after();
+            if (elect_one()) {
+              issue_stage_rt(ksteps, d_tmem, ad + r_inc * (uint64_t)r, b_desc0 + b_inc * (uint64_t)sb, idesc,
+                             (g | r) != 0);
+              umma_commit(&emptyB[sb]);
+              if (r == 2) {
+                umma_commit(&emptyA[sa]);
+                if (g == groups - 1) umma_commit(&tfull_bar[acc]);
+              }
+            }
+            if (++sb == stages_b) sb = 0, pb ^= 1;
+          }
         }
+        if (++sa == stages_a) sa = 0, pa ^= 1;
       }
-      if (elect_one()) umma_commit(&tfull_bar[acc]);
-      __syncwarp();
+      if (++acc == n_acc) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
     }
   } else {
     persistent_epilogue(p, tmem_base, tfull_bar, tempty_bar, s_bias, s_slope, warp, lane);
