@@ -157,7 +157,7 @@ int b2f_cosine_pairs(const float* a, const float* b, int pairs, int dim, float* 
 /* ---- a18 / a19: gallery matching -------------------------------------------------------------------
  * coarse pass: tcgen05 GEMM of queries x gallery^T with a running top-k epilogue (never materialises
  * Q x G); replaces the per-target Python loop at reference main.py:136-142 and the Qdrant scan behind
- * qdrant_manager.py:164-170.  part_* are [Q][n_splits][topk]. */
+ * qdrant_manager.py:164-170.  part_* are [Q][2*n_splits][topk] (each CTA reports its two column halves). */
 int b2f_match_partial(const void* queries, int q, const void* gallery, long long g, int dim, int dtype,
                       const float* row_scale, const float* col_scale, int topk, int n_splits,
                       float* part_score, int* part_idx, void* stream);

@@ -112,7 +112,7 @@ struct UmmaParams {
   long long n_valid;        // gallery rows
   const float* row_scale;   // per query (M) multiplier or null
   const float* col_scale;   // per gallery row (N) multiplier or null
-  float* part_score;        // [Q][gridDim.y][topk]
+  float* part_score;        // [Q][gridDim.y][2 column halves][topk]
   int* part_idx;
   // EPI_PAIRS (rows row_begin.. of the same matrix against all rows; only j > i is reported)
   int row_begin;
@@ -195,8 +195,10 @@ __device__ __forceinline__ void issue_stage_rt(int ksteps, uint32_t d_tmem, uint
 // ------------------------------------------------------------------------------------------
 // the kernel: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue
 // ------------------------------------------------------------------------------------------
+constexpr int kV1Threads = 64 + 2 * 128;   // producer warp, MMA warp, two epilogue groups of four warps
+
 template <int EPI>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kV1Threads, 1)
 umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const UmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -214,7 +216,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // tile coordinates
+  // tile coordinates: one M tile per CTA, a contiguous range of N tiles looped with two TMEM accumulators
   const int m_tile = blockIdx.x;
   const int tx = m_tile % p.tiles_x;
   const int ty = (m_tile / p.tiles_x) % p.tiles_y;
@@ -235,7 +237,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], 8);
     }
     fence_barrier_init();
   }
@@ -251,25 +253,26 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)(p.tw * p.th * p.tn) * row_bytes + (uint32_t)p.block_n * row_bytes;
+      const int kh = p.kh, kw = p.kw, cchunks = p.cchunks, kchunk = p.kchunk, block_n = p.block_n, stages = p.stages;
+      const int ax = x0 * p.stride - p.pad, ay = y0 * p.stride - p.pad;
+      const uint32_t tx_bytes = (uint32_t)(p.tw * p.th * p.tn) * row_bytes + (uint32_t)block_n * row_bytes;
       int stage = 0;
       uint32_t phase = 0;
       for (int nt = nt_begin; nt < nt_end; ++nt) {
-        for (int kk = 0; kk < k_iters; ++kk) {
-          const int tap = kk / p.cchunks;
-          const int cc = kk - tap * p.cchunks;
-          const int r = tap / p.kw;
-          const int s = tap - r * p.kw;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* a_dst = smem + stage * stage_bytes;
-          uint8_t* b_dst = a_dst + kATileBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-          tma_load_4d(a_dst, &tmA, &full_bar[stage], cc * p.kchunk, x0 * p.stride + s - p.pad,
-                      y0 * p.stride + r - p.pad, n0);
-          tma_load_3d(b_dst, &tmB, &full_bar[stage], cc * p.kchunk, nt * p.block_n, tap);
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
+        int tap = 0;
+        for (int r = 0; r < kh; ++r) {
+          for (int sx = 0; sx < kw; ++sx, ++tap) {
+            for (int cc = 0; cc < cchunks; ++cc) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* a_dst = smem + stage * stage_bytes;
+              mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+              tma_load_4d(a_dst, &tmA, &full_bar[stage], cc * kchunk, ax + sx, ay + r, n0);
+              tma_load_3d(a_dst + kATileBytes, &tmB, &full_bar[stage], cc * kchunk, nt * block_n, tap);
+              if (++stage == stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
           }
         }
       }
@@ -277,6 +280,11 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     const uint32_t idesc = umma_idesc(128, (uint32_t)p.block_n, (uint32_t)p.is_bf16);
+    const int ksteps = p.kchunk >> 4, stages = p.stages;
+    const uint32_t block_n = (uint32_t)p.block_n;
+    const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem), row_bytes);
+    const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem) + kATileBytes, row_bytes);
+    const uint64_t stage_inc = (uint64_t)(stage_bytes >> 4);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -285,36 +293,35 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * block_n;
       for (int kk = 0; kk < k_iters; ++kk) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        {
-          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-          const uint64_t da = umma_smem_desc(a_addr, row_bytes);
-          const uint64_t db = umma_smem_desc(a_addr + kATileBytes, row_bytes);
-          if (elect_one()) {
-            issue_stage_rt(p.kchunk >> 4, d_tmem, da, db, idesc, kk != 0);
-            umma_commit(&empty_bar[stage]);           // frees the smem slot when these MMAs retire
-            if (kk == k_iters - 1) umma_commit(&tfull_bar[acc]);
-          }
+        if (elect_one()) {
+          const uint64_t off = stage_inc * (uint64_t)stage;
+          issue_stage_rt(ksteps, d_tmem, a_desc0 + off, b_desc0 + off, idesc, kk != 0);
+          umma_commit(&empty_bar[stage]);           // frees the smem slot when these MMAs retire
+          if (kk == k_iters - 1) umma_commit(&tfull_bar[acc]);
         }
-        __syncwarp();
-        if (++stage == p.stages) {
+        if (++stage == stages) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
   } else {
-    // ================================ epilogue (4 warps) ================================
+    // ================================ epilogue: two groups of four warps split the columns ================
+    const int group = (warp - 2) >> 2;
     const int q = warp & 3;                       // TMEM lane quarter this warp may touch
-    const int m = q * 32 + lane;                  // accumulator row == output pixel within the tile
+    const int m = q * 32 + lane;                  // accumulator row == output pixel / query within the tile
     const int lx = m % p.tw;
     const int ly = (m / p.tw) % p.th;
     const int lz = m / (p.tw * p.th);
     const int ox = x0 + lx, oy = y0 + ly, on = n0 + lz;
     const bool valid = (lz < p.tn) && ox < p.Wo && oy < p.Ho && on < p.N;
+    const int half = ((p.block_n >> 1) + 15) & ~15;
+    const int c_begin = group == 0 ? 0 : half;
+    const int c_end = group == 0 ? half : p.block_n;
 
     if (EPI == EPI_STORE) {
       int cls = 0;
@@ -340,8 +347,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
         const int cbase = nt * p.block_n;
-        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
           uint32_t r[16];
+          __syncwarp();                               // the TMEM load is warp-collective: reconverge first
           tmem_ld16(t_addr + (uint32_t)c0, r);
           tmem_ld_wait();
           const int c = cbase + c0;
@@ -379,15 +387,20 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
         const long long cbase = (long long)nt * p.block_n;
-        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
           uint32_t r[16];
+          __syncwarp();                               // the TMEM load is warp-collective: reconverge first
           tmem_ld16(t_addr + (uint32_t)c0, r);
           tmem_ld_wait();
+          float mx = __uint_as_float(r[0]);
+#pragma unroll
+          for (int i = 1; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+          if (!(valid && mx >= p.thr_coarse)) continue;           // nothing in this chunk can pass
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const long long gj = cbase + c0 + i;
             const float v = __uint_as_float(r[i]);
-            if (valid && gj > gi && gj < p.n_valid && v >= p.thr_coarse) {
+            if (gj > gi && gj < p.n_valid && v >= p.thr_coarse) {
               bool hit = true;
               if (p.exact_rows) {
                 const float* a = p.exact_rows + (size_t)gi * p.exact_dim;
@@ -408,7 +421,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
     } else {
-      // running top-k over this CTA's slice of gallery rows; one query row per thread
+      // running top-k over this CTA's slice of gallery rows; one query row per thread and column half
       float best_s[kTopKMax];
       int best_i[kTopKMax];
 #pragma unroll
@@ -416,8 +429,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         best_s[t] = -INFINITY;
         best_i[t] = -1;
       }
+      const bool scaled = p.row_scale != nullptr || p.col_scale != nullptr;
       const float rsc = (valid && p.row_scale) ? __ldg(p.row_scale + on) : 1.f;
-      float worst = -INFINITY;   // current k-th best: most columns fail this test and skip the insertion
+      float worst = -INFINITY;   // current k-th best: most chunks fail one max test and skip the insertion
       int it = 0;
       for (int nt = nt_begin; nt < nt_end; ++nt, ++it) {
         const int acc = it & 1;
@@ -426,16 +440,28 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
         const long long cbase = (long long)nt * p.block_n;
-        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
           uint32_t r[16];
+          __syncwarp();                               // the TMEM load is warp-collective: reconverge first
           tmem_ld16(t_addr + (uint32_t)c0, r);
           tmem_ld_wait();
+          const long long g0 = cbase + c0;
+          const bool full_chunk = g0 + 16 <= p.n_valid;
+          if (full_chunk && !scaled) {
+            float mx = __uint_as_float(r[0]);
+#pragma unroll
+            for (int i = 1; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+            if (!(mx > worst)) continue;
+          }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const long long g = cbase + c0 + i;
-            if (g < p.n_valid) {
-              float v = __uint_as_float(r[i]) * rsc;
-              if (p.col_scale) v *= __ldg(p.col_scale + g);
+            const long long g = g0 + i;
+            if (full_chunk || g < p.n_valid) {
+              float v = __uint_as_float(r[i]);
+              if (scaled) {
+                v *= rsc;
+                if (p.col_scale) v *= __ldg(p.col_scale + g);
+              }
               if (v > worst) {
                 // insertion into the descending list; strict '>' keeps the lowest index among equals
                 float cs = v;
@@ -463,7 +489,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
       if (valid) {
-        const size_t o = ((size_t)on * gridDim.y + blockIdx.y) * p.topk;
+        const size_t o = (((size_t)on * gridDim.y + blockIdx.y) * 2 + group) * p.topk;
 #pragma unroll
         for (int t = 0; t < kTopKMax; ++t) {
           if (t < p.topk) {
@@ -482,7 +508,6 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
-
 
 // ------------------------------------------------------------------------------------------
 // persistent convolution kernel (EPI_STORE only): one CTA per SM loops over output tiles.
@@ -962,7 +987,7 @@ static int launch_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaParam
   });
   B2F_CHECK_CUDA(attr_rc);
   B2F_REQUIRE(smem <= 227 * 1024, "umma kernel: %zu bytes of shared memory requested", smem);
-  umma_conv_kernel<EPI><<<dim3(m_tiles, grid_y), 192, smem, stream>>>(tmA, tmB, p);
+  umma_conv_kernel<EPI><<<dim3(m_tiles, grid_y), kV1Threads, smem, stream>>>(tmA, tmB, p);
   g_launches.fetch_add(1);
   B2F_LAUNCH_CHECK();
   return 0;

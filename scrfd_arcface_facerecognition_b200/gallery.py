@@ -110,8 +110,8 @@ class Gallery:
         key = (q, splits)
         if key not in self._scratch:
             self._scratch[key] = dict(
-                ps=torch.empty((q, splits, KMAX), dtype=torch.float32, device=self.device),
-                pi=torch.empty((q, splits, KMAX), dtype=torch.int32, device=self.device),
+                ps=torch.empty((q, 2 * splits, KMAX), dtype=torch.float32, device=self.device),
+                pi=torch.empty((q, 2 * splits, KMAX), dtype=torch.int32, device=self.device),
                 os=torch.empty((q, KMAX), dtype=torch.float32, device=self.device),
                 oi=torch.empty((q, KMAX), dtype=torch.int64, device=self.device))
         return self._scratch[key]
@@ -135,7 +135,7 @@ class Gallery:
                                               None, KMAX, splits, sc["ps"].data_ptr(), sc["pi"].data_ptr(),
                                               stream_ptr()), "b2f_match_partial")
         thr = float(threshold) if np.isfinite(threshold) else -3.0e38
-        _lib.check(self.lib.b2f_match_merge(sc["ps"].data_ptr(), sc["pi"].data_ptr(), q, splits * KMAX,
+        _lib.check(self.lib.b2f_match_merge(sc["ps"].data_ptr(), sc["pi"].data_ptr(), q, 2 * splits * KMAX,
                                             qf.data_ptr(), self.f32.data_ptr(), self.dim, KMAX, thr,
                                             1 if strict else 0, self.idx_base, sc["os"].data_ptr(),
                                             sc["oi"].data_ptr(), stream_ptr()), "b2f_match_merge")
