@@ -189,6 +189,17 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t row_
   d |= layout << 61;
   return d;
 }
+// same, with an explicit stride between 8-row groups (rows inside a group stay `row_bytes` apart)
+__device__ __forceinline__ uint64_t umma_smem_desc_sbo(uint32_t saddr, uint32_t row_bytes, uint32_t sbo_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
 // instruction descriptor for kind::f16: fp32 accumulate, A/B K-major, M x N tile
 //   [4,6) c_format=1(F32) | [7,10) a_format | [10,13) b_format (0=F16, 1=BF16) | [17,23) N>>3 | [24,29) M>>4
 __device__ __forceinline__ uint32_t umma_idesc(uint32_t m, uint32_t n, uint32_t is_bf16) {

@@ -1,0 +1,782 @@
+// Persistent tcgen05 convolution kernel for sm_100a (the conv / FC layers of SCRFD and ArcFace; replaces the
+// ONNX Runtime Conv/BN/Relu/PRelu/Add/Gemm nodes behind reference models/scrfd.py:83 and models/arcface.py:51).
+//
+// One CTA per SM walks a list of work items.  Roles:
+//   warp 0      TMA producer (one thread): activation boxes into the A ring, weight tiles into the B ring
+//               (or all of them once, when they fit: "resident" weights)
+//   warp 1      tcgen05.mma issuer: M = 128 output pixels x N <= 256 output channels, fp32 accumulators in a ring
+//               of TMEM accumulators, so the epilogue of one tile overlaps the MMAs of the next ones
+//   warps 2..   epilogue groups of four warps (one TMEM lane quarter each), alternating tiles
+//
+// What bounds these layers on B200 is not the tensor pipe but (a) the L2 -> SM fabric (~40 B/clk/SM) when every
+// filter tap re-fetches its activation box and every tile re-fetches the weights, and (b) the LSU when 128
+// threads store 16-byte pieces 128+ bytes apart.  Hence:
+//   * A operand, three modes: one box per filter tap (any conv); one (th+2) x tw box per horizontal tap (3x3
+//     stride 1: the three vertical taps read it at row offsets); one (th+2) x (tw+2) box per channel chunk
+//     (tw == 8: all nine taps read it; the UMMA descriptor's 8-row group stride becomes one box row -- the
+//     hardware applies the 128B/64B/32B swizzle to absolute shared-memory address bits, so a tap is only a
+//     different start address)
+//   * B operand: resident, or streamed once per PAIR of M tiles (mt == 2: two accumulators share each weight tile)
+//   * epilogue: TMEM -> registers -> bias / residual / activation -> swizzled staging tile in shared memory ->
+//     one TMA tensor store per 16/32/64-channel slice (bounds clipping for free); the residual arrives through TMA
+//     into the same staging buffers two slices ahead
+#include "umma_shared.cuh"
+#include "../../include/b2f.h"
+
+#include <atomic>
+#include <stdlib.h>
+
+namespace b2f {
+
+extern std::atomic<long long> g_launches;
+extern int g_max_block_n;
+extern int g_debug;
+extern int g_vhalo;
+int g_tile_groups = 0;   // 0 = auto, else 2 or 4 epilogue groups
+int g_tile_mt = 0;       // 0 = auto, else 1 or 2 M tiles per weight tile
+int g_tile_amode = -1;   // -1 = auto, else force A mode 0 / 1 / 2 where legal
+int g_tile_epi = -1;     // -1 = auto, 0 = direct global stores, 1 = TMA stores
+
+constexpr int kTStages = 16;
+constexpr int kTAcc = 4;
+constexpr int kTGroups = 4;
+constexpr int kStgBufs = 3;
+constexpr int kSmemMax = 227 * 1024;
+
+struct TileParams {
+  int N, Ho, Wo, H, W, cout_p;
+  int kh, kw, stride, pad;
+  int cchunks, kchunk;
+  int tw, th, tn, tiles_x, tiles_y, m_tiles;
+  int block_n, n_tiles, items, mt;
+  int a_mode, boxes_per_chunk, taps_per_box;
+  int a_bytes, a_box_bytes, a_stage_bytes, stages_a;
+  int b_tile_bytes, stages_b, b_resident;
+  int n_acc_log2, acc_stride;
+  int groups;
+  int is_bf16, debug;
+  int epi_tma, res_smem, ochunk, n_sub, stg_bytes, stg_box_bytes;
+  void* out;
+  int out_dtype;
+  const float* bias;
+  int bias_classes;
+  const float* slope;
+  int act, sig_hi;
+  const void* residual;
+  int res_mode, res_h, res_w;
+  int off_b, off_stg, off_bar, off_tab;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX: TMA tensor store, bulk async groups, named barriers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_named(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, int is_bf16, float* f) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (is_bf16) {
+      __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      f[2 * i] = __bfloat162float(h.x);
+      f[2 * i + 1] = __bfloat162float(h.y);
+    } else {
+      __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      f[2 * i] = __half2float(h.x);
+      f[2 * i + 1] = __half2float(h.y);
+    }
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f, int is_bf16) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (is_bf16) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    } else {
+      __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// bias (+ residual) + activation on 16 accumulator columns; the caller decides where the result goes
+__device__ __forceinline__ void epi_math16(const TileParams& p, const uint32_t* r, const float* bias_row,
+                                           const float* s_slope, int c, const float* res, float* f) {
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const float4 b4 = *(reinterpret_cast<const float4*>(bias_row + c) + v);     // shared memory, broadcast
+    f[4 * v + 0] = __uint_as_float(r[4 * v + 0]) + b4.x;
+    f[4 * v + 1] = __uint_as_float(r[4 * v + 1]) + b4.y;
+    f[4 * v + 2] = __uint_as_float(r[4 * v + 2]) + b4.z;
+    f[4 * v + 3] = __uint_as_float(r[4 * v + 3]) + b4.w;
+  }
+  if (res) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] += res[i];
+  }
+  if (p.act == 1) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+  } else if (p.act == 2) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const float4 s4 = *(reinterpret_cast<const float4*>(s_slope + c) + v);
+      f[4 * v + 0] = fmaxf(f[4 * v + 0], 0.f) + s4.x * fminf(f[4 * v + 0], 0.f);
+      f[4 * v + 1] = fmaxf(f[4 * v + 1], 0.f) + s4.y * fminf(f[4 * v + 1], 0.f);
+      f[4 * v + 2] = fmaxf(f[4 * v + 2], 0.f) + s4.z * fminf(f[4 * v + 2], 0.f);
+      f[4 * v + 3] = fmaxf(f[4 * v + 3], 0.f) + s4.w * fminf(f[4 * v + 3], 0.f);
+    }
+  } else if (p.act == 3) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (p.sig_hi == 0 || c + i < p.sig_hi) f[i] = 1.f / (1.f + expf(-f[i]));
+  }
+}
+
+struct TileCoord {
+  int x0, y0, n0, cbase, m_tile;
+};
+
+__device__ __forceinline__ TileCoord tile_of(const TileParams& p, int seq) {
+  const int l = seq / p.mt, u = seq - l * p.mt;
+  const int i = blockIdx.x + l * gridDim.x;
+  const int nt = i % p.n_tiles, mp = i / p.n_tiles;
+  const int m_tile = mp * p.mt + u;
+  const int tiles_xy = p.tiles_x * p.tiles_y;
+  TileCoord t;
+  t.m_tile = m_tile;
+  t.x0 = (m_tile % p.tiles_x) * p.tw;
+  t.y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.th;
+  t.n0 = (m_tile / tiles_xy) * p.tn;
+  t.cbase = nt * p.block_n;
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------
+// MMA issue loop, specialised on (A mode, M tiles per weight tile, resident weights, K steps per stage) so the
+// nine-tap body is straight-line code: the issuing thread's instruction stream is the critical path of narrow
+// tiles (every extra instruction per tcgen05.mma is tensor-pipe idle time)
+// ------------------------------------------------------------------------------------------
+struct MmaCtx {
+  int items_cta;
+  uint32_t tmem_base, a_ring, b_base;
+  uint64_t *fullA, *emptyA, *fullB, *emptyB, *tfull, *tempty, *bres;
+};
+
+template <int MODE, int MT, bool RES, int KSTEPS>
+__device__ __forceinline__ void mma_issuer(const TileParams& p, const MmaCtx& c) {
+  constexpr int TPB = MODE == 0 ? 1 : (MODE == 1 ? 3 : 9);
+  const uint32_t row_bytes = p.kchunk * 2;
+  const uint32_t idesc = umma_idesc(128, (uint32_t)p.block_n, (uint32_t)p.is_bf16);
+  const int groups_per_item = p.cchunks * p.boxes_per_chunk;
+  const int stages_a = p.stages_a, stages_b = p.stages_b, items_cta = c.items_cta;
+  const int acc_mask = (1 << p.n_acc_log2) - 1, acc_log2 = p.n_acc_log2;
+  const uint32_t acc_stride = (uint32_t)p.acc_stride, tmem_base = c.tmem_base;
+  const int box_w = MODE == 2 ? p.tw + 2 : p.tw;
+  // mode 2: an 8-row group of the A tile = 8 consecutive pixels of one box row, groups one box row apart
+  const uint32_t sbo = MODE == 2 ? (uint32_t)box_w * row_bytes : 8u * row_bytes;
+  const uint64_t a_desc0 = umma_smem_desc_sbo(c.a_ring, row_bytes, sbo);
+  const uint64_t b_desc0 = umma_smem_desc(c.b_base, row_bytes);
+  const uint64_t a_inc = (uint64_t)(p.a_stage_bytes >> 4), b_inc = (uint64_t)(p.b_tile_bytes >> 4);
+  const uint64_t u_inc = (uint64_t)(p.a_box_bytes >> 4);
+  const uint64_t r_inc = (uint64_t)(((uint32_t)box_w * row_bytes) >> 4);       // one row of the box
+  const uint64_t s_inc = (uint64_t)(row_bytes >> 4);                             // one pixel
+  const bool do_mma = !(p.debug & 4);
+  uint64_t* const fullA = c.fullA;
+  uint64_t* const emptyA = c.emptyA;
+  uint64_t* const fullB = c.fullB;
+  uint64_t* const emptyB = c.emptyB;
+  uint64_t* const tfull = c.tfull;
+  uint64_t* const tempty = c.tempty;
+  int sa = 0, sb = 0;
+  uint32_t pa = 0, pb = 0;
+  if (RES) {
+    mbar_wait(c.bres, 0);
+    tc_fence_after();
+  }
+  int seq = 0;
+  for (int l = 0; l < items_cta; ++l, seq += MT) {
+    const int acc0 = seq & acc_mask, acc1 = (seq + 1) & acc_mask;
+    mbar_wait(&tempty[acc0], ((uint32_t)(seq >> acc_log2) & 1u) ^ 1u);
+    if (MT == 2) mbar_wait(&tempty[acc1], ((uint32_t)((seq + 1) >> acc_log2) & 1u) ^ 1u);
+    tc_fence_after();
+    const uint32_t d0 = tmem_base + (uint32_t)acc0 * acc_stride, d1 = tmem_base + (uint32_t)acc1 * acc_stride;
+    uint64_t bd = b_desc0;                               // resident weights: consumed in load order
+    for (int g = 0; g < groups_per_item; ++g) {
+      mbar_wait(&fullA[sa], pa);
+      tc_fence_after();
+      const uint64_t ad = a_desc0 + a_inc * (uint64_t)sa;
+      if (RES) {
+        if (elect_one()) {
+          if (do_mma) {
+#pragma unroll
+            for (int j = 0; j < TPB; ++j) {
+              const uint64_t aoff = MODE == 0 ? 0ull : (MODE == 1 ? r_inc * (uint64_t)j
+                                                                  : s_inc * (uint64_t)(j / 3) + r_inc * (uint64_t)(j % 3));
+              issue_stage<KSTEPS>(d0, ad + aoff, bd + b_inc * (uint64_t)j, idesc, j == 0 ? (uint32_t)(g != 0) : 1u);
+            }
+          }
+          umma_commit(&emptyA[sa]);
+          if (g == groups_per_item - 1) umma_commit(&tfull[acc0]);
+        }
+        bd += b_inc * (uint64_t)TPB;
+      } else {
+#pragma unroll
+        for (int j = 0; j < TPB; ++j) {
+          const uint64_t aoff = MODE == 0 ? 0ull : (MODE == 1 ? r_inc * (uint64_t)j
+                                                              : s_inc * (uint64_t)(j / 3) + r_inc * (uint64_t)(j % 3));
+          mbar_wait(&fullB[sb], pb);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t bdj = b_desc0 + b_inc * (uint64_t)sb;
+            const uint32_t accum = j == 0 ? (uint32_t)(g != 0) : 1u;
+            if (do_mma) {
+              issue_stage<KSTEPS>(d0, ad + aoff, bdj, idesc, accum);
+              if (MT == 2) issue_stage<KSTEPS>(d1, ad + aoff + u_inc, bdj, idesc, accum);
+            }
+            umma_commit(&emptyB[sb]);
+            if (j == TPB - 1) {
+              umma_commit(&emptyA[sa]);
+              if (g == groups_per_item - 1) {
+                umma_commit(&tfull[acc0]);
+                if (MT == 2) umma_commit(&tfull[acc1]);
+              }
+            }
+          }
+          if (++sb == stages_b) sb = 0, pb ^= 1;
+        }
+      }
+      if (++sa == stages_a) sa = 0, pa ^= 1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64 + 128 * kTGroups, 1)
+conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const TileParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+
+  uint8_t* a_ring = smem;
+  uint8_t* b_base = smem + p.off_b;
+  uint8_t* stg_base = smem + p.off_stg;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = bars + kTStages;
+  uint64_t* fullB = bars + 2 * kTStages;
+  uint64_t* emptyB = bars + 3 * kTStages;
+  uint64_t* tfull = bars + 4 * kTStages;
+  uint64_t* tempty = tfull + kTAcc;
+  uint64_t* bres = tempty + kTAcc;
+  uint64_t* rbar = bres + 1;                         // [kTGroups][kStgBufs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + kTGroups * kStgBufs);
+  float* s_bias = reinterpret_cast<float*>(smem + p.off_tab);
+  float* s_slope = s_bias + p.bias_classes * p.cout_p;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t row_bytes = p.kchunk * 2;
+  const int n_acc = 1 << p.n_acc_log2;
+  // work items of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...; each item = mt consecutive M tiles of one N tile
+  const int items_cta = (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tiles_cta = items_cta * p.mt;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.epi_tma) tma_prefetch_desc(&tmO);
+    if (p.res_smem) tma_prefetch_desc(&tmR);
+    for (int s = 0; s < kTStages; ++s) {
+      mbar_init(&fullA[s], 1);
+      mbar_init(&emptyA[s], 1);
+      mbar_init(&fullB[s], 1);
+      mbar_init(&emptyB[s], 1);
+    }
+    for (int s = 0; s < kTAcc; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 4);
+    }
+    mbar_init(bres, 1);
+    for (int s = 0; s < kTGroups * kStgBufs; ++s) mbar_init(&rbar[s], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < p.bias_classes * p.cout_p; i += blockDim.x) s_bias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.cout_p; i += blockDim.x) s_slope[i] = p.act == 2 ? p.slope[i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      const int mode = p.a_mode, mt = p.mt, n_tiles = p.n_tiles, cchunks = p.cchunks, kchunk = p.kchunk;
+      const int boxes = p.boxes_per_chunk, tpb = p.taps_per_box, kw = p.kw, block_n = p.block_n;
+      const int stages_a = p.stages_a, stages_b = p.stages_b;
+      const int a_stage_bytes = p.a_stage_bytes, a_box_bytes = p.a_box_bytes, b_tile_bytes = p.b_tile_bytes;
+      const int tiles_x = p.tiles_x, tiles_y = p.tiles_y, tiles_xy = tiles_x * tiles_y;
+      const int sx_scale = p.tw * p.stride, sy_scale = p.th * p.stride, org = mode == 0 ? p.pad : 1;
+      const bool resident = p.b_resident != 0;
+      const uint32_t a_tx = (uint32_t)(p.a_bytes * mt);
+      const uint32_t b_bytes = (uint32_t)block_n * row_bytes;
+      if (resident) {
+        mbar_arrive_expect_tx(bres, b_bytes * (uint32_t)(cchunks * boxes * tpb));
+        uint8_t* dst = b_base;
+        for (int cc = 0; cc < cchunks; ++cc)
+          for (int b = 0; b < boxes; ++b)
+            for (int j = 0; j < tpb; ++j, dst += b_tile_bytes) {
+              const int tap = mode == 0 ? b : (mode == 1 ? j * 3 + b : (j % 3) * 3 + j / 3);
+              tma_load_3d(dst, &tmB, bres, cc * kchunk, 0, tap);
+            }
+      }
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      // boxes of one channel chunk as a (dy, dx) grid, weight taps of one box as (sxi, r): no division per stage
+      const int nbx = mode == 0 ? kw : (mode == 1 ? 3 : 1), nby = mode == 0 ? p.kh : 1;
+      const int nsx = mode == 2 ? 3 : 1, nr = mode == 0 ? 1 : 3;
+      const bool skip_a = (p.debug & 8) != 0;
+      for (int i = blockIdx.x; i < p.items; i += gridDim.x) {
+        const int nt = i % n_tiles, mp = i / n_tiles;
+        const int nrow = nt * block_n;
+        const int m0 = mp * mt, m1 = m0 + 1;
+        const int ax0 = (m0 % tiles_x) * sx_scale - org, ay0 = ((m0 / tiles_x) % tiles_y) * sy_scale - org;
+        const int an0 = (m0 / tiles_xy) * p.tn;
+        const int ax1 = (m1 % tiles_x) * sx_scale - org, ay1 = ((m1 / tiles_x) % tiles_y) * sy_scale - org;
+        const int an1 = (m1 / tiles_xy) * p.tn;
+        for (int cc = 0; cc < cchunks; ++cc) {
+          const int c0 = cc * kchunk;
+          for (int dy = 0; dy < nby; ++dy) {
+            for (int dx = 0; dx < nbx; ++dx) {
+              mbar_wait(&emptyA[sa], pa ^ 1);
+              if (skip_a) {
+                mbar_arrive(&fullA[sa]);
+              } else {
+                mbar_arrive_expect_tx(&fullA[sa], a_tx);
+                uint8_t* dst = a_ring + (size_t)sa * a_stage_bytes;
+                tma_load_4d(dst, &tmA, &fullA[sa], c0, ax0 + dx, ay0 + dy, an0);
+                if (mt == 2) tma_load_4d(dst + a_box_bytes, &tmA, &fullA[sa], c0, ax1 + dx, ay1 + dy, an1);
+              }
+              if (++sa == stages_a) sa = 0, pa ^= 1;
+              if (!resident) {
+                for (int sxi = 0; sxi < nsx; ++sxi) {
+                  for (int r = 0; r < nr; ++r) {
+                    const int tap = mode == 0 ? dy * kw + dx : r * 3 + dx + sxi;
+                    mbar_wait(&emptyB[sb], pb ^ 1);
+                    mbar_arrive_expect_tx(&fullB[sb], b_bytes);
+                    tma_load_3d(b_base + (size_t)sb * b_tile_bytes, &tmB, &fullB[sb], c0, nrow, tap);
+                    if (++sb == stages_b) sb = 0, pb ^= 1;
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    MmaCtx c;
+    c.items_cta = items_cta;
+    c.tmem_base = tmem_base;
+    c.a_ring = smem_u32(a_ring), c.b_base = smem_u32(b_base);
+    c.fullA = fullA, c.emptyA = emptyA, c.fullB = fullB, c.emptyB = emptyB, c.tfull = tfull, c.tempty = tempty, c.bres = bres;
+    const int ks = p.kchunk >> 4;
+    const int variant = p.a_mode * 3 + (p.b_resident ? 0 : p.mt);     // (mode, {resident, streamed mt=1, streamed mt=2})
+#define B2F_MMA_CASE(MODE, V, MT, RES)                                         \
+    case MODE * 3 + V:                                                           \
+      if (ks == 4) mma_issuer<MODE, MT, RES, 4>(p, c);                           \
+      else if (ks == 2) mma_issuer<MODE, MT, RES, 2>(p, c);                      \
+      else mma_issuer<MODE, MT, RES, 1>(p, c);                                   \
+      break;
+    switch (variant) {
+      B2F_MMA_CASE(0, 0, 1, true)
+      B2F_MMA_CASE(0, 1, 1, false)
+      B2F_MMA_CASE(0, 2, 2, false)
+      B2F_MMA_CASE(1, 0, 1, true)
+      B2F_MMA_CASE(1, 1, 1, false)
+      B2F_MMA_CASE(1, 2, 2, false)
+      B2F_MMA_CASE(2, 0, 1, true)
+      B2F_MMA_CASE(2, 1, 1, false)
+      B2F_MMA_CASE(2, 2, 2, false)
+      default: break;
+    }
+#undef B2F_MMA_CASE
+  } else if (warp < 2 + 4 * p.groups) {
+    // ================================ epilogue ================================
+    const int group = (warp - 2) >> 2;
+    const int q = warp & 3;                          // TMEM lane quarter this warp may read
+    const int m = q * 32 + lane;                     // accumulator row == pixel of the tile
+    const int lx = m % p.tw;
+    const int ly = (m / p.tw) % p.th;
+    const int lz = m / (p.tw * p.th);
+    const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
+    const int G = p.groups;
+
+    if (p.epi_tma) {
+      const int n_sub = p.n_sub, och = p.ochunk;
+      const uint32_t orow = (uint32_t)och * 2;                           // staging row bytes: 64 / 32
+      const uint32_t swz_mask = orow == 64 ? 3u : 1u;
+      uint8_t* stg = stg_base + (size_t)group * kStgBufs * p.stg_bytes;
+      uint64_t* my_rbar = rbar + group * kStgBufs;
+      const int my_tiles = tiles_cta > group ? (tiles_cta - group + G - 1) / G : 0;
+      const int total_sub = my_tiles * n_sub;
+      const uint32_t row_off = (uint32_t)m * orow;
+      auto issue_res = [&](int s) {                                      // leader only: residual slice of sub s
+        const TileCoord t = tile_of(p, group + (s / n_sub) * G);
+        const int buf = s % kStgBufs;
+        mbar_arrive_expect_tx(&my_rbar[buf], (uint32_t)p.stg_box_bytes);
+        tma_load_4d(stg + (size_t)buf * p.stg_bytes, &tmR, &my_rbar[buf], t.cbase + (s % n_sub) * och, t.x0, t.y0, t.n0);
+      };
+      if (leader && p.res_smem)
+        for (int s = 0; s < kStgBufs - 1 && s < total_sub; ++s) issue_res(s);
+      int k = 0;
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        const int seq = group + tl * G;
+        const TileCoord t = tile_of(p, seq);
+        const int ox = t.x0 + lx, oy = t.y0 + ly;
+        int cls = 0;
+        if (p.bias_classes == 9) {
+          const int iy = oy * p.stride - p.pad, ix = ox * p.stride - p.pad;
+          const int cy = iy < 0 ? 0 : (iy + p.kh - 1 >= p.H ? 2 : 1);
+          const int cx = ix < 0 ? 0 : (ix + p.kw - 1 >= p.W ? 2 : 1);
+          cls = cy * 3 + cx;
+        }
+        const float* bias_row = s_bias + cls * p.cout_p;
+        const int acc = seq & (n_acc - 1);
+        const uint32_t ph = (uint32_t)(seq >> p.n_acc_log2) & 1u;
+        mbar_wait(&tfull[acc], ph);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+        for (int j = 0; j < n_sub; ++j, ++k) {
+          const int buf = k % kStgBufs;
+          uint8_t* bufp = stg + (size_t)buf * p.stg_bytes;
+          if (leader) {
+            bulk_wait_read0();                               // the store issued one slice ago has left its buffer
+            if (p.res_smem && k + kStgBufs - 1 < total_sub) issue_res(k + kStgBufs - 1);
+          }
+          uint32_t r[32];
+          if (och == 16) {
+            uint32_t r16[16];
+            tmem_ld16(t_addr + (uint32_t)(j * och), r16);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = r16[i];
+          } else {
+            tmem_ld32(t_addr + (uint32_t)(j * och), r);
+            tmem_ld_wait();
+          }
+          if (j == n_sub - 1) {                              // accumulator fully read: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          if (p.res_smem) mbar_wait(&my_rbar[buf], (uint32_t)(k / kStgBufs) & 1u);
+          if (!(p.debug & 16)) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (h * 16 < och) {
+                const uint32_t o0 = row_off + (uint32_t)h * 32, o1 = o0 + 16;
+                uint4* p0 = reinterpret_cast<uint4*>(bufp + (o0 ^ (((o0 >> 7) & swz_mask) << 4)));
+                uint4* p1 = reinterpret_cast<uint4*>(bufp + (o1 ^ (((o1 >> 7) & swz_mask) << 4)));
+                float rs[16], f[16];
+                if (p.res_smem) {
+                  unpack8(*p0, p.is_bf16, rs);
+                  unpack8(*p1, p.is_bf16, rs + 8);
+                }
+                epi_math16(p, r + h * 16, bias_row, s_slope, t.cbase + j * och + h * 16, p.res_smem ? rs : nullptr, f);
+                *p0 = pack8(f, p.out_dtype == 1);
+                *p1 = pack8(f + 8, p.out_dtype == 1);
+              }
+            }
+          }
+          fence_proxy_async();
+          bar_sync_named(1 + group, 128);
+          if (leader && !(p.debug & 1)) {
+            tma_store_4d(&tmO, bufp, t.cbase + j * och, t.x0, t.y0, t.n0);
+            bulk_commit();
+          }
+        }
+      }
+      if (leader) bulk_wait_all();
+    } else {
+      // direct stores (fp32 outputs, up-sampled residual): each thread writes its pixel's channels
+      const int esz = p.out_dtype == 2 ? 4 : 2;
+      for (int seq = group; seq < tiles_cta; seq += G) {
+        const TileCoord t = tile_of(p, seq);
+        const int ox = t.x0 + lx, oy = t.y0 + ly, on = t.n0 + lz;
+        const bool valid = (lz < p.tn) && ox < p.Wo && oy < p.Ho && on < p.N;
+        int cls = 0;
+        if (p.bias_classes == 9) {
+          const int iy = oy * p.stride - p.pad, ix = ox * p.stride - p.pad;
+          const int cy = iy < 0 ? 0 : (iy + p.kh - 1 >= p.H ? 2 : 1);
+          const int cx = ix < 0 ? 0 : (ix + p.kw - 1 >= p.W ? 2 : 1);
+          cls = cy * 3 + cx;
+        }
+        const float* bias_row = s_bias + cls * p.cout_p;
+        const size_t pix = ((size_t)on * p.Ho + oy) * p.Wo + ox;
+        size_t res_pix = pix;
+        if (p.res_mode == 2) {
+          const int ry = min(oy >> 1, p.res_h - 1), rx = min(ox >> 1, p.res_w - 1);
+          res_pix = ((size_t)on * p.res_h + ry) * p.res_w + rx;
+        }
+        const int acc = seq & (n_acc - 1);
+        const uint32_t ph = (uint32_t)(seq >> p.n_acc_log2) & 1u;
+        mbar_wait(&tfull[acc], ph);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+        for (int c0 = 0; c0 < p.block_n && !(p.debug & 16); c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_addr + (uint32_t)c0, r);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (c0 + h * 16 < p.block_n) {
+                const int c = t.cbase + c0 + h * 16;
+                float rs[16], f[16];
+                if (p.res_mode)
+                  load16_as_float(reinterpret_cast<const uint8_t*>(p.residual) + (res_pix * p.cout_p + c) * 2, p.is_bf16, rs);
+                epi_math16(p, r + h * 16, bias_row, s_slope, c, p.res_mode ? rs : nullptr, f);
+                if (!(p.debug & 1))
+                  store16(reinterpret_cast<uint8_t*>(p.out) + (pix * p.cout_p + c) * esz, p.out_dtype, f);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host: plan + launch
+// ------------------------------------------------------------------------------------------
+static int g_sms = 0;
+
+static inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+void pick_m_tile(int N, int Ho, int Wo, int stride, int* tw, int* th, int* tn);   // umma_conv.cu
+
+struct TilePlan {
+  int mode, tw, th, tn, mt, groups, resident, stages_a, stages_b;
+  double cost;
+};
+
+int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream) {
+  if (g_sms == 0) {
+    int dev = 0;
+    B2F_CHECK_CUDA(cudaGetDevice(&dev));
+    B2F_CHECK_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int Ho = d->ho, Wo = d->wo;
+  TileParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->n, p.Ho = Ho, p.Wo = Wo, p.H = d->h, p.W = d->w, p.cout_p = d->cout_p;
+  p.kh = d->kh, p.kw = d->kw, p.stride = d->stride, p.pad = d->pad;
+  p.kchunk = kchunk, p.cchunks = d->cin_p / kchunk;
+  const int row_bytes = kchunk * 2, ksteps = kchunk / 16, taps = d->kh * d->kw;
+  int n_tiles = (d->cout_p + g_max_block_n - 1) / g_max_block_n;
+  while ((d->cout_p % n_tiles) != 0 || ((d->cout_p / n_tiles) % 16) != 0) ++n_tiles;
+  p.n_tiles = n_tiles;
+  p.block_n = d->cout_p / n_tiles;
+  p.b_tile_bytes = round_up(p.block_n * row_bytes, 1024);
+  p.acc_stride = round_up(p.block_n, 32);
+  p.n_acc_log2 = p.acc_stride <= 128 ? 2 : 1;
+  p.is_bf16 = d->dtype == 1;
+  p.debug = g_debug;
+  p.out = d->out, p.out_dtype = d->out_dtype;
+  p.bias = d->bias, p.bias_classes = d->bias_classes;
+  p.slope = d->slope, p.act = d->act, p.sig_hi = d->sig_hi;
+  p.residual = d->residual, p.res_mode = d->residual ? d->res_mode : 0;
+  p.res_h = d->res_h, p.res_w = d->res_w;
+
+  // ---- epilogue flavour -------------------------------------------------------------------------------
+  // wide tiles (N > 128) keep every byte of shared memory for the operand rings: their epilogue hides behind the MMAs
+  p.epi_tma = (d->out_dtype != 2 && p.res_mode != 2 && (p.block_n <= 128 || g_tile_epi == 1)) ? 1 : 0;
+  if (g_tile_epi >= 0) p.epi_tma = p.epi_tma && g_tile_epi;
+  if (p.epi_tma) {
+    p.ochunk = (p.block_n % 32 == 0) ? 32 : 16;
+    p.n_sub = p.block_n / p.ochunk;
+    p.stg_bytes = round_up(128 * p.ochunk * 2, 1024);
+    p.res_smem = p.res_mode == 1 ? 1 : 0;
+  }
+  const int tab_bytes = round_up((p.bias_classes + 1) * p.cout_p * 4, 256);
+  const int fixed = 1024 /*align*/ + 1024 /*barriers*/ + tab_bytes;
+
+  // ---- choose A mode, tile geometry, weight sharing and epilogue groups with a per-tile cycle model -----------
+  const double kFabric = 40.0;                               // L2 -> SM bytes per clock per SM (measured ~37-42)
+  const double mma_tap = ksteps * ((p.block_n / 2.0) > ((128 + p.block_n) / 4.0) ? (p.block_n / 2.0) : ((128 + p.block_n) / 4.0));
+  const bool halo_ok = g_vhalo && d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1;
+  const int b_all = taps * p.cchunks * p.b_tile_bytes;
+  TilePlan best;
+  best.cost = -1;
+  for (int relax = 0; relax < 2 && best.cost < 0; ++relax) {      // forced knobs that cannot fit are dropped
+  const int f_groups = relax ? 0 : g_tile_groups, f_mt = relax ? 0 : g_tile_mt;
+  for (int mode = 0; mode <= (halo_ok ? 2 : 0); ++mode) {
+    if (g_tile_amode >= 0 && halo_ok && mode != g_tile_amode) continue;
+    for (int tw = (mode == 0 ? 0 : 8); tw <= (mode == 1 ? 128 : (mode == 2 ? 8 : 0)); tw = tw ? tw * 2 : 1) {
+      int gw, gh, gn;
+      if (mode == 0) pick_m_tile(d->n, Ho, Wo, d->stride, &gw, &gh, &gn);
+      else gw = tw, gh = 128 / tw, gn = 1;
+      if (mode == 1 && gw > round_up(Wo, 8)) break;
+      const long long m_tiles = (long long)((Wo + gw - 1) / gw) * ((Ho + gh - 1) / gh) * ((d->n + gn - 1) / gn);
+      const int boxes = mode == 0 ? taps : (mode == 1 ? 3 : 1);
+      const int a_bytes = (mode == 0 ? gw * gh * gn : (mode == 1 ? gw * (gh + 2) : (gw + 2) * (gh + 2))) * row_bytes;
+      const int a_box = round_up(a_bytes, 1024);
+      for (int mt = 1; mt <= 2; ++mt) {
+        const int resident = (mt == 1 && n_tiles == 1 && b_all <= 100 * 1024) ? 1 : 0;   // sharing only pays when streaming
+        if (f_mt && mt != f_mt && !(mt == 1 && (p.n_acc_log2 < 2 || m_tiles < 2))) continue;
+        if (mt == 2 && (p.n_acc_log2 < 2 || m_tiles < 2)) continue;
+        for (int groups = 4; groups >= 2; groups -= 2) {
+          if (groups > (1 << p.n_acc_log2)) continue;          // a group must never be a whole accumulator phase ahead
+          if (f_groups && groups != f_groups && f_groups <= (1 << p.n_acc_log2)) continue;
+          const int staging = p.epi_tma ? groups * kStgBufs * p.stg_bytes : 0;
+          int avail = kSmemMax - fixed - staging;
+          int stages_a = 0, stages_b = 0;
+          const int tpb = taps / boxes;
+          if (resident) {
+            stages_a = (avail - b_all) / (mt * a_box);
+            if (stages_a > kTStages) stages_a = kTStages;
+          } else {
+            // s weight tiles in flight, and the activation boxes that feed them (one box serves tpb taps)
+            for (int sb = kTStages; sb >= 2 && !stages_b; --sb) {
+              int sa = (sb + tpb - 1) / tpb + 1;
+              if (sa < 2) sa = 2;
+              if (sa > kTStages) sa = kTStages;
+              if (sa * mt * a_box + sb * p.b_tile_bytes <= avail) stages_a = sa, stages_b = sb;
+            }
+          }
+          if (stages_a < 2) continue;
+          // cycles per M tile: tensor pipe (operand reads from shared memory included), L2 -> SM traffic at the
+          // rate the bytes in flight can sustain (Little: ~2000 cycles from issue to a reusable slot), epilogue
+          const double mma = taps * p.cchunks * mma_tap;
+          const double b_bytes = (double)p.block_n * row_bytes;
+          const double bytes = (double)p.cchunks * boxes * a_bytes + (resident ? 0.0 : (double)taps * p.cchunks * b_bytes / mt);
+          const double inflight = (double)(stages_a - 1) * mt * a_bytes + (resident ? 0.0 : (double)(stages_b - 1) * b_bytes);
+          double rate = inflight / 2000.0;
+          if (rate > kFabric) rate = kFabric;
+          const double fab = bytes / rate;
+          const double epi = (p.epi_tma ? (p.block_n / 32.0) * 900.0 : (p.block_n / 32.0) * 1500.0) / groups;
+          // TMA writes share the shared-memory port with the MMA operand reads (128 B/clk)
+          double t = mma + bytes / 128.0;
+          if (fab > t) t = fab;
+          if (epi > t) t = epi;
+          // hand-shake overhead of the single issuing threads: per activation box, and per streamed weight tile
+          t += 150.0 * p.cchunks * boxes / mt + (resident ? 0.0 : 60.0 * p.cchunks * taps / mt);
+          const double cost = (double)m_tiles * n_tiles * t;
+          if (best.cost < 0 || cost < best.cost) {
+            best.cost = cost, best.mode = mode, best.tw = gw, best.th = gh, best.tn = gn, best.mt = mt;
+            best.groups = groups, best.resident = resident, best.stages_a = stages_a, best.stages_b = stages_b;
+          }
+        }
+      }
+      if (mode != 1) break;
+    }
+  }
+  }
+  B2F_REQUIRE(best.cost >= 0, "conv: no tile plan fits in shared memory (cin_p %d cout_p %d k %d)", d->cin_p, d->cout_p, d->kh);
+  p.a_mode = best.mode, p.tw = best.tw, p.th = best.th, p.tn = best.tn, p.mt = best.mt, p.groups = best.groups;
+  p.b_resident = best.resident, p.stages_a = best.stages_a, p.stages_b = best.stages_b;
+  p.tiles_x = (Wo + p.tw - 1) / p.tw;
+  p.tiles_y = (Ho + p.th - 1) / p.th;
+  p.m_tiles = p.tiles_x * p.tiles_y * ((d->n + p.tn - 1) / p.tn);
+  p.items = n_tiles * ((p.m_tiles + p.mt - 1) / p.mt);
+  p.boxes_per_chunk = p.a_mode == 0 ? taps : (p.a_mode == 1 ? 3 : 1);
+  p.taps_per_box = taps / p.boxes_per_chunk;
+  const int box_w = p.a_mode == 0 ? p.tw * d->stride : (p.a_mode == 1 ? p.tw : p.tw + 2);
+  const int box_h = p.a_mode == 0 ? p.th * d->stride : p.th + 2;
+  p.a_bytes = (p.a_mode == 0 ? p.tw * p.th * p.tn : box_w * box_h) * row_bytes;
+  p.a_box_bytes = round_up(p.a_bytes, 1024);
+  p.a_stage_bytes = p.a_box_bytes * p.mt;
+  p.stg_box_bytes = p.tw * p.th * p.tn * p.ochunk * 2;
+  p.off_b = p.stages_a * p.a_stage_bytes;
+  p.off_stg = p.off_b + (p.b_resident ? b_all : p.stages_b * p.b_tile_bytes);
+  p.off_bar = p.off_stg + (p.epi_tma ? p.groups * kStgBufs * p.stg_bytes : 0);
+  p.off_tab = p.off_bar + 1024;
+  size_t smem = (size_t)p.off_tab + tab_bytes + 1024;
+  B2F_REQUIRE(smem <= (size_t)kSmemMax, "conv tile kernel: %zu bytes of shared memory requested", smem);
+  if (smem < 120 * 1024) smem = 120 * 1024;      // one CTA per SM: it owns all 512 TMEM columns
+
+  CUtensorMap tmA, tmB, tmO, tmR;
+  {
+    uint64_t dims[4] = {(uint64_t)d->cin_p, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
+    uint64_t str[3] = {(uint64_t)d->cin_p * 2, (uint64_t)d->w * d->cin_p * 2, (uint64_t)d->h * d->w * d->cin_p * 2};
+    uint32_t box[4] = {(uint32_t)kchunk, (uint32_t)box_w, (uint32_t)box_h, (uint32_t)p.tn};
+    uint32_t es[4] = {1, 1, 1, 1};
+    if (p.a_mode == 0) es[1] = es[2] = (uint32_t)d->stride;
+    int rc = make_tmap(&tmA, d->in, 4, dims, str, box, es, row_bytes, p.is_bf16);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)d->cin_p, (uint64_t)d->cout_p, (uint64_t)taps};
+    uint64_t str[2] = {(uint64_t)d->cin_p * 2, (uint64_t)d->cout_p * d->cin_p * 2};
+    uint32_t box[3] = {(uint32_t)kchunk, (uint32_t)p.block_n, 1};
+    uint32_t es[3] = {1, 1, 1};
+    int rc = make_tmap(&tmB, d->weight, 3, dims, str, box, es, row_bytes, p.is_bf16);
+    if (rc) return rc;
+  }
+  tmO = tmA, tmR = tmA;
+  if (p.epi_tma) {
+    uint64_t dims[4] = {(uint64_t)d->cout_p, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)d->n};
+    uint64_t str[3] = {(uint64_t)d->cout_p * 2, (uint64_t)Wo * d->cout_p * 2, (uint64_t)Ho * Wo * d->cout_p * 2};
+    uint32_t box[4] = {(uint32_t)p.ochunk, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
+    uint32_t es[4] = {1, 1, 1, 1};
+    int rc = make_tmap(&tmO, d->out, 4, dims, str, box, es, p.ochunk * 2, d->out_dtype == 1);
+    if (rc) return rc;
+    if (p.res_smem) {
+      rc = make_tmap(&tmR, d->residual, 4, dims, str, box, es, p.ochunk * 2, p.is_bf16);
+      if (rc) return rc;
+    }
+  }
+  static std::once_flag once;
+  static cudaError_t attr_rc = cudaSuccess;
+  std::call_once(once, [] {
+    attr_rc = cudaFuncSetAttribute(conv_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+  });
+  B2F_CHECK_CUDA(attr_rc);
+  static const bool trace = getenv("B2F_PLAN_TRACE") != nullptr;
+  if (trace)
+    fprintf(stderr, "[b2f plan] n%d %dx%d %d->%d k%d s%d: mode %d tile %dx%dx%d mt %d groups %d resident %d stagesA %d stagesB %d "
+            "block_n %d kchunk %d epi_tma %d res_smem %d smem %zu items %d\n", d->n, d->h, d->w, d->cin_p, d->cout_p, d->kh, d->stride,
+            p.a_mode, p.tw, p.th, p.tn, p.mt, p.groups, p.b_resident, p.stages_a, p.stages_b, p.block_n, kchunk, p.epi_tma,
+            p.res_smem, smem, p.items);
+  const int grid = p.items < g_sms ? p.items : g_sms;
+  conv_tile_kernel<<<grid, 64 + 128 * p.groups, smem, stream>>>(tmA, tmB, tmO, tmR, p);
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace b2f

@@ -11,6 +11,8 @@ extern int g_smem_budget_single;
 extern int g_max_block_n;
 extern int g_persistent;
 extern int g_vhalo;
+extern int g_debug;
+extern int g_tile_groups, g_tile_mt, g_tile_amode, g_tile_epi;
 }  // namespace b2f
 
 static thread_local char g_err[1024] = "";
@@ -38,13 +40,21 @@ extern "C" int b2f_set_tuning(int key, int value) {
     return 0;
   }
   if (key == 2) {
-    b2f::g_persistent = value ? 1 : 0;
+    b2f::g_persistent = value;
     return 0;
   }
   if (key == 3) {
-    b2f::g_vhalo = value ? 1 : 0;
+    b2f::g_vhalo = value;
     return 0;
   }
+  if (key == 4) {
+    b2f::g_debug = value;
+    return 0;
+  }
+  if (key == 5) { b2f::g_tile_groups = value; return 0; }
+  if (key == 6) { b2f::g_tile_mt = value; return 0; }
+  if (key == 7) { b2f::g_tile_amode = value; return 0; }
+  if (key == 8) { b2f::g_tile_epi = value; return 0; }
   b2f_set_error("unknown tuning key %d", key);
   return 2;
 }

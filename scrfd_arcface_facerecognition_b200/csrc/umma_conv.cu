@@ -11,7 +11,7 @@
 // = conv padding, elementStrides = conv stride) -> 128B/64B/32B-swizzled smem ring -> tcgen05.mma
 // (M=128 output pixels x N<=256 output channels, fp32 accumulators in TMEM) -> tcgen05.ld epilogue
 // (bias table / residual / ReLU|PReLU|sigmoid, or running top-k) -> global.
-#include "b2f_common.cuh"
+#include "umma_shared.cuh"
 #include "../../include/b2f.h"
 
 #include <atomic>
@@ -20,55 +20,6 @@
 namespace b2f {
 
 extern std::atomic<long long> g_launches;
-
-// ------------------------------------------------------------------------------------------
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed)
-// ------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
-// rank-R map over 2-byte elements; dims/strides innermost first; strides in bytes for dims 1..R-1
-static int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
-                     const uint32_t* box, const uint32_t* estr, int swizzle_bytes, int is_bf16) {
-  EncodeTiledFn fn = get_encode_fn();
-  B2F_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
-  CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
-                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
-                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
-                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
-  cuuint64_t gd[5], gs[4];
-  cuuint32_t bx[5], es[5];
-  for (int i = 0; i < rank; ++i) {
-    gd[i] = dims[i];
-    bx[i] = box[i];
-    es[i] = estr[i];
-  }
-  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_b[i];
-  CUresult r = fn(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank,
-                  const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  B2F_REQUIRE(r == CUDA_SUCCESS,
-              "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u] estr [%u %u %u %u] sw %d",
-              (int)r, rank, (unsigned long long)gd[0], (unsigned long long)gd[1],
-              (unsigned long long)(rank > 2 ? gd[2] : 0), (unsigned long long)(rank > 3 ? gd[3] : 0), bx[0], bx[1],
-              rank > 2 ? bx[2] : 0, rank > 3 ? bx[3] : 0, es[0], es[1], rank > 2 ? es[2] : 0, rank > 3 ? es[3] : 0,
-              swizzle_bytes);
-  return 0;
-}
 
 // ------------------------------------------------------------------------------------------
 // kernel parameters
@@ -95,7 +46,9 @@ struct UmmaParams {
   int stages, b_tile_bytes, tmem_cols;
   int total_tiles, n_acc, acc_stride;   // persistent kernel: tiles = M tiles x N tiles, TMEM accumulator ring
   int a_stage_bytes, stages_a, stages_b, b_resident;   // vertical-halo kernel
+  int halo2;                // 1: one (th+2) x (tw+2) box per channel chunk serves all nine taps (tw == 8)
   int is_bf16;
+  int debug;                // bottleneck isolation (b2f_set_tuning key 4): 1 no stores, 2 no residual, 4 no MMA, 8 no A loads, 16 no epilogue math
   // EPI_STORE
   void* out;
   int out_dtype;            // 0 f16, 1 bf16, 2 f32
@@ -124,73 +77,6 @@ struct UmmaParams {
   long long max_pairs;
   unsigned long long* pair_count;
 };
-
-// ------------------------------------------------------------------------------------------
-// epilogue helpers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float act_apply(float v, int act, float slope) {
-  if (act == 1) return fmaxf(v, 0.f);
-  if (act == 2) return v >= 0.f ? v : v * slope;
-  if (act == 3) return 1.f / (1.f + expf(-v));
-  return v;
-}
-
-__device__ __forceinline__ void load16_as_float(const void* p, int is_bf16, float (&f)[16]) {
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-  uint4 a = __ldg(q), b = __ldg(q + 1);
-  uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (is_bf16) {
-      __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&w[i]);
-      f[2 * i] = __bfloat162float(h.x);
-      f[2 * i + 1] = __bfloat162float(h.y);
-    } else {
-      __half2 h = *reinterpret_cast<__half2*>(&w[i]);
-      f[2 * i] = __half2float(h.x);
-      f[2 * i + 1] = __half2float(h.y);
-    }
-  }
-}
-
-__device__ __forceinline__ void store16(void* p, int dtype, const float (&f)[16]) {
-  if (dtype == 2) {
-    float4* q = reinterpret_cast<float4*>(p);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) q[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-    return;
-  }
-  uint32_t w[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (dtype == 1) {
-      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-      w[i] = *reinterpret_cast<uint32_t*>(&h);
-    } else {
-      __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-      w[i] = *reinterpret_cast<uint32_t*>(&h);
-    }
-  }
-  uint4* q = reinterpret_cast<uint4*>(p);
-  q[0] = make_uint4(w[0], w[1], w[2], w[3]);
-  q[1] = make_uint4(w[4], w[5], w[6], w[7]);
-}
-
-
-// K-steps of one pipeline stage, fully unrolled (the issuing thread's instruction stream is the critical path
-// for narrow tiles: every extra instruction per tcgen05.mma shows up as tensor-pipe idle time)
-template <int KSTEPS>
-__device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t first_acc) {
-#pragma unroll
-  for (int k = 0; k < KSTEPS; ++k)
-    umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, k == 0 ? first_acc : 1u);
-}
-__device__ __forceinline__ void issue_stage_rt(int ksteps, uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc,
-                                               uint32_t first_acc) {
-  if (ksteps == 4) issue_stage<4>(d_tmem, da, db, idesc, first_acc);
-  else if (ksteps == 2) issue_stage<2>(d_tmem, da, db, idesc, first_acc);
-  else issue_stage<1>(d_tmem, da, db, idesc, first_acc);
-}
 
 // ------------------------------------------------------------------------------------------
 // the kernel: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue
@@ -531,7 +417,7 @@ __device__ __forceinline__ void epilogue_store16(const UmmaParams& p, const uint
     f[4 * v + 2] = __uint_as_float(r[4 * v + 2]) + b4.z;
     f[4 * v + 3] = __uint_as_float(r[4 * v + 3]) + b4.w;
   }
-  if (p.res_mode) {
+  if (p.res_mode && !(p.debug & 2)) {
     float rs[16];
     load16_as_float(reinterpret_cast<const uint8_t*>(p.residual) + (res_pix * p.cout_p + c) * 2, p.is_bf16, rs);
 #pragma unroll
@@ -554,6 +440,7 @@ __device__ __forceinline__ void epilogue_store16(const UmmaParams& p, const uint
     for (int i = 0; i < 16; ++i)
       if (p.sig_hi == 0 || c + i < p.sig_hi) f[i] = 1.f / (1.f + expf(-f[i]));
   }
+  if ((p.debug & 1) && f[0] != 12345.678f) return;
   store16(reinterpret_cast<uint8_t*>(p.out) + (pix * p.cout_p + c) * esz, p.out_dtype, f);
 }
 
@@ -606,7 +493,7 @@ __device__ __forceinline__ void persistent_epilogue(const UmmaParams& p, uint32_
     const int cbase = nt * p.block_n;
     const int c_begin = col_part * 128;                                   // split == 2 only when block_n > 128
     const int c_end = split == 1 ? p.block_n : min(p.block_n, c_begin + 128);
-    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+    for (int c0 = c_begin; c0 < c_end && !(p.debug & 16); c0 += 32) {
       uint32_t r[32];
       tmem_ld32(t_addr + (uint32_t)c0, r);
       tmem_ld_wait();
@@ -693,8 +580,12 @@ umma_conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
             for (int cc = 0; cc < cchunks; ++cc) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* a_dst = smem + stage * stage_bytes;
-              mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-              tma_load_4d(a_dst, &tmA, &full_bar[stage], cc * kchunk, x0 + sx, y0 + r, n0);
+              if (p.debug & 8) {
+                mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)block_n * row_bytes);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                tma_load_4d(a_dst, &tmA, &full_bar[stage], cc * kchunk, x0 + sx, y0 + r, n0);
+              }
               tma_load_3d(a_dst + kATileBytes, &tmB, &full_bar[stage], cc * kchunk, nrow, tap);
               if (++stage == stages) {
                 stage = 0;
@@ -726,7 +617,7 @@ umma_conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         tc_fence_after();
         if (elect_one()) {
           const uint64_t off = stage_inc * (uint64_t)stage;
-          issue_stage_rt(ksteps, d_tmem, a_desc0 + off, b_desc0 + off, idesc, kk != 0);
+          if (!(p.debug & 4)) issue_stage_rt(ksteps, d_tmem, a_desc0 + off, b_desc0 + off, idesc, kk != 0);
           umma_commit(&empty_bar[stage]);
           if (kk == k_iters - 1) umma_commit(&tfull_bar[acc]);
         }
@@ -823,7 +714,7 @@ umma_conv_vhalo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int stages_a = p.stages_a, stages_b = p.stages_b, a_stage_bytes = p.a_stage_bytes;
       const int b_tile_bytes = p.b_tile_bytes;
       const bool resident = p.b_resident != 0;
-      const uint32_t a_bytes = (uint32_t)((th + 2) * tw) * row_bytes;
+      const uint32_t a_bytes = (uint32_t)((th + 2) * (p.halo2 ? tw + 2 : tw)) * row_bytes;
       const uint32_t b_bytes = (uint32_t)block_n * row_bytes;
       if (resident) {
         mbar_arrive_expect_tx(bres_bar, b_bytes * 9u * (uint32_t)cchunks);
@@ -835,6 +726,7 @@ umma_conv_vhalo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
+      const int n_boxes = p.halo2 ? 1 : 3, sx_per_box = p.halo2 ? 3 : 1;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         const int nt = t % n_tiles;
         const int m_tile = t / n_tiles;
@@ -843,17 +735,23 @@ umma_conv_vhalo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int n0 = m_tile / tiles_xy;
         const int nrow = nt * block_n;
         for (int cc = 0; cc < cchunks; ++cc) {
-          for (int sx = 0; sx < 3; ++sx) {
+          for (int bx = 0; bx < n_boxes; ++bx) {
             mbar_wait(&emptyA[sa], pa ^ 1);
-            mbar_arrive_expect_tx(&fullA[sa], a_bytes);
-            tma_load_4d(a_ring + (size_t)sa * a_stage_bytes, &tmA, &fullA[sa], cc * kchunk, x0 + sx, y0, n0);
+            if (p.debug & 8) {
+              mbar_arrive(&fullA[sa]);
+            } else {
+              mbar_arrive_expect_tx(&fullA[sa], a_bytes);
+              tma_load_4d(a_ring + (size_t)sa * a_stage_bytes, &tmA, &fullA[sa], cc * kchunk, x0 + bx, y0, n0);
+            }
             if (++sa == stages_a) sa = 0, pa ^= 1;
             if (!resident) {
-              for (int r = 0; r < 3; ++r) {
-                mbar_wait(&emptyB[sb], pb ^ 1);
-                mbar_arrive_expect_tx(&fullB[sb], b_bytes);
-                tma_load_3d(b_base + (size_t)sb * b_tile_bytes, &tmB, &fullB[sb], cc * kchunk, nrow, r * 3 + sx);
-                if (++sb == stages_b) sb = 0, pb ^= 1;
+              for (int sxi = 0; sxi < sx_per_box; ++sxi) {
+                for (int r = 0; r < 3; ++r) {
+                  mbar_wait(&emptyB[sb], pb ^ 1);
+                  mbar_arrive_expect_tx(&fullB[sb], b_bytes);
+                  tma_load_3d(b_base + (size_t)sb * b_tile_bytes, &tmB, &fullB[sb], cc * kchunk, nrow, r * 3 + bx + sxi);
+                  if (++sb == stages_b) sb = 0, pb ^= 1;
+                }
               }
             }
           }
@@ -863,14 +761,20 @@ umma_conv_vhalo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     const uint32_t idesc = umma_idesc(128, (uint32_t)p.block_n, (uint32_t)p.is_bf16);
-    const int ksteps = p.kchunk >> 4, total = p.total_tiles, n_acc = p.n_acc, groups = 3 * p.cchunks;
+    const int ksteps = p.kchunk >> 4, total = p.total_tiles, n_acc = p.n_acc;
+    const int groups = (p.halo2 ? 1 : 3) * p.cchunks, sx_per_box = p.halo2 ? 3 : 1;
     const int stages_a = p.stages_a, stages_b = p.stages_b;
     const bool resident = p.b_resident != 0;
     const uint32_t acc_stride = (uint32_t)p.acc_stride;
-    const uint64_t a_desc0 = umma_smem_desc(smem_u32(a_ring), row_bytes);
+    const int box_w = p.halo2 ? p.tw + 2 : p.tw;
+    // 8-row groups of the A tile are 8 consecutive pixels of one box row: group stride = one box row when the
+    // box is wider than the tile (halo2), else the canonical 8 rows
+    const uint32_t sbo = p.halo2 ? (uint32_t)box_w * row_bytes : 8u * row_bytes;
+    const uint64_t a_desc0 = umma_smem_desc_sbo(smem_u32(a_ring), row_bytes, sbo);
     const uint64_t b_desc0 = umma_smem_desc(smem_u32(b_base), row_bytes);
     const uint64_t a_inc = (uint64_t)(p.a_stage_bytes >> 4), b_inc = (uint64_t)(p.b_tile_bytes >> 4);
-    const uint64_t r_inc = (uint64_t)(((uint32_t)p.tw * row_bytes) >> 4);       // one tile row of the halo box
+    const uint64_t r_inc = (uint64_t)(((uint32_t)box_w * row_bytes) >> 4);       // one row of the halo box
+    const uint64_t s_inc = (uint64_t)(row_bytes >> 4);                             // one pixel
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
     int acc = 0;
@@ -883,34 +787,41 @@ umma_conv_vhalo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
-      uint64_t bd = b_desc0;
-      for (int g = 0; g < groups; ++g) {                 // one (channel chunk, horizontal tap) group = one A box
+      for (int g = 0; g < groups; ++g) {                 // one A box: (channel chunk, horizontal tap) or a whole chunk
         mbar_wait(&fullA[sa], pa);
         tc_fence_after();
         const uint64_t ad = a_desc0 + a_inc * (uint64_t)sa;
         if (resident) {
           if (elect_one()) {
-            issue_stage_rt(ksteps, d_tmem, ad, bd, idesc, g != 0);
-            issue_stage_rt(ksteps, d_tmem, ad + r_inc, bd + b_inc, idesc, 1u);
-            issue_stage_rt(ksteps, d_tmem, ad + 2 * r_inc, bd + 2 * b_inc, idesc, 1u);
+            if (!(p.debug & 4)) {
+              uint64_t bd = b_desc0 + b_inc * (uint64_t)(3 * sx_per_box * g);
+              for (int sxi = 0; sxi < sx_per_box; ++sxi, bd += 3 * b_inc) {
+                const uint64_t as = ad + s_inc * (uint64_t)sxi;
+                issue_stage_rt(ksteps, d_tmem, as, bd, idesc, (g | sxi) != 0);
+                issue_stage_rt(ksteps, d_tmem, as + r_inc, bd + b_inc, idesc, 1u);
+                issue_stage_rt(ksteps, d_tmem, as + 2 * r_inc, bd + 2 * b_inc, idesc, 1u);
+              }
+            }
             umma_commit(&emptyA[sa]);
             if (g == groups - 1) umma_commit(&tfull_bar[acc]);
           }
-          bd += 3 * b_inc;
         } else {
-          for (int r = 0; r < 3; ++r) {
-            mbar_wait(&fullB[sb], pb);
-            tc_fence_after();
-            if (elect_one()) {
-              issue_stage_rt(ksteps, d_tmem, ad + r_inc * (uint64_t)r, b_desc0 + b_inc * (uint64_t)sb, idesc,
-                             (g | r) != 0);
-              umma_commit(&emptyB[sb]);
-              if (r == 2) {
-                umma_commit(&emptyA[sa]);
-                if (g == groups - 1) umma_commit(&tfull_bar[acc]);
+          for (int sxi = 0; sxi < sx_per_box; ++sxi) {
+            for (int r = 0; r < 3; ++r) {
+              mbar_wait(&fullB[sb], pb);
+              tc_fence_after();
+              if (elect_one()) {
+                if (!(p.debug & 4))
+                  issue_stage_rt(ksteps, d_tmem, ad + s_inc * (uint64_t)sxi + r_inc * (uint64_t)r,
+                                 b_desc0 + b_inc * (uint64_t)sb, idesc, (g | sxi | r) != 0);
+                umma_commit(&emptyB[sb]);
+                if (r == 2 && sxi == sx_per_box - 1) {
+                  umma_commit(&emptyA[sa]);
+                  if (g == groups - 1) umma_commit(&tfull_bar[acc]);
+                }
               }
+              if (++sb == stages_b) sb = 0, pb ^= 1;
             }
-            if (++sb == stages_b) sb = 0, pb ^= 1;
           }
         }
         if (++sa == stages_a) sa = 0, pa ^= 1;
@@ -941,7 +852,7 @@ static int pow2_cols(int n) {
   return c;
 }
 
-static void pick_m_tile(int N, int Ho, int Wo, int stride, int* tw, int* th, int* tn) {
+void pick_m_tile(int N, int Ho, int Wo, int stride, int* tw, int* th, int* tn) {
   long long best = -1;
   int bw = 1, bh = 1, bn = 1;
   const int max_w = Wo < 128 ? Wo : 128;
@@ -993,7 +904,8 @@ static int launch_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaParam
   return 0;
 }
 
-int g_persistent = 1;
+int g_persistent = 2;     // 0: one CTA per tile, 1: first persistent kernels, 2: conv_tile_kernel (conv_tile.cu)
+int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream);
 int g_num_sms = 0;
 
 static int launch_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaParams& p, int m_tiles,
@@ -1030,6 +942,7 @@ static int launch_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, Umm
 }
 
 int g_vhalo = 1;
+int g_debug = 0;
 
 static int launch_vhalo(const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaParams& p, int m_tiles,
                         cudaStream_t stream) {
@@ -1039,7 +952,7 @@ static int launch_vhalo(const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaPara
     B2F_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int row_bytes = p.kchunk * 2;
-  p.a_stage_bytes = (((p.th + 2) * p.tw * row_bytes) + 1023) & ~1023;
+  p.a_stage_bytes = (((p.th + 2) * (p.halo2 ? p.tw + 2 : p.tw) * row_bytes) + 1023) & ~1023;
   const int budget = 226 * 1024 - 1024 - 512 - kEpiSmemBytes;
   int b_bytes_total;
   if (p.b_resident) {
@@ -1105,6 +1018,14 @@ extern "C" int b2f_conv2d(const b2f_conv_desc* d, void* stream_) {
   p.kh = d->kh, p.kw = d->kw, p.stride = d->stride, p.pad = d->pad;
   p.kchunk = d->force_kchunk ? d->force_kchunk : pick_kchunk(d->cin_p);
   B2F_REQUIRE(d->cin_p % p.kchunk == 0, "b2f_conv2d: kchunk %d does not divide cin_p %d", p.kchunk, d->cin_p);
+  B2F_REQUIRE(d->act != 2 || d->slope != nullptr, "b2f_conv2d: PReLU needs a slope vector");
+  {
+    // conv_tile_kernel (halo boxes, shared weight tiles, TMA-store epilogue) wins wherever a tile is at most 128
+    // channels wide; wider tiles are tensor-pipe bound already and keep the first persistent kernel
+    int nt = (d->cout_p + g_max_block_n - 1) / g_max_block_n;
+    while ((d->cout_p % nt) != 0 || ((d->cout_p / nt) % 16) != 0) ++nt;
+    if (g_persistent == 3 || (g_persistent == 2 && d->cout_p / nt <= 128)) return conv_tile_launch(d, p.kchunk, stream);
+  }
   p.cchunks = d->cin_p / p.kchunk;
   pick_m_tile(d->n, Ho, Wo, d->stride, &p.tw, &p.th, &p.tn);
   p.tiles_x = (Wo + p.tw - 1) / p.tw;
@@ -1125,6 +1046,7 @@ extern "C" int b2f_conv2d(const b2f_conv_desc* d, void* stream_) {
   B2F_REQUIRE(d->act != 2 || d->slope != nullptr, "b2f_conv2d: PReLU needs a slope vector");
   p.residual = d->residual, p.res_mode = d->residual ? d->res_mode : 0;
   p.res_h = d->res_h, p.res_w = d->res_w;
+  p.debug = g_debug;
 
   // ---- vertical-halo variant: 3x3 / stride 1 / pad 1 on maps wide enough for 8-pixel-aligned tiles ----------
   bool vhalo = false;
@@ -1148,7 +1070,14 @@ extern "C" int b2f_conv2d(const b2f_conv_desc* d, void* stream_) {
       const double t = tiles * (mma > bytes / kFabric ? mma : bytes / kFabric);
       if (best < 0 || t < best) best = t, btw = tw;
     }
-    if (best >= 0 && best < 0.9 * def_time) {
+    if (g_vhalo == 2) {          // full-halo variant: 8 x 16 tiles, one (10 x 18) box per channel chunk
+      vhalo = true;
+      p.halo2 = 1;
+      p.tw = 8, p.th = 16, p.tn = 1;
+      p.tiles_x = (Wo + p.tw - 1) / p.tw;
+      p.tiles_y = (Ho + p.th - 1) / p.th;
+      p.b_resident = can_res ? 1 : 0;
+    } else if (best >= 0 && best < 0.9 * def_time) {
       vhalo = true;
       p.tw = btw, p.th = 128 / btw, p.tn = 1;
       p.tiles_x = (Wo + p.tw - 1) / p.tw;
@@ -1162,7 +1091,7 @@ extern "C" int b2f_conv2d(const b2f_conv_desc* d, void* stream_) {
   if (vhalo) {
     uint64_t dims[4] = {(uint64_t)d->cin_p, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
     uint64_t str[3] = {(uint64_t)d->cin_p * 2, (uint64_t)d->w * d->cin_p * 2, (uint64_t)d->h * d->w * d->cin_p * 2};
-    uint32_t box[4] = {(uint32_t)p.kchunk, (uint32_t)p.tw, (uint32_t)(p.th + 2), 1};
+    uint32_t box[4] = {(uint32_t)p.kchunk, (uint32_t)(p.halo2 ? p.tw + 2 : p.tw), (uint32_t)(p.th + 2), 1};
     uint32_t es[4] = {1, 1, 1, 1};
     int rc = make_tmap(&tmA, d->in, 4, dims, str, box, es, p.kchunk * 2, p.is_bf16);
     if (rc) return rc;

@@ -1,0 +1,126 @@
+// Pieces shared by the tcgen05 kernels of libb2f (umma_conv.cu, conv_tile.cu): tensor-map encoding on the host,
+// epilogue arithmetic and the unrolled MMA issue helpers on the device.
+#pragma once
+#include "b2f_common.cuh"
+
+#include <mutex>
+
+namespace b2f {
+
+// ------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// rank-R map over 2-byte elements; dims/strides innermost first; strides in bytes for dims 1..R-1
+static inline int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+                     const uint32_t* box, const uint32_t* estr, int swizzle_bytes, int is_bf16) {
+  EncodeTiledFn fn = get_encode_fn();
+  B2F_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = estr[i];
+  }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_b[i];
+  CUresult r = fn(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank,
+                  const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B2F_REQUIRE(r == CUDA_SUCCESS,
+              "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u] estr [%u %u %u %u] sw %d",
+              (int)r, rank, (unsigned long long)gd[0], (unsigned long long)gd[1],
+              (unsigned long long)(rank > 2 ? gd[2] : 0), (unsigned long long)(rank > 3 ? gd[3] : 0), bx[0], bx[1],
+              rank > 2 ? bx[2] : 0, rank > 3 ? bx[3] : 0, es[0], es[1], rank > 2 ? es[2] : 0, rank > 3 ? es[3] : 0,
+              swizzle_bytes);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// epilogue helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_apply(float v, int act, float slope) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return v >= 0.f ? v : v * slope;
+  if (act == 3) return 1.f / (1.f + expf(-v));
+  return v;
+}
+
+__device__ __forceinline__ void load16_as_float(const void* p, int is_bf16, float (&f)[16]) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (is_bf16) {
+      __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&w[i]);
+      f[2 * i] = __bfloat162float(h.x);
+      f[2 * i + 1] = __bfloat162float(h.y);
+    } else {
+      __half2 h = *reinterpret_cast<__half2*>(&w[i]);
+      f[2 * i] = __half2float(h.x);
+      f[2 * i + 1] = __half2float(h.y);
+    }
+  }
+}
+
+__device__ __forceinline__ void store16(void* p, int dtype, const float (&f)[16]) {
+  if (dtype == 2) {
+    float4* q = reinterpret_cast<float4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+    return;
+  }
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (dtype == 1) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    } else {
+      __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+  }
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+
+// K-steps of one pipeline stage, fully unrolled (the issuing thread's instruction stream is the critical path
+// for narrow tiles: every extra instruction per tcgen05.mma shows up as tensor-pipe idle time)
+template <int KSTEPS>
+__device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t first_acc) {
+#pragma unroll
+  for (int k = 0; k < KSTEPS; ++k)
+    umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, k == 0 ? first_acc : 1u);
+}
+__device__ __forceinline__ void issue_stage_rt(int ksteps, uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc,
+                                               uint32_t first_acc) {
+  if (ksteps == 4) issue_stage<4>(d_tmem, da, db, idesc, first_acc);
+  else if (ksteps == 2) issue_stage<2>(d_tmem, da, db, idesc, first_acc);
+  else issue_stage<1>(d_tmem, da, db, idesc, first_acc);
+}
+
+}  // namespace b2f

@@ -218,10 +218,10 @@ def test_conv2d_epilogue_variants(lib):
 
 
 @pytest.mark.parametrize("case", [(2, 64, 64, 64, 64), (2, 48, 80, 96, 96), (1, 32, 32, 128, 128), (3, 24, 40, 32, 32),
-                                  (2, 56, 56, 64, 128), (2, 20, 20, 224, 224), (1, 33, 47, 64, 32)],
+                                  (2, 56, 56, 64, 128), (2, 20, 20, 224, 224), (1, 33, 47, 64, 32), (2, 40, 24, 80, 80)],
                          ids=lambda c: "x".join(map(str, c)))
 def test_conv_kernel_variants_agree(lib, case):
-    """per-tile kernel, persistent kernel and vertical-halo kernel (resident / streamed weights) on 3x3 s1 convs"""
+    """per-tile kernel, persistent kernel, vertical-halo and full-halo kernels (resident / streamed weights) on 3x3 s1 convs"""
     n, h, w, cin, cout = case
     g = torch.Generator().manual_seed(sum(case))
     x = _q(torch.randn((n, cin, h, w), generator=g))
@@ -229,16 +229,24 @@ def test_conv_kernel_variants_agree(lib, case):
     b = torch.randn(cout, generator=g) * 0.1
     res = _q(torch.randn((n, cout, h, w), generator=g))
     ref = torch.relu(F.conv2d(x, wt, b, 1, 1) + res)
+    # (generation, vhalo, a_mode, mt, groups, tma_epilogue): 0 = CTA per tile, 1 = first persistent kernels,
+    # 2 = default dispatch, 3 = conv_tile_kernel for every layer
+    variants = [(0, 0, -1, 0, 0, -1), (1, 0, -1, 0, 0, -1), (1, 1, -1, 0, 0, -1), (1, 2, -1, 0, 0, -1), (2, 1, -1, 0, 0, -1),
+                (3, 1, -1, 0, 0, -1)]
+    variants += [(3, 1, am, mt, gr, 1) for am in (0, 1, 2) for mt in (1, 2) for gr in (2, 4)]
+    variants += [(3, 1, 2, 1, 4, 0), (3, 1, 0, 2, 2, 0)]
     try:
-        for persistent, vhalo in ((0, 0), (1, 0), (1, 1)):
-            _lib.check(lib.b2f_set_tuning(2, persistent))
-            _lib.check(lib.b2f_set_tuning(3, vhalo))
-            out = run_conv(lib, x, wt, b, 1, 1, act=1, residual=res, res_mode=1, out_f32=True)
-            err = (out - ref).abs().max().item()
-            assert err <= 2e-3 * max(1.0, ref.abs().max().item()), f"persistent={persistent} vhalo={vhalo}: {err}"
+        for persistent, vhalo, amode, mt, groups, epi in variants:
+            for key, val in ((2, persistent), (3, vhalo), (7, amode), (6, mt), (5, groups), (8, epi)):
+                _lib.check(lib.b2f_set_tuning(key, val))
+            for f32 in (True, False):
+                out = run_conv(lib, x, wt, b, 1, 1, act=1, residual=res, res_mode=1, out_f32=f32)
+                err = (out - ref).abs().max().item()
+                tol = (2e-3 if f32 else 4e-3) * max(1.0, ref.abs().max().item())
+                assert err <= tol, f"variant {(persistent, vhalo, amode, mt, groups, epi)} f32={f32}: {err}"
     finally:
-        _lib.check(lib.b2f_set_tuning(2, 1))
-        _lib.check(lib.b2f_set_tuning(3, 1))
+        for key, val in ((2, 2), (3, 1), (7, -1), (6, 0), (5, 0), (8, -1)):
+            _lib.check(lib.b2f_set_tuning(key, val))
 
 
 # =============================================================================================

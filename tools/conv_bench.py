@@ -14,7 +14,7 @@ def main():
     bias9 = a[9] if len(a) > 9 else 0
     reps = a[10] if len(a) > 10 else 20
     lib = _lib.lib()
-    for key, env in ((2, "B2F_PERSISTENT"), (3, "B2F_VHALO"), (1, "B2F_MAXN")):
+    for key, env in ((2, "B2F_PERSISTENT"), (3, "B2F_VHALO"), (1, "B2F_MAXN"), (4, "B2F_DEBUG"), (5, "B2F_GROUPS"), (6, "B2F_MT"), (7, "B2F_AMODE"), (8, "B2F_EPI")):
         if env in os.environ:
             _lib.check(lib.b2f_set_tuning(key, int(os.environ[env])))
     pad = k // 2 if k == 3 else 0
@@ -48,7 +48,7 @@ def main():
     fl = 2.0 * n * ho * wo * cout * cin * k * k
     byts = (x.numel() + out.numel() + (r.numel() if res else 0)) * 2
     print(f"conv n{n} {h}x{w} {cin}->{cout} k{k} s{stride} act{act} res{res} b9{bias9} "
-          f"[P{os.environ.get('B2F_PERSISTENT','1')} V{os.environ.get('B2F_VHALO','1')}]: {ms*1e3:8.1f} us  "
+          f"[P{os.environ.get('B2F_PERSISTENT','1')} V{os.environ.get('B2F_VHALO','1')} D{os.environ.get('B2F_DEBUG','0')}]: {ms*1e3:8.1f} us  "
           f"{fl/ms/1e9:7.1f} TFLOP/s  {byts/ms/1e6:7.1f} GB/s(act)")
 
 main()
