@@ -147,6 +147,88 @@ __device__ __forceinline__ void epi_math16(const TileParams& p, const uint32_t* 
   }
 }
 
+// ---- specialised epilogue arithmetic: straight-line code per (activation, dtype, residual) ------------------
+template <bool BF16>
+__device__ __forceinline__ void unpack8_t(const uint4& v, float* f) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (BF16) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    } else {
+      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = t.x, f[2 * i + 1] = t.y;
+    }
+  }
+}
+template <bool BF16>
+__device__ __forceinline__ uint4 pack8_t(const float* f) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (BF16) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    } else {
+      __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// 16 accumulator columns -> bias (+ residual read from the staging row) -> activation -> packed into the staging row
+template <int ACT, bool BF16, bool RES>
+__device__ __forceinline__ void epi_slice16(const uint32_t* r, const float* bias_c, const float* slope_c, uint4* p0,
+                                            uint4* p1, int c, int sig_hi) {
+  float f[16];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const float4 b4 = *(reinterpret_cast<const float4*>(bias_c) + v);           // shared memory, broadcast
+    f[4 * v + 0] = __uint_as_float(r[4 * v + 0]) + b4.x;
+    f[4 * v + 1] = __uint_as_float(r[4 * v + 1]) + b4.y;
+    f[4 * v + 2] = __uint_as_float(r[4 * v + 2]) + b4.z;
+    f[4 * v + 3] = __uint_as_float(r[4 * v + 3]) + b4.w;
+  }
+  if (RES) {
+    float rs[16];
+    unpack8_t<BF16>(*p0, rs);
+    unpack8_t<BF16>(*p1, rs + 8);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] += rs[i];
+  }
+  if (ACT == 1) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+  } else if (ACT == 2) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const float4 s4 = *(reinterpret_cast<const float4*>(slope_c) + v);
+      f[4 * v + 0] = fmaxf(f[4 * v + 0], 0.f) + s4.x * fminf(f[4 * v + 0], 0.f);
+      f[4 * v + 1] = fmaxf(f[4 * v + 1], 0.f) + s4.y * fminf(f[4 * v + 1], 0.f);
+      f[4 * v + 2] = fmaxf(f[4 * v + 2], 0.f) + s4.z * fminf(f[4 * v + 2], 0.f);
+      f[4 * v + 3] = fmaxf(f[4 * v + 3], 0.f) + s4.w * fminf(f[4 * v + 3], 0.f);
+    }
+  } else if (ACT == 3) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (sig_hi == 0 || c + i < sig_hi) f[i] = 1.f / (1.f + expf(-f[i]));
+  }
+  *p0 = pack8_t<BF16>(f);
+  *p1 = pack8_t<BF16>(f + 8);
+}
+
+struct EpiCtx {
+  uint32_t tmem_base;
+  uint64_t *tfull, *tempty, *rbar;
+  uint8_t* stg;
+  const float *s_bias, *s_slope;
+  const CUtensorMap *tmO, *tmR;
+  int tiles_cta, group, q, lane;
+  bool leader;
+};
+
 struct TileCoord {
   int x0, y0, n0, cbase, m_tile;
 };
@@ -164,6 +246,102 @@ __device__ __forceinline__ TileCoord tile_of(const TileParams& p, int seq) {
   t.n0 = (m_tile / tiles_xy) * p.tn;
   t.cbase = nt * p.block_n;
   return t;
+}
+
+// TMA-store epilogue of one group of four warps: TMEM -> registers -> arithmetic -> swizzled staging slice ->
+// cp.async.bulk.tensor store.  Staging buffers form a ring of kStgBufs per group; with a residual, the slice that
+// will be processed two steps later is TMA-loaded into its buffer first, and each thread reads / overwrites only
+// its own 16-byte pieces of it.
+template <int ACT, bool BF16, bool RES>
+__device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& c) {
+  const int G = p.groups, n_sub = p.n_sub, och = p.ochunk, group = c.group;
+  const int n_acc_mask = (1 << p.n_acc_log2) - 1;
+  const uint32_t orow = (uint32_t)och * 2;                           // staging row bytes: 64 / 32
+  const uint32_t swz_mask = orow == 64 ? 3u : 1u;
+  const int m = c.q * 32 + c.lane;
+  const int lx = m % p.tw, ly = (m / p.tw) % p.th;
+  const int my_tiles = c.tiles_cta > group ? (c.tiles_cta - group + G - 1) / G : 0;
+  const int total_sub = my_tiles * n_sub;
+  const uint32_t row_off = (uint32_t)m * orow;
+  // swizzled byte offsets of this thread's four 16-byte pieces (two per 16 channels)
+  uint32_t off[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t o = row_off + (uint32_t)i * 16;
+    off[i] = o ^ (((o >> 7) & swz_mask) << 4);
+  }
+  const bool skip_math = (p.debug & 16) != 0, skip_store = (p.debug & 1) != 0;
+  const int stg_bytes = p.stg_bytes, sig_hi = p.sig_hi, cout_p = p.cout_p;
+  auto issue_res = [&](int s) {                                      // leader only: residual slice of sub s
+    const TileCoord t = tile_of(p, group + (s / n_sub) * G);
+    const int buf = s % kStgBufs;
+    mbar_arrive_expect_tx(&c.rbar[buf], (uint32_t)p.stg_box_bytes);
+    tma_load_4d(c.stg + (size_t)buf * stg_bytes, c.tmR, &c.rbar[buf], t.cbase + (s % n_sub) * och, t.x0, t.y0, t.n0);
+  };
+  if (RES && c.leader)
+    for (int s = 0; s < kStgBufs - 1 && s < total_sub; ++s) issue_res(s);
+  int k = 0;
+  for (int tl = 0; tl < my_tiles; ++tl) {
+    const int seq = group + tl * G;
+    const TileCoord t = tile_of(p, seq);
+    int cls = 0;
+    if (p.bias_classes == 9) {
+      const int ox = t.x0 + lx, oy = t.y0 + ly;
+      const int iy = oy * p.stride - p.pad, ix = ox * p.stride - p.pad;
+      const int cy = iy < 0 ? 0 : (iy + p.kh - 1 >= p.H ? 2 : 1);
+      const int cx = ix < 0 ? 0 : (ix + p.kw - 1 >= p.W ? 2 : 1);
+      cls = cy * 3 + cx;
+    }
+    const float* bias_row = c.s_bias + cls * cout_p + t.cbase;
+    const float* slope_row = c.s_slope + t.cbase;
+    const int acc = seq & n_acc_mask;
+    const uint32_t ph = (uint32_t)(seq >> p.n_acc_log2) & 1u;
+    mbar_wait(&c.tfull[acc], ph);
+    tc_fence_after();
+    const uint32_t t_addr = c.tmem_base + ((uint32_t)(c.q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+    for (int j = 0; j < n_sub; ++j, ++k) {
+      const int buf = k % kStgBufs;
+      uint8_t* bufp = c.stg + (size_t)buf * stg_bytes;
+      uint32_t r[32];
+      if (och == 16) {
+        uint32_t r16[16];
+        tmem_ld16(t_addr + (uint32_t)(j * och), r16);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = r16[i];
+      } else {
+        tmem_ld32(t_addr + (uint32_t)(j * och), r);
+        tmem_ld_wait();
+      }
+      if (j == n_sub - 1) {                              // accumulator fully read: hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (c.lane == 0) mbar_arrive(&c.tempty[acc]);
+      }
+      if (RES) mbar_wait(&c.rbar[buf], (uint32_t)(k / kStgBufs) & 1u);
+      if (!skip_math) {
+        const int cl = j * och;
+        epi_slice16<ACT, BF16, RES>(r, bias_row + cl, slope_row + cl, reinterpret_cast<uint4*>(bufp + off[0]),
+                                    reinterpret_cast<uint4*>(bufp + off[1]), t.cbase + cl, sig_hi);
+        if (och == 32)
+          epi_slice16<ACT, BF16, RES>(r + 16, bias_row + cl + 16, slope_row + cl + 16, reinterpret_cast<uint4*>(bufp + off[2]),
+                                      reinterpret_cast<uint4*>(bufp + off[3]), t.cbase + cl + 16, sig_hi);
+      }
+      fence_proxy_async();
+      if (c.leader) {
+        // the store issued one slice ago has had this slice's arithmetic to leave its buffer; once it has, the
+        // residual of the slice two steps ahead may land there
+        bulk_wait_read0();
+        if (RES && k + kStgBufs - 1 < total_sub) issue_res(k + kStgBufs - 1);
+      }
+      bar_sync_named(1 + group, 128);
+      if (c.leader && !skip_store) {
+        tma_store_4d(c.tmO, bufp, t.cbase + j * och, t.x0, t.y0, t.n0);
+        bulk_commit();
+      }
+    }
+  }
+  if (c.leader) bulk_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -435,91 +613,25 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int G = p.groups;
 
     if (p.epi_tma) {
-      const int n_sub = p.n_sub, och = p.ochunk;
-      const uint32_t orow = (uint32_t)och * 2;                           // staging row bytes: 64 / 32
-      const uint32_t swz_mask = orow == 64 ? 3u : 1u;
-      uint8_t* stg = stg_base + (size_t)group * kStgBufs * p.stg_bytes;
-      uint64_t* my_rbar = rbar + group * kStgBufs;
-      const int my_tiles = tiles_cta > group ? (tiles_cta - group + G - 1) / G : 0;
-      const int total_sub = my_tiles * n_sub;
-      const uint32_t row_off = (uint32_t)m * orow;
-      auto issue_res = [&](int s) {                                      // leader only: residual slice of sub s
-        const TileCoord t = tile_of(p, group + (s / n_sub) * G);
-        const int buf = s % kStgBufs;
-        mbar_arrive_expect_tx(&my_rbar[buf], (uint32_t)p.stg_box_bytes);
-        tma_load_4d(stg + (size_t)buf * p.stg_bytes, &tmR, &my_rbar[buf], t.cbase + (s % n_sub) * och, t.x0, t.y0, t.n0);
-      };
-      if (leader && p.res_smem)
-        for (int s = 0; s < kStgBufs - 1 && s < total_sub; ++s) issue_res(s);
-      int k = 0;
-      for (int tl = 0; tl < my_tiles; ++tl) {
-        const int seq = group + tl * G;
-        const TileCoord t = tile_of(p, seq);
-        const int ox = t.x0 + lx, oy = t.y0 + ly;
-        int cls = 0;
-        if (p.bias_classes == 9) {
-          const int iy = oy * p.stride - p.pad, ix = ox * p.stride - p.pad;
-          const int cy = iy < 0 ? 0 : (iy + p.kh - 1 >= p.H ? 2 : 1);
-          const int cx = ix < 0 ? 0 : (ix + p.kw - 1 >= p.W ? 2 : 1);
-          cls = cy * 3 + cx;
-        }
-        const float* bias_row = s_bias + cls * p.cout_p;
-        const int acc = seq & (n_acc - 1);
-        const uint32_t ph = (uint32_t)(seq >> p.n_acc_log2) & 1u;
-        mbar_wait(&tfull[acc], ph);
-        tc_fence_after();
-        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
-        for (int j = 0; j < n_sub; ++j, ++k) {
-          const int buf = k % kStgBufs;
-          uint8_t* bufp = stg + (size_t)buf * p.stg_bytes;
-          if (leader) {
-            bulk_wait_read0();                               // the store issued one slice ago has left its buffer
-            if (p.res_smem && k + kStgBufs - 1 < total_sub) issue_res(k + kStgBufs - 1);
-          }
-          uint32_t r[32];
-          if (och == 16) {
-            uint32_t r16[16];
-            tmem_ld16(t_addr + (uint32_t)(j * och), r16);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = r16[i];
-          } else {
-            tmem_ld32(t_addr + (uint32_t)(j * och), r);
-            tmem_ld_wait();
-          }
-          if (j == n_sub - 1) {                              // accumulator fully read: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-          }
-          if (p.res_smem) mbar_wait(&my_rbar[buf], (uint32_t)(k / kStgBufs) & 1u);
-          if (!(p.debug & 16)) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              if (h * 16 < och) {
-                const uint32_t o0 = row_off + (uint32_t)h * 32, o1 = o0 + 16;
-                uint4* p0 = reinterpret_cast<uint4*>(bufp + (o0 ^ (((o0 >> 7) & swz_mask) << 4)));
-                uint4* p1 = reinterpret_cast<uint4*>(bufp + (o1 ^ (((o1 >> 7) & swz_mask) << 4)));
-                float rs[16], f[16];
-                if (p.res_smem) {
-                  unpack8(*p0, p.is_bf16, rs);
-                  unpack8(*p1, p.is_bf16, rs + 8);
-                }
-                epi_math16(p, r + h * 16, bias_row, s_slope, t.cbase + j * och + h * 16, p.res_smem ? rs : nullptr, f);
-                *p0 = pack8(f, p.out_dtype == 1);
-                *p1 = pack8(f + 8, p.out_dtype == 1);
-              }
-            }
-          }
-          fence_proxy_async();
-          bar_sync_named(1 + group, 128);
-          if (leader && !(p.debug & 1)) {
-            tma_store_4d(&tmO, bufp, t.cbase + j * och, t.x0, t.y0, t.n0);
-            bulk_commit();
-          }
-        }
+      EpiCtx c;
+      c.tmem_base = tmem_base, c.tfull = tfull, c.tempty = tempty, c.rbar = rbar + group * kStgBufs;
+      c.stg = stg_base + (size_t)group * kStgBufs * p.stg_bytes;
+      c.s_bias = s_bias, c.s_slope = s_slope, c.tmO = &tmO, c.tmR = &tmR;
+      c.tiles_cta = tiles_cta, c.group = group, c.q = q, c.lane = lane, c.leader = leader;
+      const int variant = p.act * 4 + (p.is_bf16 ? 2 : 0) + (p.res_smem ? 1 : 0);
+#define B2F_EPI_CASE(ACT)                                                   \
+      case ACT * 4 + 0: epilogue_tma<ACT, false, false>(p, c); break;         \
+      case ACT * 4 + 1: epilogue_tma<ACT, false, true>(p, c); break;          \
+      case ACT * 4 + 2: epilogue_tma<ACT, true, false>(p, c); break;          \
+      case ACT * 4 + 3: epilogue_tma<ACT, true, true>(p, c); break;
+      switch (variant) {
+        B2F_EPI_CASE(0)
+        B2F_EPI_CASE(1)
+        B2F_EPI_CASE(2)
+        B2F_EPI_CASE(3)
+        default: break;
       }
-      if (leader) bulk_wait_all();
+#undef B2F_EPI_CASE
     } else {
       // direct stores (fp32 outputs, up-sampled residual): each thread writes its pixel's channels
       const int esz = p.out_dtype == 2 ? 4 : 2;
@@ -624,7 +736,7 @@ int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream) {
 
   // ---- epilogue flavour -------------------------------------------------------------------------------
   // wide tiles (N > 128) keep every byte of shared memory for the operand rings: their epilogue hides behind the MMAs
-  p.epi_tma = (d->out_dtype != 2 && p.res_mode != 2 && (p.block_n <= 128 || g_tile_epi == 1)) ? 1 : 0;
+  p.epi_tma = (d->out_dtype == d->dtype && p.res_mode != 2 && (p.block_n <= 128 || g_tile_epi == 1)) ? 1 : 0;
   if (g_tile_epi >= 0) p.epi_tma = p.epi_tma && g_tile_epi;
   if (p.epi_tma) {
     p.ochunk = (p.block_n % 32 == 0) ? 32 : 16;
