@@ -6,12 +6,15 @@ Public surface (mirrors Kumar2421/scrfd_arcface_facerecognition):
     helpers.compute_similarity / estimate_norm / norm_crop_image ...   reference utils/helpers.py
     Gallery (cosine top-k, duplicate merge)                            reference main.py:136-142,
                                                                        qdrant_manager.py, duplicate.py:2726-2797
+    QdrantManager (same method surface, GPU resident)                  reference qdrant_manager.py:17-300
+    FaceAnalysis(name).prepare(...).get(img) -> [Face]                 reference duplicate.py:353-359, 1473-1496
 Importing the package does not touch CUDA; the heavy modules load lazily.
 """
 __version__ = "0.1.0"
 
 _LAZY = {"SCRFD": ".scrfd", "ArcFace": ".arcface", "Gallery": ".gallery", "FacePipeline": ".pipeline",
-         "helpers": ".helpers"}
+         "helpers": ".helpers", "FaceAnalysis": ".face_analysis", "Face": ".face_analysis",
+         "QdrantManager": ".vector_store", "GalleryManager": ".vector_store"}
 
 
 def __getattr__(name):

@@ -752,6 +752,9 @@ int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream) {
   const double mma_tap = ksteps * ((p.block_n / 2.0) > ((128 + p.block_n) / 4.0) ? (p.block_n / 2.0) : ((128 + p.block_n) / 4.0));
   const bool halo_ok = g_vhalo && d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1;
   const int b_all = taps * p.cchunks * p.b_tile_bytes;
+  // The plan (A mode, weight sharing) fixes the order in which taps are accumulated; it is chosen for a batch of
+  // at least 128 images so that an image's result does not depend on how many others share its launch.
+  const int n_plan = d->n < 128 ? 128 : d->n;
   TilePlan best;
   best.cost = -1;
   for (int relax = 0; relax < 2 && best.cost < 0; ++relax) {      // forced knobs that cannot fit are dropped
@@ -760,10 +763,10 @@ int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream) {
     if (g_tile_amode >= 0 && halo_ok && mode != g_tile_amode) continue;
     for (int tw = (mode == 0 ? 0 : 8); tw <= (mode == 1 ? 128 : (mode == 2 ? 8 : 0)); tw = tw ? tw * 2 : 1) {
       int gw, gh, gn;
-      if (mode == 0) pick_m_tile(d->n, Ho, Wo, d->stride, &gw, &gh, &gn);
+      if (mode == 0) pick_m_tile(n_plan, Ho, Wo, d->stride, &gw, &gh, &gn);
       else gw = tw, gh = 128 / tw, gn = 1;
       if (mode == 1 && gw > round_up(Wo, 8)) break;
-      const long long m_tiles = (long long)((Wo + gw - 1) / gw) * ((Ho + gh - 1) / gh) * ((d->n + gn - 1) / gn);
+      const long long m_tiles = (long long)((Wo + gw - 1) / gw) * ((Ho + gh - 1) / gh) * ((n_plan + gn - 1) / gn);
       const int boxes = mode == 0 ? taps : (mode == 1 ? 3 : 1);
       const int a_bytes = (mode == 0 ? gw * gh * gn : (mode == 1 ? gw * (gh + 2) : (gw + 2) * (gh + 2))) * row_bytes;
       const int a_box = round_up(a_bytes, 1024);
@@ -819,6 +822,7 @@ int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream) {
   }
   }
   B2F_REQUIRE(best.cost >= 0, "conv: no tile plan fits in shared memory (cin_p %d cout_p %d k %d)", d->cin_p, d->cout_p, d->kh);
+  if (best.mode == 0) pick_m_tile(d->n, Ho, Wo, d->stride, &best.tw, &best.th, &best.tn);   // geometry for the real batch
   p.a_mode = best.mode, p.tw = best.tw, p.th = best.th, p.tn = best.tn, p.mt = best.mt, p.groups = best.groups;
   p.b_resident = best.resident, p.stages_a = best.stages_a, p.stages_b = best.stages_b;
   p.tiles_x = (Wo + p.tw - 1) / p.tw;

@@ -1056,8 +1056,11 @@ extern "C" int b2f_conv2d(const b2f_conv_desc* d, void* stream_) {
     const double kFabric = 37.0;
     const double row_b = p.kchunk * 2.0;
     const double mma = 9.0 * p.cchunks * (p.kchunk / 16) * (p.block_n / 2.0);
-    const double def_tiles = (double)p.tiles_x * p.tiles_y * tiles_z * p.n_tiles;
-    const double def_bytes = 9.0 * p.cchunks * (p.tw * p.th * p.tn + p.block_n) * row_b;
+    const int n_plan = d->n < 128 ? 128 : d->n;      // batch-independent choice (fixes the accumulation order)
+    int ptw, pth, ptn;
+    pick_m_tile(n_plan, Ho, Wo, d->stride, &ptw, &pth, &ptn);
+    const double def_tiles = (double)((Wo + ptw - 1) / ptw) * ((Ho + pth - 1) / pth) * ((n_plan + ptn - 1) / ptn) * p.n_tiles;
+    const double def_bytes = 9.0 * p.cchunks * (ptw * pth * ptn + p.block_n) * row_b;
     const double def_time = def_tiles * (mma > def_bytes / kFabric ? mma : def_bytes / kFabric);
     const bool can_res = p.n_tiles == 1 && 9 * p.cchunks * p.b_tile_bytes <= 100 * 1024;
     double best = -1;
@@ -1065,7 +1068,7 @@ extern "C" int b2f_conv2d(const b2f_conv_desc* d, void* stream_) {
     for (int tw = 8; tw <= 128; tw <<= 1) {
       const int th = 128 / tw;
       if (tw > ((Wo + 7) & ~7)) continue;
-      const double tiles = (double)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * d->n * p.n_tiles;
+      const double tiles = (double)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * n_plan * p.n_tiles;
       const double bytes = p.cchunks * (3.0 * (th + 2) * tw + (can_res ? 0.0 : 9.0 * p.block_n)) * row_b;
       const double t = tiles * (mma > bytes / kFabric ? mma : bytes / kFabric);
       if (best < 0 || t < best) best = t, btw = tw;

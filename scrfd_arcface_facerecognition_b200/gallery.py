@@ -76,9 +76,18 @@ class Gallery:
             embeddings = torch.from_numpy(np.ascontiguousarray(embeddings, dtype=np.float32))
         f32, h16 = self._normalise(embeddings)
         start = len(self)
-        self.f32 = torch.cat([self.f32, f32])
-        self.h16 = torch.cat([self.h16, h16])
         n = f32.shape[0]
+        # rows live in capacity-doubling stores, so one-by-one enrolment (reference main.py:78-105,
+        # qdrant_manager.py:91-136) does not re-copy the gallery on every insert; f32 / h16 are views of them
+        cap = getattr(self, "_cap", 0)
+        if start + n > cap or getattr(self, "_store32", None) is None or self._store32.data_ptr() != self.f32.data_ptr():
+            cap = max(start + n, 2 * cap, 1024)
+            s32 = torch.empty((cap, self.dim), dtype=torch.float32, device=self.device)
+            s16 = torch.empty((cap, self.dim), dtype=torch_dtype(self.dtype), device=self.device)
+            s32[:start], s16[:start] = self.f32, self.h16
+            self._store32, self._store16, self._cap = s32, s16, cap
+        self._store32[start:start + n], self._store16[start:start + n] = f32, h16
+        self.f32, self.h16 = self._store32[:start + n], self._store16[:start + n]
         self.ids.extend(ids if ids is not None else range(start, start + n))
         self.payloads.extend(payloads if payloads is not None else [{} for _ in range(n)])
 
@@ -87,6 +96,8 @@ class Gallery:
         self.f32 = torch.empty((0, self.dim), dtype=torch.float32, device=self.device)
         self.h16 = torch.empty((0, self.dim), dtype=torch_dtype(self.dtype), device=self.device)
         self.ids, self.payloads = [], []
+        self._store32 = self._store16 = None
+        self._cap = 0
         self.add(embeddings)
         self.idx_base = int(idx_base)
 
@@ -97,9 +108,12 @@ class Gallery:
         self.h16[rows] = h16
 
     def remove(self, row: int) -> None:
-        keep = torch.ones(len(self), dtype=torch.bool, device=self.device)
-        keep[row] = False
-        self.f32, self.h16 = self.f32[keep].contiguous(), self.h16[keep].contiguous()
+        """Delete one row; later rows keep their order (indices above `row` shift down by one)."""
+        n = len(self)
+        if row < n - 1:
+            self.f32[row:n - 1] = self.f32[row + 1:n].clone()
+            self.h16[row:n - 1] = self.h16[row + 1:n].clone()
+        self.f32, self.h16 = self.f32[:n - 1], self.h16[:n - 1]
         del self.ids[row], self.payloads[row]
 
     def clear(self) -> None:
@@ -222,6 +236,11 @@ class Gallery:
             bufs = [torch.empty_like(padded) for _ in range(self.world_size)]
             dist.all_gather(bufs, padded, group=self.group)
             pairs = torch.sort(torch.cat([b[:int(c.item())] for b, c in zip(bufs, cnts)])).values
+        return self.resolve_pairs(pairs)
+
+    def resolve_pairs(self, pairs: torch.Tensor) -> np.ndarray:
+        """Greedy one-hop leader merge (ascending id order) over a sorted pair list -> leader[i] per row."""
+        n = len(self)
         leader = torch.empty(3 * n + 8, dtype=torch.int32, device=self.device)
         _lib.check(self.lib.b2f_cluster_resolve(pairs.data_ptr(), pairs.numel(), n, leader.data_ptr(), stream_ptr()),
                    "b2f_cluster_resolve")
