@@ -138,6 +138,11 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)
             fn.argtypes = args
             fn.restype = _RESTYPES.get(name, C.c_int)
+        # B2F_TUNE="key=value,..." applies b2f_set_tuning knobs at load (A/B runs of bench.py and the tests)
+        for item in filter(None, os.environ.get("B2F_TUNE", "").split(",")):
+            key, _, val = item.partition("=")
+            if handle.b2f_set_tuning(int(key), int(val)) != 0:
+                raise B2FError(f"B2F_TUNE: bad knob {item!r}")
         _lib = handle
     return _lib
 

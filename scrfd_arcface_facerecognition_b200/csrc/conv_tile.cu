@@ -42,6 +42,7 @@ constexpr int kTAcc = 4;
 constexpr int kTGroups = 4;
 constexpr int kStgBufs = 3;
 constexpr int kSmemMax = 227 * 1024;
+constexpr int kTileDeclined = -1000;
 
 struct TileParams {
   int N, Ho, Wo, H, W, cout_p;
@@ -52,10 +53,12 @@ struct TileParams {
   int a_mode, boxes_per_chunk, taps_per_box;
   int a_bytes, a_box_bytes, a_stage_bytes, stages_a;
   int b_tile_bytes, stages_b, b_resident;
+  int b_stride;             // bytes between weight stages; mode 0 streamed: the stage also holds its activation box(es)
+  int combined;             // 1: one barrier pair per tap covers the weight tile and the activation boxes (mode 0, streamed)
   int n_acc_log2, acc_stride;
   int groups;
   int is_bf16, debug;
-  int epi_tma, res_smem, ochunk, n_sub, stg_bytes, stg_box_bytes;
+  int epi_tma, res_smem, res_global, ochunk, n_sub, stg_bytes, stg_box_bytes, stg_bufs;
   void* out;
   int out_dtype;
   const float* bias;
@@ -179,9 +182,9 @@ __device__ __forceinline__ uint4 pack8_t(const float* f) {
 }
 
 // 16 accumulator columns -> bias (+ residual read from the staging row) -> activation -> packed into the staging row
-template <int ACT, bool BF16, bool RES>
+template <int ACT, bool BF16, int RES>
 __device__ __forceinline__ void epi_slice16(const uint32_t* r, const float* bias_c, const float* slope_c, uint4* p0,
-                                            uint4* p1, int c, int sig_hi) {
+                                            uint4* p1, int c, int sig_hi, const uint4* gres) {
   float f[16];
 #pragma unroll
   for (int v = 0; v < 4; ++v) {
@@ -191,12 +194,20 @@ __device__ __forceinline__ void epi_slice16(const uint32_t* r, const float* bias
     f[4 * v + 2] = __uint_as_float(r[4 * v + 2]) + b4.z;
     f[4 * v + 3] = __uint_as_float(r[4 * v + 3]) + b4.w;
   }
-  if (RES) {
+  if (RES == 1) {                                   // residual slice was TMA-loaded into this staging row
     float rs[16];
     unpack8_t<BF16>(*p0, rs);
     unpack8_t<BF16>(*p1, rs + 8);
 #pragma unroll
     for (int i = 0; i < 16; ++i) f[i] += rs[i];
+  } else if (RES == 2) {                            // residual straight from global memory (wide tiles)
+    if (gres != nullptr) {
+      float rs[16];
+      unpack8_t<BF16>(__ldg(gres), rs);
+      unpack8_t<BF16>(__ldg(gres + 1), rs + 8);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] += rs[i];
+    }
   }
   if (ACT == 1) {
 #pragma unroll
@@ -252,14 +263,15 @@ __device__ __forceinline__ TileCoord tile_of(const TileParams& p, int seq) {
 // cp.async.bulk.tensor store.  Staging buffers form a ring of kStgBufs per group; with a residual, the slice that
 // will be processed two steps later is TMA-loaded into its buffer first, and each thread reads / overwrites only
 // its own 16-byte pieces of it.
-template <int ACT, bool BF16, bool RES>
+template <int ACT, bool BF16, int RES>
 __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& c) {
   const int G = p.groups, n_sub = p.n_sub, och = p.ochunk, group = c.group;
   const int n_acc_mask = (1 << p.n_acc_log2) - 1;
   const uint32_t orow = (uint32_t)och * 2;                           // staging row bytes: 64 / 32
   const uint32_t swz_mask = orow == 64 ? 3u : 1u;
   const int m = c.q * 32 + c.lane;
-  const int lx = m % p.tw, ly = (m / p.tw) % p.th;
+  const int lx = m % p.tw, ly = (m / p.tw) % p.th, lz = m / (p.tw * p.th);
+  const int NB = p.stg_bufs;
   const int my_tiles = c.tiles_cta > group ? (c.tiles_cta - group + G - 1) / G : 0;
   const int total_sub = my_tiles * n_sub;
   const uint32_t row_off = (uint32_t)m * orow;
@@ -274,12 +286,12 @@ __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& 
   const int stg_bytes = p.stg_bytes, sig_hi = p.sig_hi, cout_p = p.cout_p;
   auto issue_res = [&](int s) {                                      // leader only: residual slice of sub s
     const TileCoord t = tile_of(p, group + (s / n_sub) * G);
-    const int buf = s % kStgBufs;
+    const int buf = s % NB;
     mbar_arrive_expect_tx(&c.rbar[buf], (uint32_t)p.stg_box_bytes);
     tma_load_4d(c.stg + (size_t)buf * stg_bytes, c.tmR, &c.rbar[buf], t.cbase + (s % n_sub) * och, t.x0, t.y0, t.n0);
   };
-  if (RES && c.leader)
-    for (int s = 0; s < kStgBufs - 1 && s < total_sub; ++s) issue_res(s);
+  if (RES == 1 && c.leader)
+    for (int s = 0; s < NB - 1 && s < total_sub; ++s) issue_res(s);
   int k = 0;
   for (int tl = 0; tl < my_tiles; ++tl) {
     const int seq = group + tl * G;
@@ -294,13 +306,19 @@ __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& 
     }
     const float* bias_row = c.s_bias + cls * cout_p + t.cbase;
     const float* slope_row = c.s_slope + t.cbase;
+    const uint8_t* gres_row = nullptr;
+    if (RES == 2) {
+      const int ox = t.x0 + lx, oy = t.y0 + ly, on = t.n0 + lz;
+      if (lz < p.tn && ox < p.Wo && oy < p.Ho && on < p.N)
+        gres_row = reinterpret_cast<const uint8_t*>(p.residual) + ((((size_t)on * p.Ho + oy) * p.Wo + ox) * cout_p + t.cbase) * 2;
+    }
     const int acc = seq & n_acc_mask;
     const uint32_t ph = (uint32_t)(seq >> p.n_acc_log2) & 1u;
     mbar_wait(&c.tfull[acc], ph);
     tc_fence_after();
     const uint32_t t_addr = c.tmem_base + ((uint32_t)(c.q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
     for (int j = 0; j < n_sub; ++j, ++k) {
-      const int buf = k % kStgBufs;
+      const int buf = k % NB;
       uint8_t* bufp = c.stg + (size_t)buf * stg_bytes;
       uint32_t r[32];
       if (och == 16) {
@@ -318,21 +336,22 @@ __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& 
         __syncwarp();
         if (c.lane == 0) mbar_arrive(&c.tempty[acc]);
       }
-      if (RES) mbar_wait(&c.rbar[buf], (uint32_t)(k / kStgBufs) & 1u);
+      if (RES == 1) mbar_wait(&c.rbar[buf], (uint32_t)(k / NB) & 1u);
       if (!skip_math) {
         const int cl = j * och;
+        const uint4* g0 = (RES == 2 && gres_row) ? reinterpret_cast<const uint4*>(gres_row + cl * 2) : nullptr;
         epi_slice16<ACT, BF16, RES>(r, bias_row + cl, slope_row + cl, reinterpret_cast<uint4*>(bufp + off[0]),
-                                    reinterpret_cast<uint4*>(bufp + off[1]), t.cbase + cl, sig_hi);
+                                    reinterpret_cast<uint4*>(bufp + off[1]), t.cbase + cl, sig_hi, g0);
         if (och == 32)
           epi_slice16<ACT, BF16, RES>(r + 16, bias_row + cl + 16, slope_row + cl + 16, reinterpret_cast<uint4*>(bufp + off[2]),
-                                      reinterpret_cast<uint4*>(bufp + off[3]), t.cbase + cl + 16, sig_hi);
+                                      reinterpret_cast<uint4*>(bufp + off[3]), t.cbase + cl + 16, sig_hi, g0 ? g0 + 2 : nullptr);
       }
       fence_proxy_async();
       if (c.leader) {
         // the store issued one slice ago has had this slice's arithmetic to leave its buffer; once it has, the
         // residual of the slice two steps ahead may land there
         bulk_wait_read0();
-        if (RES && k + kStgBufs - 1 < total_sub) issue_res(k + kStgBufs - 1);
+        if (RES == 1 && k + NB - 1 < total_sub) issue_res(k + NB - 1);
       }
       bar_sync_named(1 + group, 128);
       if (c.leader && !skip_store) {
@@ -369,8 +388,9 @@ __device__ __forceinline__ void mma_issuer(const TileParams& p, const MmaCtx& c)
   const uint32_t sbo = MODE == 2 ? (uint32_t)box_w * row_bytes : 8u * row_bytes;
   const uint64_t a_desc0 = umma_smem_desc_sbo(c.a_ring, row_bytes, sbo);
   const uint64_t b_desc0 = umma_smem_desc(c.b_base, row_bytes);
-  const uint64_t a_inc = (uint64_t)(p.a_stage_bytes >> 4), b_inc = (uint64_t)(p.b_tile_bytes >> 4);
+  const uint64_t a_inc = (uint64_t)(p.a_stage_bytes >> 4), b_inc = (uint64_t)(p.b_stride >> 4);
   const uint64_t u_inc = (uint64_t)(p.a_box_bytes >> 4);
+  const uint64_t a_in_b = umma_smem_desc(c.b_base + (uint32_t)p.b_tile_bytes, row_bytes);   // combined stages
   const uint64_t r_inc = (uint64_t)(((uint32_t)box_w * row_bytes) >> 4);       // one row of the box
   const uint64_t s_inc = (uint64_t)(row_bytes >> 4);                             // one pixel
   const bool do_mma = !(p.debug & 4);
@@ -395,6 +415,25 @@ __device__ __forceinline__ void mma_issuer(const TileParams& p, const MmaCtx& c)
     const uint32_t d0 = tmem_base + (uint32_t)acc0 * acc_stride, d1 = tmem_base + (uint32_t)acc1 * acc_stride;
     uint64_t bd = b_desc0;                               // resident weights: consumed in load order
     for (int g = 0; g < groups_per_item; ++g) {
+      if (MODE == 0 && !RES) {
+        // combined stage: weight tile + activation box(es) behind one barrier pair
+        mbar_wait(&fullB[sb], pb);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t off = b_inc * (uint64_t)sb;
+          if (do_mma) {
+            issue_stage<KSTEPS>(d0, a_in_b + off, b_desc0 + off, idesc, (uint32_t)(g != 0));
+            if (MT == 2) issue_stage<KSTEPS>(d1, a_in_b + off + u_inc, b_desc0 + off, idesc, (uint32_t)(g != 0));
+          }
+          umma_commit(&emptyB[sb]);
+          if (g == groups_per_item - 1) {
+            umma_commit(&tfull[acc0]);
+            if (MT == 2) umma_commit(&tfull[acc1]);
+          }
+        }
+        if (++sb == stages_b) sb = 0, pb ^= 1;
+        continue;
+      }
       mbar_wait(&fullA[sa], pa);
       tc_fence_after();
       const uint64_t ad = a_desc0 + a_inc * (uint64_t)sa;
@@ -522,19 +561,25 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (resident) {
         mbar_arrive_expect_tx(bres, b_bytes * (uint32_t)(cchunks * boxes * tpb));
         uint8_t* dst = b_base;
-        for (int cc = 0; cc < cchunks; ++cc)
-          for (int b = 0; b < boxes; ++b)
-            for (int j = 0; j < tpb; ++j, dst += b_tile_bytes) {
-              const int tap = mode == 0 ? b : (mode == 1 ? j * 3 + b : (j % 3) * 3 + j / 3);
-              tma_load_3d(dst, &tmB, bres, cc * kchunk, 0, tap);
-            }
+        if (mode == 0) {
+          for (int b = 0; b < boxes; ++b)                          // consumption order: tap-major, channel chunks inner
+            for (int cc = 0; cc < cchunks; ++cc, dst += b_tile_bytes) tma_load_3d(dst, &tmB, bres, cc * kchunk, 0, b);
+        } else {
+          for (int cc = 0; cc < cchunks; ++cc)
+            for (int b = 0; b < boxes; ++b)
+              for (int j = 0; j < tpb; ++j, dst += b_tile_bytes) {
+                const int tap = mode == 1 ? j * 3 + b : (j % 3) * 3 + j / 3;
+                tma_load_3d(dst, &tmB, bres, cc * kchunk, 0, tap);
+              }
+        }
       }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       // boxes of one channel chunk as a (dy, dx) grid, weight taps of one box as (sxi, r): no division per stage
       const int nbx = mode == 0 ? kw : (mode == 1 ? 3 : 1), nby = mode == 0 ? p.kh : 1;
       const int nsx = mode == 2 ? 3 : 1, nr = mode == 0 ? 1 : 3;
-      const bool skip_a = (p.debug & 8) != 0;
+      const bool skip_a = (p.debug & 8) != 0, combined = p.combined != 0;
+      const int b_stride = p.b_stride;
       for (int i = blockIdx.x; i < p.items; i += gridDim.x) {
         const int nt = i % n_tiles, mp = i / n_tiles;
         const int nrow = nt * block_n;
@@ -543,10 +588,28 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int an0 = (m0 / tiles_xy) * p.tn;
         const int ax1 = (m1 % tiles_x) * sx_scale - org, ay1 = ((m1 / tiles_x) % tiles_y) * sy_scale - org;
         const int an1 = (m1 / tiles_xy) * p.tn;
-        for (int cc = 0; cc < cchunks; ++cc) {
-          const int c0 = cc * kchunk;
-          for (int dy = 0; dy < nby; ++dy) {
-            for (int dx = 0; dx < nbx; ++dx) {
+        // mode 0 walks taps outer / channel chunks inner (the accumulation order of the first persistent kernel, so
+        // either kernel yields the same bits); the halo modes walk chunks outer / boxes inner
+        const int n_outer = mode == 0 ? nby * nbx : cchunks, n_inner = mode == 0 ? cchunks : nbx;
+        int dy = 0, dx = 0;
+        for (int o = 0; o < n_outer; ++o) {
+          for (int in = 0; in < n_inner; ++in) {
+            const int c0 = (mode == 0 ? in : o) * kchunk;
+            if (mode != 0) dx = in;
+            {
+              if (combined) {
+                // mode 0, streamed weights: one stage = weight tile + activation box(es), one barrier pair per tap
+                mbar_wait(&emptyB[sb], pb ^ 1);
+                uint8_t* dst = b_base + (size_t)sb * b_stride;
+                mbar_arrive_expect_tx(&fullB[sb], skip_a ? b_bytes : b_bytes + a_tx);
+                if (!skip_a) {
+                  tma_load_4d(dst + b_tile_bytes, &tmA, &fullB[sb], c0, ax0 + dx, ay0 + dy, an0);
+                  if (mt == 2) tma_load_4d(dst + b_tile_bytes + a_box_bytes, &tmA, &fullB[sb], c0, ax1 + dx, ay1 + dy, an1);
+                }
+                tma_load_3d(dst, &tmB, &fullB[sb], c0, nrow, dy * kw + dx);
+                if (++sb == stages_b) sb = 0, pb ^= 1;
+                continue;
+              }
               mbar_wait(&emptyA[sa], pa ^ 1);
               if (skip_a) {
                 mbar_arrive(&fullA[sa]);
@@ -560,16 +623,17 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (!resident) {
                 for (int sxi = 0; sxi < nsx; ++sxi) {
                   for (int r = 0; r < nr; ++r) {
-                    const int tap = mode == 0 ? dy * kw + dx : r * 3 + dx + sxi;
+                    const int tap = r * 3 + dx + sxi;            // halo modes only (mode 0 streamed is combined)
                     mbar_wait(&emptyB[sb], pb ^ 1);
                     mbar_arrive_expect_tx(&fullB[sb], b_bytes);
-                    tma_load_3d(b_base + (size_t)sb * b_tile_bytes, &tmB, &fullB[sb], c0, nrow, tap);
+                    tma_load_3d(b_base + (size_t)sb * b_stride, &tmB, &fullB[sb], c0, nrow, tap);
                     if (++sb == stages_b) sb = 0, pb ^= 1;
                   }
                 }
               }
             }
           }
+          if (mode == 0 && ++dx == nbx) dx = 0, ++dy;
         }
       }
     }
@@ -615,15 +679,17 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (p.epi_tma) {
       EpiCtx c;
       c.tmem_base = tmem_base, c.tfull = tfull, c.tempty = tempty, c.rbar = rbar + group * kStgBufs;
-      c.stg = stg_base + (size_t)group * kStgBufs * p.stg_bytes;
+      c.stg = stg_base + (size_t)group * p.stg_bufs * p.stg_bytes;
       c.s_bias = s_bias, c.s_slope = s_slope, c.tmO = &tmO, c.tmR = &tmR;
       c.tiles_cta = tiles_cta, c.group = group, c.q = q, c.lane = lane, c.leader = leader;
-      const int variant = p.act * 4 + (p.is_bf16 ? 2 : 0) + (p.res_smem ? 1 : 0);
+      const int variant = p.act * 6 + (p.is_bf16 ? 3 : 0) + (p.res_smem ? 1 : (p.res_global ? 2 : 0));
 #define B2F_EPI_CASE(ACT)                                                   \
-      case ACT * 4 + 0: epilogue_tma<ACT, false, false>(p, c); break;         \
-      case ACT * 4 + 1: epilogue_tma<ACT, false, true>(p, c); break;          \
-      case ACT * 4 + 2: epilogue_tma<ACT, true, false>(p, c); break;          \
-      case ACT * 4 + 3: epilogue_tma<ACT, true, true>(p, c); break;
+      case ACT * 6 + 0: epilogue_tma<ACT, false, 0>(p, c); break;             \
+      case ACT * 6 + 1: epilogue_tma<ACT, false, 1>(p, c); break;             \
+      case ACT * 6 + 2: epilogue_tma<ACT, false, 2>(p, c); break;             \
+      case ACT * 6 + 3: epilogue_tma<ACT, true, 0>(p, c); break;              \
+      case ACT * 6 + 4: epilogue_tma<ACT, true, 1>(p, c); break;              \
+      case ACT * 6 + 5: epilogue_tma<ACT, true, 2>(p, c); break;
       switch (variant) {
         B2F_EPI_CASE(0)
         B2F_EPI_CASE(1)
@@ -703,10 +769,12 @@ void pick_m_tile(int N, int Ho, int Wo, int stride, int* tw, int* th, int* tn); 
 
 struct TilePlan {
   int mode, tw, th, tn, mt, groups, resident, stages_a, stages_b;
+  long long m_tiles_plan;
   double cost;
 };
 
-int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream) {
+// returns kTileDeclined (nothing launched) when `optional` and the first persistent kernel is the better fit
+int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream, int optional) {
   if (g_sms == 0) {
     int dev = 0;
     B2F_CHECK_CUDA(cudaGetDevice(&dev));
@@ -735,22 +803,28 @@ int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream) {
   p.res_h = d->res_h, p.res_w = d->res_w;
 
   // ---- epilogue flavour -------------------------------------------------------------------------------
-  // wide tiles (N > 128) keep every byte of shared memory for the operand rings: their epilogue hides behind the MMAs
-  p.epi_tma = (d->out_dtype == d->dtype && p.res_mode != 2 && (p.block_n <= 128 || g_tile_epi == 1)) ? 1 : 0;
+  // TMA-store epilogue whenever the output has the activation dtype.  Narrow tiles: 32-channel slices, a ring of
+  // three per group, residual prefetched into the ring by TMA.  Wide tiles (N > 128) need the shared memory for
+  // four operand stages: 16-channel slices, a ring of two, residual read straight from global memory.
+  p.epi_tma = (d->out_dtype == d->dtype && p.res_mode != 2) ? 1 : 0;
   if (g_tile_epi >= 0) p.epi_tma = p.epi_tma && g_tile_epi;
   if (p.epi_tma) {
-    p.ochunk = (p.block_n % 32 == 0) ? 32 : 16;
+    const bool wide = p.block_n > 128;
+    p.ochunk = (!wide && p.block_n % 32 == 0) ? 32 : 16;
     p.n_sub = p.block_n / p.ochunk;
     p.stg_bytes = round_up(128 * p.ochunk * 2, 1024);
-    p.res_smem = p.res_mode == 1 ? 1 : 0;
+    p.stg_bufs = wide ? 2 : 3;
+    p.res_smem = (p.res_mode == 1 && !wide) ? 1 : 0;
+    p.res_global = (p.res_mode == 1 && wide) ? 1 : 0;
   }
   const int tab_bytes = round_up((p.bias_classes + 1) * p.cout_p * 4, 256);
   const int fixed = 1024 /*align*/ + 1024 /*barriers*/ + tab_bytes;
 
   // ---- choose A mode, tile geometry, weight sharing and epilogue groups with a per-tile cycle model -----------
-  const double kFabric = 40.0;                               // L2 -> SM bytes per clock per SM (measured ~37-42)
+  const double kFabric = 64.0;                               // L2 -> SM bytes per clock per SM the rings can pull (measured 50-65)
   const double mma_tap = ksteps * ((p.block_n / 2.0) > ((128 + p.block_n) / 4.0) ? (p.block_n / 2.0) : ((128 + p.block_n) / 4.0));
-  const bool halo_ok = g_vhalo && d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1;
+  // halo modes only for narrow tiles: wide ones keep one accumulation order across both kernel generations
+  const bool halo_ok = g_vhalo && d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && p.block_n <= 128;
   const int b_all = taps * p.cchunks * p.b_tile_bytes;
   // The plan (A mode, weight sharing) fixes the order in which taps are accumulated; it is chosen for a batch of
   // at least 128 images so that an image's result does not depend on how many others share its launch.
@@ -777,13 +851,18 @@ int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream) {
         for (int groups = 4; groups >= 2; groups -= 2) {
           if (groups > (1 << p.n_acc_log2)) continue;          // a group must never be a whole accumulator phase ahead
           if (f_groups && groups != f_groups && f_groups <= (1 << p.n_acc_log2)) continue;
-          const int staging = p.epi_tma ? groups * kStgBufs * p.stg_bytes : 0;
+          const int staging = p.epi_tma ? groups * p.stg_bufs * p.stg_bytes : 0;
           int avail = kSmemMax - fixed - staging;
           int stages_a = 0, stages_b = 0;
           const int tpb = taps / boxes;
           if (resident) {
             stages_a = (avail - b_all) / (mt * a_box);
             if (stages_a > kTStages) stages_a = kTStages;
+          } else if (mode == 0) {
+            // combined stages: weight tile + activation box(es) per tap behind one barrier pair
+            stages_b = avail / (p.b_tile_bytes + mt * a_box);
+            if (stages_b > kTStages) stages_b = kTStages;
+            stages_a = stages_b;
           } else {
             // s weight tiles in flight, and the activation boxes that feed them (one box serves tpb taps)
             for (int sb = kTStages; sb >= 2 && !stages_b; --sb) {
@@ -814,6 +893,7 @@ int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream) {
           if (best.cost < 0 || cost < best.cost) {
             best.cost = cost, best.mode = mode, best.tw = gw, best.th = gh, best.tn = gn, best.mt = mt;
             best.groups = groups, best.resident = resident, best.stages_a = stages_a, best.stages_b = stages_b;
+            best.m_tiles_plan = m_tiles;
           }
         }
       }
@@ -829,6 +909,10 @@ int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream) {
   p.tiles_y = (Ho + p.th - 1) / p.th;
   p.m_tiles = p.tiles_x * p.tiles_y * ((d->n + p.tn - 1) / p.tn);
   p.items = n_tiles * ((p.m_tiles + p.mt - 1) / p.mt);
+  // wide tiles have two accumulators and two epilogue groups: with only a few tiles per SM the exposed epilogue of
+  // the last tile costs more than the first persistent kernel's column-split epilogue
+  // (both kernels accumulate wide tiles in the same order, so this batch-dependent choice does not change results)
+  if (optional && p.block_n > 128 && p.items < 8 * g_sms) return kTileDeclined;
   p.boxes_per_chunk = p.a_mode == 0 ? taps : (p.a_mode == 1 ? 3 : 1);
   p.taps_per_box = taps / p.boxes_per_chunk;
   const int box_w = p.a_mode == 0 ? p.tw * d->stride : (p.a_mode == 1 ? p.tw : p.tw + 2);
@@ -837,9 +921,12 @@ int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream) {
   p.a_box_bytes = round_up(p.a_bytes, 1024);
   p.a_stage_bytes = p.a_box_bytes * p.mt;
   p.stg_box_bytes = p.tw * p.th * p.tn * p.ochunk * 2;
+  p.combined = (p.a_mode == 0 && !p.b_resident) ? 1 : 0;
+  p.b_stride = p.combined ? p.b_tile_bytes + p.a_stage_bytes : p.b_tile_bytes;
+  if (p.combined) p.stages_a = 0;                      // activation boxes live inside the weight stages
   p.off_b = p.stages_a * p.a_stage_bytes;
-  p.off_stg = p.off_b + (p.b_resident ? b_all : p.stages_b * p.b_tile_bytes);
-  p.off_bar = p.off_stg + (p.epi_tma ? p.groups * kStgBufs * p.stg_bytes : 0);
+  p.off_stg = p.off_b + (p.b_resident ? b_all : p.stages_b * p.b_stride);
+  p.off_bar = p.off_stg + (p.epi_tma ? p.groups * p.stg_bufs * p.stg_bytes : 0);
   p.off_tab = p.off_bar + 1024;
   size_t smem = (size_t)p.off_tab + tab_bytes + 1024;
   B2F_REQUIRE(smem <= (size_t)kSmemMax, "conv tile kernel: %zu bytes of shared memory requested", smem);
@@ -885,9 +972,9 @@ int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream) {
   static const bool trace = getenv("B2F_PLAN_TRACE") != nullptr;
   if (trace)
     fprintf(stderr, "[b2f plan] n%d %dx%d %d->%d k%d s%d: mode %d tile %dx%dx%d mt %d groups %d resident %d stagesA %d stagesB %d "
-            "block_n %d kchunk %d epi_tma %d res_smem %d smem %zu items %d\n", d->n, d->h, d->w, d->cin_p, d->cout_p, d->kh, d->stride,
+            "block_n %d kchunk %d epi_tma %d res_smem %d ochunk %d bufs %d smem %zu items %d\n", d->n, d->h, d->w, d->cin_p, d->cout_p, d->kh, d->stride,
             p.a_mode, p.tw, p.th, p.tn, p.mt, p.groups, p.b_resident, p.stages_a, p.stages_b, p.block_n, kchunk, p.epi_tma,
-            p.res_smem, smem, p.items);
+            p.res_smem, p.ochunk, p.stg_bufs, smem, p.items);
   const int grid = p.items < g_sms ? p.items : g_sms;
   conv_tile_kernel<<<grid, 64 + 128 * p.groups, smem, stream>>>(tmA, tmB, tmO, tmR, p);
   g_launches.fetch_add(1);

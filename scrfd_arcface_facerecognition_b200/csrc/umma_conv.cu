@@ -905,7 +905,8 @@ static int launch_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaParam
 }
 
 int g_persistent = 2;     // 0: one CTA per tile, 1: first persistent kernels, 2: conv_tile_kernel (conv_tile.cu)
-int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream);
+int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream, int optional);
+int g_tile_max_n = 256;
 int g_num_sms = 0;
 
 static int launch_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaParams& p, int m_tiles,
@@ -1019,12 +1020,11 @@ extern "C" int b2f_conv2d(const b2f_conv_desc* d, void* stream_) {
   p.kchunk = d->force_kchunk ? d->force_kchunk : pick_kchunk(d->cin_p);
   B2F_REQUIRE(d->cin_p % p.kchunk == 0, "b2f_conv2d: kchunk %d does not divide cin_p %d", p.kchunk, d->cin_p);
   B2F_REQUIRE(d->act != 2 || d->slope != nullptr, "b2f_conv2d: PReLU needs a slope vector");
-  {
-    // conv_tile_kernel (halo boxes, shared weight tiles, TMA-store epilogue) wins wherever a tile is at most 128
-    // channels wide; wider tiles are tensor-pipe bound already and keep the first persistent kernel
-    int nt = (d->cout_p + g_max_block_n - 1) / g_max_block_n;
-    while ((d->cout_p % nt) != 0 || ((d->cout_p / nt) % 16) != 0) ++nt;
-    if (g_persistent == 3 || (g_persistent == 2 && d->cout_p / nt <= 128)) return conv_tile_launch(d, p.kchunk, stream);
+  if (g_persistent >= 2) {
+    // conv_tile_kernel (halo boxes, shared weight tiles, TMA-store epilogue) unless it declines a wide-tile layer
+    // with too few tiles per SM; g_persistent == 3 forces it
+    const int rc = conv_tile_launch(d, p.kchunk, stream, g_persistent == 2);
+    if (rc != -1000) return rc;
   }
   p.cchunks = d->cin_p / p.kchunk;
   pick_m_tile(d->n, Ho, Wo, d->stride, &p.tw, &p.th, &p.tn);
@@ -1050,7 +1050,9 @@ extern "C" int b2f_conv2d(const b2f_conv_desc* d, void* stream_) {
 
   // ---- vertical-halo variant: 3x3 / stride 1 / pad 1 on maps wide enough for 8-pixel-aligned tiles ----------
   bool vhalo = false;
-  if (g_persistent && g_vhalo && d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && Wo >= 8 && Ho >= 2) {
+  // under the default dispatch only wide tiles arrive here, and they keep the tap-major order of the persistent
+  // kernel (conv_tile_kernel's mode 0 uses the same one), so the vertical-halo variant is for g_persistent == 1
+  if (g_persistent == 1 && g_vhalo && d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && Wo >= 8 && Ho >= 2) {
     // per-tile time model (cycles): tensor pipe = N/2 per 128xNx16 MMA; L2->SM fabric ~37 B/clk/SM (measured:
     // ~10.4 TB/s over 148 SMs on the 256-channel layers, which is what bounds them)
     const double kFabric = 37.0;

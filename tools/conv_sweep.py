@@ -29,7 +29,7 @@ VARIANTS = {
 DEFAULTS = {2: 2, 3: 1, 4: 0, 5: 0, 6: 0, 7: -1, 8: -1}
 
 
-def bench(lib, shape, reps=10):
+def bench(lib, shape, reps=30):
     n, h, w, cin, cout, k, stride, act, res, bias9 = shape
     pad = k // 2 if k == 3 else 0
     ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
@@ -49,7 +49,7 @@ def bench(lib, shape, reps=10):
     if res:
         d.residual, d.res_mode = r.data_ptr(), 1
     sp = torch.cuda.current_stream().cuda_stream
-    for _ in range(2):
+    for _ in range(6):
         _lib.check(lib.b2f_conv2d(C.byref(d), sp))
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
