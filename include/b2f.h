@@ -52,6 +52,11 @@ int b2f_letterbox_u8(const uint8_t* frames, int batch, int h, int w, int new_w, 
  * replaces reference models/scrfd.py:135-138 + cv2.dnn.blobFromImage at :76-82. */
 int b2f_preprocess(const uint8_t* frames, int batch, int h, int w, int new_w, int new_h, int in_w, int in_h,
                    float mean, float scale, void* out_nhwc, int c_pad, int dtype, void* stream);
+/* same, fused with the 3x3 / pad 1 patch extraction of the detector's first convolution: writes
+ * [batch][ho][wo][32] patches (k = tap*3 + rgb) that b2f_conv2d consumes as a 1x1 convolution; bit-identical to
+ * b2f_preprocess followed by b2f_im2col3x3 (reference models/scrfd.py:76-83, 135-138) */
+int b2f_preprocess_patches(const uint8_t* frames, int batch, int h, int w, int new_w, int new_h, int in_w, int in_h,
+                           int stride, float mean, float scale, void* out_patches, int dtype, void* stream);
 
 /* ---- a3 exact: u8 BGR HWC -> fp32 NCHW RGB blob, (float(x)-mean)*scale, bit-exact vs
  * cv2.dnn.blobFromImage(s) (reference models/scrfd.py:76-82, models/arcface.py:44-50). */
@@ -102,6 +107,11 @@ int b2f_warp_affine_u8(const uint8_t* frames, int h, int w, const int* frame_idx
 int b2f_norm_crop(const uint8_t* frames, int h, int w, const int* frame_idx, const float* landmarks, int faces,
                   int size, float mean, float scale, void* out_nhwc, int c_pad, int dtype,
                   uint8_t* crop_u8 /*may be null*/, double* m_out /*may be null*/, void* stream);
+/* norm_crop fused with normalisation and the 3x3 / pad 1 / stride 1 patch extraction of ArcFace's first convolution:
+ * writes [faces][112][112][32] patches; bit-identical to b2f_norm_crop followed by b2f_im2col3x3
+ * (reference utils/helpers.py:18-59, models/arcface.py:44-57) */
+int b2f_norm_crop_patches(const uint8_t* frames, int h, int w, const int* frame_idx, const float* landmarks, int faces,
+                          int size, float mean, float scale, void* out_patches, int dtype, void* stream);
 
 /* ---- a4 / a15: convolution layers of the detector / embedder ------------------------------------
  * replaces onnxruntime session.run at reference models/scrfd.py:83 and models/arcface.py:51.

@@ -79,6 +79,7 @@ SIGNATURES = {
     "b2f_set_tuning": [_i, _i],
     "b2f_letterbox_u8": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "b2f_preprocess": [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _i, _i, _vp],
+    "b2f_preprocess_patches": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _i, _vp],
     "b2f_blob_nchw_f32": [_vp, _i, _i, _i, _f, _f, _vp, _vp],
     "b2f_decode_nms": [C.POINTER(DetLevels), _i, _i, _i, _vp, _vp, _f, _f, _i, _i, _i, _i, _vp, _vp, _vp, _vp,
                        _vp, _ll, _vp],
@@ -89,6 +90,7 @@ SIGNATURES = {
     "b2f_estimate_norm": [_vp, _i, _i, _vp, _vp],
     "b2f_warp_affine_u8": [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp],
     "b2f_norm_crop": [_vp, _i, _i, _vp, _vp, _i, _i, _f, _f, _vp, _i, _i, _vp, _vp, _vp],
+    "b2f_norm_crop_patches": [_vp, _i, _i, _vp, _vp, _i, _i, _f, _f, _vp, _i, _vp],
     "b2f_conv2d": [C.POINTER(ConvDesc), _vp],
     "b2f_stem_conv3x3": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "b2f_im2col3x3": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],

@@ -49,6 +49,7 @@ class ArcFace:
         w, h = self.input_size
         self._engine = NetEngine(compile_graph(graph, (h, w)))
         self._scale = float(np.float32(1.0 / self.input_std))   # blobFromImages multiplies by float32(1/std)
+        self.fuse_stem = True
         if session is None:
             self.session = self                                  # keeps `recognizer.session` truthy for callers
 
@@ -100,6 +101,14 @@ class ArcFace:
         with self._lock:
             f = int(frame_idx.shape[0])
             w, h = self.input_size
+            patches = self._engine.patch_buffer(f) if (self.fuse_stem and crops_u8 is None and w == h == 112) else None
+            if patches is not None and patches[1] == 1:
+                # norm_crop + blob + first-layer patch extraction in one kernel (one CTA per face)
+                _lib.check(self._lib.b2f_norm_crop_patches(
+                    frames.data_ptr(), frames.shape[1], frames.shape[2], frame_idx.data_ptr(),
+                    kps.reshape(f, 10).contiguous().data_ptr(), f, w, float(self.input_mean), self._scale,
+                    patches[0].data_ptr(), self._engine.dtype, stream_ptr()), "b2f_norm_crop_patches")
+                return self._engine.run(f, start=1)[self.output_names[0]].reshape(f, -1)
             x = self._engine.input_buffer(f)
             _lib.check(self._lib.b2f_norm_crop(
                 frames.data_ptr(), frames.shape[1], frames.shape[2], frame_idx.data_ptr(),

@@ -244,6 +244,52 @@ pool_kernel(const uint16_t* __restrict__ in, int n, int h, int w, int c_p, int k
 }
 
 
+
+// max-pool k x k on packed 16-bit pairs (max is exact in any format), one thread per (output pixel, 8 channels);
+// grid (pieces of one output row, output rows, batch): 32-bit index arithmetic only
+constexpr int kPoolRows = 8;
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+maxpool_rows_kernel(const uint16_t* __restrict__ in, int h, int w, int c_p, int k, int stride, int pad, int ho, int wo,
+                    uint16_t* __restrict__ out) {
+  const int groups = c_p >> 3;
+  const int b = blockIdx.z;
+  // a CTA walks kPoolRows consecutive output rows: the input rows two neighbouring output rows share are re-read
+  // from L1 / L2 by the same CTA instead of from DRAM by another one
+  for (int oy = blockIdx.y * kPoolRows; oy < ho && oy < (blockIdx.y + 1) * kPoolRows; ++oy)
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < wo * groups; t += gridDim.x * blockDim.x) {
+    const int ox = t / groups, cg = t - ox * groups;
+    uint4 acc;
+    bool first = true;
+    for (int r = 0; r < k; ++r) {
+      const int iy = oy * stride + r - pad;
+      if (iy < 0 || iy >= h) continue;
+      const uint16_t* row = in + ((size_t)(b * h + iy) * w) * c_p + cg * 8;
+      for (int s = 0; s < k; ++s) {
+        const int ix = ox * stride + s - pad;
+        if (ix < 0 || ix >= w) continue;
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(row + (size_t)ix * c_p));
+        if (first) {
+          acc = q;
+          first = false;
+        } else if (BF16) {
+          __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&acc);
+          const __nv_bfloat162* v = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[i] = __hmax2(a[i], v[i]);
+        } else {
+          __half2* a = reinterpret_cast<__half2*>(&acc);
+          const __half2* v = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[i] = __hmax2(a[i], v[i]);
+        }
+      }
+    }
+    if (first) acc = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(out + ((size_t)(b * ho + oy) * wo + ox) * c_p + cg * 8) = acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // generic per-channel affine + add + activation (fallback for graph nodes no conv absorbed)
 // ------------------------------------------------------------------------------------------
@@ -495,6 +541,18 @@ extern "C" int b2f_pool(const void* in, int n, int h, int w, int c_p, int k, int
                         int wo, int dtype, void* out, void* stream) {
   B2F_REQUIRE(c_p % 8 == 0, "b2f_pool: channels must be padded to 8");
   const long long total = (long long)n * ho * wo * (c_p / 8);
+  if (mode == 0 && ho <= 65535 && n <= 65535 && n > 0) {
+    const dim3 grid((wo * (c_p / 8) + 255) / 256, (ho + kPoolRows - 1) / kPoolRows, n);
+    if (dtype == B2F_BF16)
+      maxpool_rows_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint16_t*>(in), h, w, c_p, k,
+                                                                       stride, pad, ho, wo, reinterpret_cast<uint16_t*>(out));
+    else
+      maxpool_rows_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint16_t*>(in), h, w, c_p, k,
+                                                                        stride, pad, ho, wo, reinterpret_cast<uint16_t*>(out));
+    g_launches.fetch_add(1);
+    B2F_LAUNCH_CHECK();
+    return 0;
+  }
   pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint16_t*>(in), n, h, w,
                                                                      c_p, k, stride, pad, mode, ho, wo,
                                                                      dtype == B2F_BF16, reinterpret_cast<uint16_t*>(out));

@@ -17,7 +17,8 @@ extern std::atomic<long long> g_launches;
 // ============================================================================================
 struct ResizeGeom {
   int H, W, new_w, new_h, in_w, in_h;
-  int mode;  // 0 copy, 1 exact-2x area average, 2 fixed-point bilinear
+  int mode;  // 0 copy, 1 exact-2x area average, 2 fixed-point bilinear, 3 odd integer ratio (bilinear weights collapse)
+  int ratio;
   double scale_x, scale_y;
 };
 
@@ -58,6 +59,12 @@ __device__ __forceinline__ void letterbox_pixel(const uint8_t* __restrict__ img,
     const uint8_t* p1 = p0 + (size_t)g.W * 3;
 #pragma unroll
     for (int c = 0; c < 3; ++c) bgr[c] = (p0[c] + p0[3 + c] + p1[c] + p1[3 + c] + 2) >> 2;
+  } else if (g.mode == 3) {
+    // odd integer ratio r: the source coordinate (d + 0.5) r - 0.5 = r d + (r - 1) / 2 is an integer, the fixed-point
+    // weights are (2048, 0) and cv2's INTER_LINEAR returns that pixel exactly (1080p -> 640 x 360 is img[1::3, 1::3])
+    const int o = (g.ratio - 1) >> 1;
+    const uint8_t* p = img + ((size_t)(y * g.ratio + o) * g.W + (x * g.ratio + o)) * 3;
+    bgr[0] = p[0], bgr[1] = p[1], bgr[2] = p[2];
   } else {
     int x0, x1, a0, a1, y0, y1, b0, b1;
     linear_coeff(x, g.scale_x, g.W, true, x0, x1, a0, a1);
@@ -111,14 +118,74 @@ __global__ void letterbox_kernel(const uint8_t* __restrict__ frames, ResizeGeom 
   }
 }
 
+
+// letterbox + normalise + 3x3 / pad 1 patch extraction in one pass: out [b][ho][wo][32], k = tap*3 + rgb (27 used).
+// A CTA owns a 32 x 8 tile of output pixels: it evaluates the letterboxed source pixels the tile touches ONCE into
+// shared memory (uint8 BGR + an inside-the-canvas flag), then every thread assembles the 27 values of its pixel.
+// Taps outside the in_h x in_w canvas are the convolution's zero padding; the letterbox pad inside it is a real
+// (normalised) zero pixel, as in the reference blob (models/scrfd.py:76-82, 135-138).
+constexpr int kLpW = 32, kLpH = 8;
+__device__ __forceinline__ uint16_t norm16(int u8v, float mean, float scale, int is_bf16) {
+  const float f = __fmul_rn(__fsub_rn((float)u8v, mean), scale);
+  if (is_bf16) {
+    __nv_bfloat16 t = __float2bfloat16_rn(f);
+    return *reinterpret_cast<uint16_t*>(&t);
+  }
+  __half t = __float2half_rn(f);
+  return *reinterpret_cast<uint16_t*>(&t);
+}
+
+__global__ void __launch_bounds__(kLpW * kLpH)
+letterbox_patches_kernel(const uint8_t* __restrict__ frames, ResizeGeom g, int stride, int ho, int wo, float mean,
+                         float scale, uint16_t* __restrict__ out, int is_bf16) {
+  constexpr int kMaxIw = kLpW * 2 + 1, kMaxIh = kLpH * 2 + 1;
+  __shared__ uint8_t tile[kMaxIh * kMaxIw * 4];                      // b, g, r, inside flag
+  const int b = blockIdx.z, ox0 = blockIdx.x * kLpW, oy0 = blockIdx.y * kLpH;
+  const int iw = (kLpW - 1) * stride + 3, ih = (kLpH - 1) * stride + 3;
+  const int ix0 = ox0 * stride - 1, iy0 = oy0 * stride - 1;
+  const uint8_t* img = frames + (size_t)b * g.H * g.W * 3;
+  for (int t = threadIdx.x; t < iw * ih; t += blockDim.x) {
+    const int ty = t / iw, tx = t - ty * iw;
+    const int iy = iy0 + ty, ix = ix0 + tx;
+    int bgr[3] = {0, 0, 0};
+    const bool inside = iy >= 0 && iy < g.in_h && ix >= 0 && ix < g.in_w;
+    if (inside) letterbox_pixel(img, g, ix, iy, bgr);
+    *reinterpret_cast<uchar4*>(tile + t * 4) = make_uchar4((unsigned char)bgr[0], (unsigned char)bgr[1],
+                                                           (unsigned char)bgr[2], inside ? 1 : 0);
+  }
+  __syncthreads();
+  // emission: one thread per output pixel (27 values from the tile; measured faster than piece-per-lane coalescing)
+  const int lx = threadIdx.x % kLpW, ly = threadIdx.x / kLpW;
+  const int ox = ox0 + lx, oy = oy0 + ly;
+  if (ox >= wo || oy >= ho) return;
+  uint16_t v[32];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const uchar4 px = *reinterpret_cast<const uchar4*>(tile + ((ly * stride + tap / 3) * iw + lx * stride + tap % 3) * 4);
+    v[tap * 3 + 0] = px.w ? norm16(px.z, mean, scale, is_bf16) : (uint16_t)0;      // R
+    v[tap * 3 + 1] = px.w ? norm16(px.y, mean, scale, is_bf16) : (uint16_t)0;      // G
+    v[tap * 3 + 2] = px.w ? norm16(px.x, mean, scale, is_bf16) : (uint16_t)0;      // B
+  }
+#pragma unroll
+  for (int k = 27; k < 32; ++k) v[k] = 0;
+  uint4* o = reinterpret_cast<uint4*>(out + (((size_t)b * ho + oy) * wo + ox) * 32);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    o[j] = make_uint4(v[8 * j] | ((uint32_t)v[8 * j + 1] << 16), v[8 * j + 2] | ((uint32_t)v[8 * j + 3] << 16),
+                      v[8 * j + 4] | ((uint32_t)v[8 * j + 5] << 16), v[8 * j + 6] | ((uint32_t)v[8 * j + 7] << 16));
+}
+
 static int make_geom(ResizeGeom* g, int h, int w, int new_w, int new_h, int in_w, int in_h) {
   B2F_REQUIRE(h > 0 && w > 0 && new_w > 0 && new_h > 0 && new_w <= in_w && new_h <= in_h,
               "letterbox: bad geometry %dx%d -> %dx%d in %dx%d", w, h, new_w, new_h, in_w, in_h);
   g->H = h, g->W = w, g->new_w = new_w, g->new_h = new_h, g->in_w = in_w, g->in_h = in_h;
+  g->ratio = 1;
   if (new_w == w && new_h == h)
     g->mode = 0;
   else if (w == 2 * new_w && h == 2 * new_h)
     g->mode = 1;
+  else if (w % new_w == 0 && h % new_h == 0 && w / new_w == h / new_h && ((w / new_w) & 1) && w / new_w <= 15)
+    g->mode = 3, g->ratio = w / new_w;
   else
     g->mode = 2;
   g->scale_x = 1.0 / ((double)new_w / (double)w);
@@ -528,6 +595,46 @@ struct WarpParams {
   double* m_out;
 };
 
+
+// Four bilinear taps (2 x 2 pixels x BGR) of cv2.warpAffine's fixed-point interpolation.  Interior pixels read the six
+// contiguous bytes of each source row through two aligned 8-byte loads instead of six byte loads (the gather is
+// bound by LSU wavefronts); pixels on the frame border take the guarded byte path (out-of-image taps add 0).
+__device__ __forceinline__ void warp_taps(const uint8_t* __restrict__ img, int h, int w, int sx, int sy, int w00, int w01,
+                                          int w10, int w11, int (&bgr)[3]) {
+  const bool interior = sx >= 0 && sx + 1 < w && sy >= 0 && sy + 1 < h;
+  const uint8_t* r0 = img + ((size_t)sy * w + sx) * 3;
+  const uint8_t* r1 = r0 + (size_t)w * 3;
+  const uint8_t* end = img + (size_t)h * w * 3;
+  const uintptr_t a0 = reinterpret_cast<uintptr_t>(r0) & ~(uintptr_t)7, a1 = reinterpret_cast<uintptr_t>(r1) & ~(uintptr_t)7;
+  if (interior && reinterpret_cast<const uint8_t*>(a1) + 16 <= end) {
+    const uint2 p0 = __ldg(reinterpret_cast<const uint2*>(a0)), p1 = __ldg(reinterpret_cast<const uint2*>(a0) + 1);
+    const uint2 q0 = __ldg(reinterpret_cast<const uint2*>(a1)), q1 = __ldg(reinterpret_cast<const uint2*>(a1) + 1);
+    const int s0 = (int)(reinterpret_cast<uintptr_t>(r0) & 7) * 8, s1 = (int)(reinterpret_cast<uintptr_t>(r1) & 7) * 8;
+    const unsigned long long lo0 = ((unsigned long long)p0.y << 32) | p0.x, hi0 = ((unsigned long long)p1.y << 32) | p1.x;
+    const unsigned long long lo1 = ((unsigned long long)q0.y << 32) | q0.x, hi1 = ((unsigned long long)q1.y << 32) | q1.x;
+    const unsigned long long t0 = s0 ? (lo0 >> s0) | (hi0 << (64 - s0)) : lo0;      // six bytes: b g r b g r
+    const unsigned long long t1 = s1 ? (lo1 >> s1) | (hi1 << (64 - s1)) : lo1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int acc = (int)((t0 >> (8 * c)) & 0xFF) * w00 + (int)((t0 >> (8 * (c + 3))) & 0xFF) * w01 +
+                      (int)((t1 >> (8 * c)) & 0xFF) * w10 + (int)((t1 >> (8 * (c + 3))) & 0xFF) * w11;
+      bgr[c] = (acc + 16384) >> 15;
+    }
+    return;
+  }
+  const bool x0ok = sx >= 0 && sx < w, x1ok = sx + 1 >= 0 && sx + 1 < w;
+  const bool y0ok = sy >= 0 && sy < h, y1ok = sy + 1 >= 0 && sy + 1 < h;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    int acc = 0;
+    if (y0ok && x0ok) acc += r0[c] * w00;
+    if (y0ok && x1ok) acc += r0[3 + c] * w01;
+    if (y1ok && x0ok) acc += r1[c] * w10;
+    if (y1ok && x1ok) acc += r1[3 + c] * w11;
+    bgr[c] = (acc + 16384) >> 15;
+  }
+}
+
 __global__ void __launch_bounds__(256) warp_affine_kernel(WarpParams p) {
   const int f = blockIdx.y;
   __shared__ double sM[6];
@@ -560,18 +667,8 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(WarpParams p) {
   const int fx = X & 31, fy = Y & 31;
   const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
   const uint8_t* img = p.frames + (size_t)p.frame_idx[f] * p.h * p.w * 3;
-  const bool x0ok = sx >= 0 && sx < p.w, x1ok = sx + 1 >= 0 && sx + 1 < p.w;
-  const bool y0ok = sy >= 0 && sy < p.h, y1ok = sy + 1 >= 0 && sy + 1 < p.h;
   int bgr[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    int acc = 0;
-    if (y0ok && x0ok) acc += img[((size_t)sy * p.w + sx) * 3 + c] * w00;
-    if (y0ok && x1ok) acc += img[((size_t)sy * p.w + sx + 1) * 3 + c] * w01;
-    if (y1ok && x0ok) acc += img[((size_t)(sy + 1) * p.w + sx) * 3 + c] * w10;
-    if (y1ok && x1ok) acc += img[((size_t)(sy + 1) * p.w + sx + 1) * 3 + c] * w11;
-    bgr[c] = (acc + 16384) >> 15;
-  }
+  warp_taps(img, p.h, p.w, sx, sy, w00, w01, w10, w11, bgr);
   const size_t opix = (size_t)f * p.size * p.size + idx;
   if (p.crop_u8) {
     uint8_t* o = p.crop_u8 + opix * 3;
@@ -593,6 +690,67 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(WarpParams p) {
     uint16_t* o = reinterpret_cast<uint16_t*>(p.out_nhwc) + opix * p.c_pad;
     *reinterpret_cast<uint2*>(o) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
     for (int c = 4; c < p.c_pad; c += 4) *reinterpret_cast<uint2*>(o + c) = make_uint2(0u, 0u);
+  }
+}
+
+
+// norm_crop + normalise + 3x3 / pad 1 / stride 1 patch extraction: one CTA per face.  The aligned crop is built once in
+// shared memory (uint8, exactly the cv2.warpAffine arithmetic of warp_affine_kernel), then every thread emits
+// 16-byte pieces of the [size][size][32] patch tensor the first ArcFace convolution consumes as a 1x1 conv.
+constexpr int kPatchCrop = 112;
+__global__ void __launch_bounds__(512) warp_patches_kernel(WarpParams p, uint16_t* __restrict__ out) {
+  __shared__ uint8_t crop[kPatchCrop * kPatchCrop * 3];
+  __shared__ uint16_t lut[256];
+  __shared__ double sM[6];
+  const int f = blockIdx.x, size = p.size;
+  if (threadIdx.x == 0) estimate_norm_dev(p.landmarks + (size_t)f * 10, size, sM);
+  if (threadIdx.x < 256) lut[threadIdx.x] = norm16((int)threadIdx.x, p.mean, p.scale, p.is_bf16);
+  __syncthreads();
+  // inverse transform, float64 without fused multiply-add (cv2.warpAffine)
+  double D = __dsub_rn(__dmul_rn(sM[0], sM[4]), __dmul_rn(sM[1], sM[3]));
+  D = D != 0.0 ? 1.0 / D : 0.0;
+  const double i00 = __dmul_rn(sM[4], D), i11 = __dmul_rn(sM[0], D);
+  const double i01 = __dmul_rn(sM[1], -D), i10 = __dmul_rn(sM[3], -D);
+  const double i02 = __dsub_rn(__dmul_rn(-i00, sM[2]), __dmul_rn(i01, sM[5]));
+  const double i12 = __dsub_rn(__dmul_rn(-i10, sM[2]), __dmul_rn(i11, sM[5]));
+  const uint8_t* img = p.frames + (size_t)p.frame_idx[f] * p.h * p.w * 3;
+  for (int idx = threadIdx.x; idx < size * size; idx += blockDim.x) {
+    const int x = idx % size, y = idx / size;
+    const int adelta = (int)__double2ll_rn(__dmul_rn(__dmul_rn(i00, (double)x), 1024.0));
+    const int bdelta = (int)__double2ll_rn(__dmul_rn(__dmul_rn(i10, (double)x), 1024.0));
+    const int X0 = (int)__double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(i01, (double)y), i02), 1024.0)) + 16;
+    const int Y0 = (int)__double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(i11, (double)y), i12), 1024.0)) + 16;
+    const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+    const int sx = min(max(X >> 5, -32768), 32767), sy = min(max(Y >> 5, -32768), 32767);
+    const int fx = X & 31, fy = Y & 31;
+    const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+    int bgr[3];
+    warp_taps(img, p.h, p.w, sx, sy, w00, w01, w10, w11, bgr);
+    crop[idx * 3 + 0] = (uint8_t)bgr[0], crop[idx * 3 + 1] = (uint8_t)bgr[1], crop[idx * 3 + 2] = (uint8_t)bgr[2];
+  }
+  __syncthreads();
+  uint16_t* o = out + (size_t)f * size * size * 32;
+  // emission: one thread per crop pixel, values through a 256-entry table (measured faster than recomputing them
+  // and than piece-per-lane coalescing)
+  for (int pix = threadIdx.x; pix < size * size; pix += blockDim.x) {
+    const int x = pix % size, y = pix / size;
+    uint16_t v[32];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int iy = y + tap / 3 - 1, ix = x + tap % 3 - 1;
+      const bool ok = iy >= 0 && iy < size && ix >= 0 && ix < size;
+      const uint8_t* c = crop + (iy * size + ix) * 3;
+      v[tap * 3 + 0] = ok ? lut[c[2]] : (uint16_t)0;       // R
+      v[tap * 3 + 1] = ok ? lut[c[1]] : (uint16_t)0;       // G
+      v[tap * 3 + 2] = ok ? lut[c[0]] : (uint16_t)0;       // B
+    }
+#pragma unroll
+    for (int k = 27; k < 32; ++k) v[k] = 0;
+    uint4* q = reinterpret_cast<uint4*>(o + (size_t)pix * 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      q[j] = make_uint4(v[8 * j] | ((uint32_t)v[8 * j + 1] << 16), v[8 * j + 2] | ((uint32_t)v[8 * j + 3] << 16),
+                        v[8 * j + 4] | ((uint32_t)v[8 * j + 5] << 16), v[8 * j + 6] | ((uint32_t)v[8 * j + 7] << 16));
   }
 }
 
@@ -622,6 +780,26 @@ extern "C" int b2f_preprocess(const uint8_t* frames, int batch, int h, int w, in
   const long long total = (long long)batch * in_h * in_w;
   letterbox_kernel<1><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(frames, g, batch, mean, scale, out_nhwc,
                                                                             c_pad, dtype == B2F_BF16);
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
+
+
+extern "C" int b2f_preprocess_patches(const uint8_t* frames, int batch, int h, int w, int new_w, int new_h, int in_w,
+                                      int in_h, int stride, float mean, float scale, void* out_patches, int dtype,
+                                      void* stream) {
+  B2F_REQUIRE(dtype == B2F_F16 || dtype == B2F_BF16, "b2f_preprocess_patches: dtype must be f16 or bf16");
+  B2F_REQUIRE(stride == 1 || stride == 2, "b2f_preprocess_patches: stride must be 1 or 2");
+  ResizeGeom g;
+  int rc = make_geom(&g, h, w, new_w, new_h, in_w, in_h);
+  if (rc) return rc;
+  const int ho = (in_h + 2 - 3) / stride + 1, wo = (in_w + 2 - 3) / stride + 1;
+  if (batch <= 0) return 0;
+  B2F_REQUIRE(batch <= 65535, "b2f_preprocess_patches: batch too large");
+  letterbox_patches_kernel<<<dim3((wo + kLpW - 1) / kLpW, (ho + kLpH - 1) / kLpH, batch), kLpW * kLpH, 0,
+                             (cudaStream_t)stream>>>(frames, g, stride, ho, wo, mean, scale,
+                                                     reinterpret_cast<uint16_t*>(out_patches), dtype == B2F_BF16);
   g_launches.fetch_add(1);
   B2F_LAUNCH_CHECK();
   return 0;
@@ -742,4 +920,20 @@ extern "C" int b2f_norm_crop(const uint8_t* frames, int h, int w, const int* fra
   p.size = size, p.mean = mean, p.scale = scale, p.out_nhwc = out_nhwc, p.c_pad = c_pad, p.is_bf16 = dtype == B2F_BF16;
   p.crop_u8 = crop_u8, p.m_out = m_out;
   return launch_warp(p, stream);
+}
+
+extern "C" int b2f_norm_crop_patches(const uint8_t* frames, int h, int w, const int* frame_idx, const float* landmarks,
+                                     int faces, int size, float mean, float scale, void* out_patches, int dtype,
+                                     void* stream) {
+  B2F_REQUIRE(size == kPatchCrop, "b2f_norm_crop_patches: crop size must be %d (got %d)", kPatchCrop, size);
+  B2F_REQUIRE(dtype == B2F_F16 || dtype == B2F_BF16, "b2f_norm_crop_patches: dtype must be f16 or bf16");
+  if (faces <= 0) return 0;
+  WarpParams p;
+  memset(&p, 0, sizeof(p));
+  p.frames = frames, p.h = h, p.w = w, p.frame_idx = frame_idx, p.landmarks = landmarks, p.faces = faces;
+  p.size = size, p.mean = mean, p.scale = scale, p.is_bf16 = dtype == B2F_BF16;
+  warp_patches_kernel<<<faces, 512, 0, (cudaStream_t)stream>>>(p, reinterpret_cast<uint16_t*>(out_patches));
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
 }

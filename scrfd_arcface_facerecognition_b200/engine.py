@@ -166,14 +166,27 @@ class NetEngine:
             self._bound[n] = self._bind(n)
         return self._bound[n][1][self.plan.input_name]
 
-    def run(self, n: int, timings: Optional[list] = None) -> Dict[str, torch.Tensor]:
-        """Run the net on whatever `input_buffer(n)` holds; returns {graph output name: [n,H,W,C] fp32 view}.
+    def patch_buffer(self, n: int) -> Optional[Tuple[torch.Tensor, int]]:
+        """When the plan starts with the 3x3 patch extraction of the first convolution, the ([n,ho,wo,32] tensor it
+        writes, its stride): the fused preprocess / norm_crop kernels fill it directly and `run(start=1)` skips it."""
+        op = self.plan.ops[0]
+        if op.kind != "im2col":
+            return None
+        if n not in self._bound:
+            self._bound[n] = self._bind(n)
+        return self._bound[n][1][op.dst], int(op.attrs["stride"])
+
+    def run(self, n: int, timings: Optional[list] = None, start: int = 0) -> Dict[str, torch.Tensor]:
+        """Run the net on whatever `input_buffer(n)` holds (or, with start=1, on a filled `patch_buffer(n)`);
+        returns {graph output name: [n,H,W,C] fp32 view}.
         `timings`, when given, receives (op index, kind, start event, end event) per launch (bench roofline)."""
         if n not in self._bound:
             self._bound[n] = self._bind(n)
         bound, tens, _ = self._bound[n]
         sp = stream_ptr()
         for i, b in enumerate(bound):
+            if i < start:
+                continue
             if timings is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()

@@ -63,6 +63,7 @@ class SCRFD:
         self.mean = 127.5
         self.std = 128.0
         self.center_cache = {}
+        self.fuse_stem = True               # letterbox + blob + first-layer patches in one kernel when the plan allows
 
         self._lock = threading.RLock()      # duplicate.py calls the shared model from a 4-thread pool
         self._engines: Dict[Tuple[int, int], NetEngine] = {}
@@ -124,6 +125,13 @@ class SCRFD:
         """frames: [B,H,W,3] uint8 cuda.  Letterbox + normalise into the engine input, run the net."""
         eng = self._engine_for(in_h, in_w)
         b, h, w, _ = frames.shape
+        patches = eng.patch_buffer(b) if self.fuse_stem else None
+        if patches is not None:           # letterbox + blob + first-layer patch extraction in one pass
+            _lib.check(self._lib.b2f_preprocess_patches(frames.data_ptr(), b, h, w, new_w, new_h, in_w, in_h, patches[1],
+                                                        float(self.mean), float(np.float32(1.0 / self.std)),
+                                                        patches[0].data_ptr(), eng.dtype, stream_ptr()),
+                       "b2f_preprocess_patches")
+            return eng.run(b, start=1)
         x = eng.input_buffer(b)
         _lib.check(self._lib.b2f_preprocess(frames.data_ptr(), b, h, w, new_w, new_h, in_w, in_h,
                                             float(self.mean), float(np.float32(1.0 / self.std)), x.data_ptr(), 4,

@@ -318,6 +318,46 @@ def test_im2col3x3(lib):
         assert torch.equal(got[..., :27], cols) and (got[..., 27:] == 0).all()
 
 
+@pytest.mark.parametrize("geom", [(1080, 1920, 640, 360, 2), (720, 1280, 640, 360, 2), (480, 640, 640, 480, 2),
+                                  (640, 640, 640, 640, 1), (333, 517, 640, 412, 2)],
+                         ids=lambda g: "x".join(map(str, g)))
+def test_fused_preprocess_patches_equal_preprocess_plus_im2col(lib, geom):
+    """letterbox + blob + 3x3 patches in one kernel == the two-kernel path, bit for bit"""
+    h, w, new_w, new_h, stride = geom
+    frames = torch.from_numpy(np.stack([inputs.frame(40 + i, h, w) for i in range(2)])).cuda()
+    ho = wo = (640 + 2 - 3) // stride + 1
+    x = torch.empty((2, 640, 640, 4), dtype=torch.float16, device="cuda")
+    _lib.check(lib.b2f_preprocess(frames.data_ptr(), 2, h, w, new_w, new_h, 640, 640, 127.5, 1 / 128.0, x.data_ptr(), 4, 0, sp()))
+    want = torch.empty((2, ho, wo, 32), dtype=torch.float16, device="cuda")
+    _lib.check(lib.b2f_im2col3x3(x.data_ptr(), 2, 640, 640, stride, ho, wo, 0, want.data_ptr(), sp()))
+    got = torch.full((2, ho, wo, 32), float("nan"), dtype=torch.float16, device="cuda")
+    _lib.check(lib.b2f_preprocess_patches(frames.data_ptr(), 2, h, w, new_w, new_h, 640, 640, stride, 127.5, 1 / 128.0,
+                                          got.data_ptr(), 0, sp()))
+    torch.cuda.synchronize()
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+
+
+def test_fused_norm_crop_patches_equal_norm_crop_plus_im2col(lib):
+    h, w, n = 360, 480, 40
+    frames = torch.from_numpy(np.stack([inputs.smooth_frame(50 + i, h, w) for i in range(2)])).cuda()
+    lm = inputs.landmarks(51, h, w, n)
+    lm[:6] += np.array([[-300.0, 0.0]], np.float32)                     # crops that hang over the frame edge
+    kps = torch.from_numpy(lm.reshape(n, 10)).cuda()
+    fidx = (torch.arange(n, device="cuda") % 2).to(torch.int32)
+    scale = float(np.float32(1.0 / 127.5))
+    for dtype, tdt in ((0, torch.float16), (1, torch.bfloat16)):
+        x = torch.empty((n, 112, 112, 4), dtype=tdt, device="cuda")
+        _lib.check(lib.b2f_norm_crop(frames.data_ptr(), h, w, fidx.data_ptr(), kps.data_ptr(), n, 112, 127.5, scale,
+                                     x.data_ptr(), 4, dtype, None, None, sp()))
+        want = torch.empty((n, 112, 112, 32), dtype=tdt, device="cuda")
+        _lib.check(lib.b2f_im2col3x3(x.data_ptr(), n, 112, 112, 1, 112, 112, dtype, want.data_ptr(), sp()))
+        got = torch.full((n, 112, 112, 32), float("nan"), dtype=tdt, device="cuda")
+        _lib.check(lib.b2f_norm_crop_patches(frames.data_ptr(), h, w, fidx.data_ptr(), kps.data_ptr(), n, 112, 127.5, scale,
+                                             got.data_ptr(), dtype, sp()))
+        torch.cuda.synchronize()
+        assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+
+
 def test_pool_and_eltwise(lib):
     g = torch.Generator().manual_seed(3)
     x = _q(torch.randn((2, 24, 21, 27), generator=g))
