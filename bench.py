@@ -428,6 +428,25 @@ def run_b200(a):
         roofline = conv_roofline(a, det, rec, static, pipe, B, F)
         roofline["share_of_step"] = roofline.pop("conv_ms_per_step") / ms_step if ms_step else None
 
+    # ---- the match stage alone (BASELINE metric, second half: "match TFLOP/s"): this rank's queries of one step
+    #      against this rank's gallery shard -- l2norm + tcgen05 cosine top-k GEMM + exact fp32 re-score
+    q_match = outs["emb"].clone()
+    for _ in range(3):
+        gal.match_local(q_match, 1, 0.4, strict=True)
+    torch.cuda.synchronize()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0.record()
+    for _ in range(10):
+        gal.match_local(q_match, 1, 0.4, strict=True)
+    m1.record()
+    torch.cuda.synchronize()
+    match_ms = m0.elapsed_time(m1) / 10
+    match_flops = 2.0 * q_match.shape[0] * len(gal) * 512
+    match_stage = {"ms": match_ms, "tflops": match_flops / match_ms / 1e9, "queries": int(q_match.shape[0]),
+                   "gallery_rows": len(gal), "flops": match_flops,
+                   "frac_of_bf16_peak": match_flops / match_ms / 1e9 / (roofline["peak"] if roofline else 1388.5),
+                   "what": "l2norm + tcgen05 cosine top-k GEMM (fp16 operands) + exact fp32 re-score, per rank"}
+
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -438,7 +457,7 @@ def run_b200(a):
         "gpu_launches": int(kernels_per_step * a.steps + eager_launches) if use_graph else int(eager_launches),
         "kernels_per_step": int(kernels_per_step), "clocks": clocks,
         "faces_per_step_per_gpu": faces_per_step, "matched_faces": matched, "top1_correct": top1_correct, "decode_overflow_frames": overflow,
-        "match_tflops": 2.0 * faces_per_step * world * a.gallery * 512 / (ms_step / 1e3) / 1e12,
+        "match_tflops": match_stage["tflops"] * world, "match": match_stage,
         "cuda_graph": use_graph,
     }
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

@@ -36,6 +36,7 @@ int g_tile_groups = 0;   // 0 = auto, else 2 or 4 epilogue groups
 int g_tile_mt = 0;       // 0 = auto, else 1 or 2 M tiles per weight tile
 int g_tile_amode = -1;   // -1 = auto, else force A mode 0 / 1 / 2 where legal
 int g_tile_epi = -1;     // -1 = auto, 0 = direct global stores, 1 = TMA stores
+int g_tile_cg2 = 1;      // CTA pairs (cta_group::2): 0 = never, 1 = wide tiles with streamed weights, 2 = wherever legal
 
 constexpr int kTStages = 16;
 constexpr int kTAcc = 4;
@@ -55,6 +56,7 @@ struct TileParams {
   int b_tile_bytes, stages_b, b_resident;
   int b_stride;             // bytes between weight stages; mode 0 streamed: the stage also holds its activation box(es)
   int combined;             // 1: one barrier pair per tap covers the weight tile and the activation boxes (mode 0, streamed)
+  int cg2;                  // 1: CTA pair (cluster of 2, tcgen05 cta_group::2): M = 256 over two SMs, each loads half of B
   int n_acc_log2, acc_stride;
   int groups;
   int is_bf16, debug;
@@ -84,6 +86,90 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void bar_sync_named(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair (cta_group::2) pieces: the two CTAs of a cluster run one M = 256 MMA; each holds its own 128 rows of A and
+// half of the N rows of B, so the weight traffic and the B operand reads per SM halve
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ uint32_t mapa_u32(const void* local, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local)), "r"(rank));
+  return remote;
+}
+// TMA loads of a CTA pair: the data lands in this CTA's shared memory, the bytes are counted on `mbar_cluster`
+// (a shared::cluster address -- the leader CTA's barrier), so the leader's MMA warp waits on ONE barrier per stage
+__device__ __forceinline__ void tma_load_4d_cg2(void* dst, const CUtensorMap* m, uint32_t mbar_cluster, int c0, int c1,
+                                                int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_cg2(void* dst, const CUtensorMap* m, uint32_t mbar_cluster, int c0, int c1,
+                                                int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
 }
 
 __device__ __forceinline__ void unpack8(const uint4& v, int is_bf16, float* f) {
@@ -237,6 +323,8 @@ struct EpiCtx {
   const float *s_bias, *s_slope;
   const CUtensorMap *tmO, *tmR;
   int tiles_cta, group, q, lane;
+  int first, stride, rank;        // work items of this CTA (or CTA pair): first, first + stride, ...; rank in the pair
+  uint64_t* peer_tempty;          // cta_group::2: the pair's second CTA releases accumulators on the leader's barrier
   bool leader;
 };
 
@@ -244,11 +332,12 @@ struct TileCoord {
   int x0, y0, n0, cbase, m_tile;
 };
 
-__device__ __forceinline__ TileCoord tile_of(const TileParams& p, int seq) {
-  const int l = seq / p.mt, u = seq - l * p.mt;
-  const int i = blockIdx.x + l * gridDim.x;
+__device__ __forceinline__ TileCoord tile_of(const TileParams& p, int first, int stride, int rank, int seq) {
+  // an item = `pair` consecutive M tiles of one N tile: mt tiles of one CTA, or one tile for each CTA of a pair
+  const int l = p.cg2 ? seq : seq / p.mt, u = p.cg2 ? rank : seq - l * p.mt;
+  const int i = first + l * stride;
   const int nt = i % p.n_tiles, mp = i / p.n_tiles;
-  const int m_tile = mp * p.mt + u;
+  const int m_tile = mp * (p.cg2 ? 2 : p.mt) + u;
   const int tiles_xy = p.tiles_x * p.tiles_y;
   TileCoord t;
   t.m_tile = m_tile;
@@ -263,7 +352,7 @@ __device__ __forceinline__ TileCoord tile_of(const TileParams& p, int seq) {
 // cp.async.bulk.tensor store.  Staging buffers form a ring of kStgBufs per group; with a residual, the slice that
 // will be processed two steps later is TMA-loaded into its buffer first, and each thread reads / overwrites only
 // its own 16-byte pieces of it.
-template <int ACT, bool BF16, int RES>
+template <int ACT, bool BF16, int RES, bool CG2>
 __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& c) {
   const int G = p.groups, n_sub = p.n_sub, och = p.ochunk, group = c.group;
   const int n_acc_mask = (1 << p.n_acc_log2) - 1;
@@ -285,7 +374,7 @@ __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& 
   const bool skip_math = (p.debug & 16) != 0, skip_store = (p.debug & 1) != 0;
   const int stg_bytes = p.stg_bytes, sig_hi = p.sig_hi, cout_p = p.cout_p;
   auto issue_res = [&](int s) {                                      // leader only: residual slice of sub s
-    const TileCoord t = tile_of(p, group + (s / n_sub) * G);
+    const TileCoord t = tile_of(p, c.first, c.stride, c.rank, group + (s / n_sub) * G);
     const int buf = s % NB;
     mbar_arrive_expect_tx(&c.rbar[buf], (uint32_t)p.stg_box_bytes);
     tma_load_4d(c.stg + (size_t)buf * stg_bytes, c.tmR, &c.rbar[buf], t.cbase + (s % n_sub) * och, t.x0, t.y0, t.n0);
@@ -295,7 +384,7 @@ __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& 
   int k = 0;
   for (int tl = 0; tl < my_tiles; ++tl) {
     const int seq = group + tl * G;
-    const TileCoord t = tile_of(p, seq);
+    const TileCoord t = tile_of(p, c.first, c.stride, c.rank, seq);
     int cls = 0;
     if (p.bias_classes == 9) {
       const int ox = t.x0 + lx, oy = t.y0 + ly;
@@ -334,7 +423,10 @@ __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& 
       if (j == n_sub - 1) {                              // accumulator fully read: hand it back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (c.lane == 0) mbar_arrive(&c.tempty[acc]);
+        if (c.lane == 0) {
+          if (CG2 && c.rank) mbar_arrive_remote(&c.peer_tempty[acc], 0);
+          else mbar_arrive(&c.tempty[acc]);
+        }
       }
       if (RES == 1) mbar_wait(&c.rbar[buf], (uint32_t)(k / NB) & 1u);
       if (!skip_math) {
@@ -369,9 +461,9 @@ __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& 
 // tiles (every extra instruction per tcgen05.mma is tensor-pipe idle time)
 // ------------------------------------------------------------------------------------------
 struct MmaCtx {
-  int items_cta;
+  int items_cta, rank;
   uint32_t tmem_base, a_ring, b_base;
-  uint64_t *fullA, *emptyA, *fullB, *emptyB, *tfull, *tempty, *bres;
+  uint64_t *fullA, *emptyA, *fullB, *emptyB, *tfull, *tempty, *bres, *peerB, *peer_tempty;
 };
 
 template <int MODE, int MT, bool RES, int KSTEPS>
@@ -482,9 +574,55 @@ __device__ __forceinline__ void mma_issuer(const TileParams& p, const MmaCtx& c)
   }
 }
 
+// cta_group::2 issue loop (mode 0, combined stages).  The TMA loads of both CTAs count their bytes on the leader's
+// stage barrier; the leader (rank 0) issues one M = 256 MMA per K step for the pair and commits to the barriers
+// of both CTAs.  Each CTA's accumulator (its 128 rows) lives in its own TMEM at the same column.
+template <int KSTEPS>
+__device__ __forceinline__ void mma_issuer_cg2(const TileParams& p, const MmaCtx& c) {
+  const uint32_t row_bytes = p.kchunk * 2;
+  const int groups_per_item = p.cchunks * p.boxes_per_chunk, stages_b = p.stages_b, items_cta = c.items_cta;
+  uint64_t* const fullB = c.fullB;
+  uint64_t* const emptyB = c.emptyB;
+  int sb = 0;
+  uint32_t pb = 0;
+  if (c.rank != 0) return;          // only the leader issues; the peer's loads are counted on the leader's barriers
+  const uint32_t idesc = umma_idesc(256, (uint32_t)p.block_n, (uint32_t)p.is_bf16);
+  const int acc_mask = (1 << p.n_acc_log2) - 1, acc_log2 = p.n_acc_log2;
+  const uint32_t acc_stride = (uint32_t)p.acc_stride, tmem_base = c.tmem_base;
+  const uint64_t b_desc0 = umma_smem_desc(c.b_base, row_bytes);
+  const uint64_t a_in_b = umma_smem_desc(c.b_base + (uint32_t)p.b_tile_bytes, row_bytes);
+  const uint64_t b_inc = (uint64_t)(p.b_stride >> 4);
+  const bool do_mma = !(p.debug & 4);
+  for (int l = 0; l < items_cta; ++l) {
+    const int acc = l & acc_mask;
+    const uint32_t ph = ((uint32_t)(l >> acc_log2) & 1u) ^ 1u;
+    mbar_wait(&c.tempty[acc], ph);
+    mbar_wait_cluster(&c.peer_tempty[acc], ph);
+    tc_fence_after();
+    const uint32_t d0 = tmem_base + (uint32_t)acc * acc_stride;
+    for (int g = 0; g < groups_per_item; ++g) {
+      mbar_wait(&fullB[sb], pb);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t off = b_inc * (uint64_t)sb;
+        if (do_mma) {
+#pragma unroll
+          for (int k = 0; k < KSTEPS; ++k)
+            umma_f16_cg2(d0, a_in_b + off + (uint64_t)(2 * k), b_desc0 + off + (uint64_t)(2 * k), idesc,
+                         k == 0 ? (uint32_t)(g != 0) : 1u);
+        }
+        umma_commit_cg2(&emptyB[sb]);
+        if (g == groups_per_item - 1) umma_commit_cg2(&c.tfull[acc]);
+      }
+      if (++sb == stages_b) sb = 0, pb ^= 1;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
+template <bool CG2>
 __global__ void __launch_bounds__(64 + 128 * kTGroups, 1)
 conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const TileParams p) {
@@ -504,7 +642,9 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tempty = tfull + kTAcc;
   uint64_t* bres = tempty + kTAcc;
   uint64_t* rbar = bres + 1;                         // [kTGroups][kStgBufs]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + kTGroups * kStgBufs);
+  uint64_t* peerB = rbar + kTGroups * kStgBufs;      // cta_group::2: "the other CTA's stage has landed" (leader side)
+  uint64_t* peer_tempty = peerB + kTStages;          // cta_group::2: the other CTA's epilogue released the accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_tempty + kTAcc);
   float* s_bias = reinterpret_cast<float*>(smem + p.off_tab);
   float* s_slope = s_bias + p.bias_classes * p.cout_p;
 
@@ -512,9 +652,15 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const uint32_t row_bytes = p.kchunk * 2;
   const int n_acc = 1 << p.n_acc_log2;
-  // work items of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...; each item = mt consecutive M tiles of one N tile
-  const int items_cta = (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int tiles_cta = items_cta * p.mt;
+  // work items of this CTA (or CTA pair): first, first + stride, ...; an item = mt consecutive M tiles of one N tile
+  // (cta_group::2: two tiles, one per CTA of the pair)
+  const int cg2 = CG2 ? 1 : 0;        // compile-time: a kernel that contains cta_group::2 code must be launched as a cluster
+  int cta_rank = 0;
+  if constexpr (CG2) cta_rank = (int)cluster_ctarank();
+  const int first = cg2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int stride_items = cg2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int items_cta = (p.items - first + stride_items - 1) / stride_items;
+  const int tiles_cta = items_cta * (cg2 ? 1 : p.mt);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -533,16 +679,24 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     mbar_init(bres, 1);
     for (int s = 0; s < kTGroups * kStgBufs; ++s) mbar_init(&rbar[s], 1);
+    for (int s = 0; s < kTStages; ++s) mbar_init(&peerB[s], 1);
+    for (int s = 0; s < kTAcc; ++s) mbar_init(&peer_tempty[s], 4);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if constexpr (CG2) {
+      tmem_alloc2(tmem_slot, 512);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   for (int i = threadIdx.x; i < p.bias_classes * p.cout_p; i += blockDim.x) s_bias[i] = p.bias[i];
   for (int i = threadIdx.x; i < p.cout_p; i += blockDim.x) s_slope[i] = p.act == 2 ? p.slope[i] : 0.f;
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG2) cluster_sync_all();  // the peer's barriers and TMEM exist before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -557,7 +711,9 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int sx_scale = p.tw * p.stride, sy_scale = p.th * p.stride, org = mode == 0 ? p.pad : 1;
       const bool resident = p.b_resident != 0;
       const uint32_t a_tx = (uint32_t)(p.a_bytes * mt);
-      const uint32_t b_bytes = (uint32_t)block_n * row_bytes;
+      // cta_group::2: this CTA loads rows [rank * N/2, +N/2) of each weight tile
+      const uint32_t b_bytes = (uint32_t)(cg2 ? block_n / 2 : block_n) * row_bytes;
+      const int b_row_off = cg2 ? cta_rank * (block_n / 2) : 0;
       if (resident) {
         mbar_arrive_expect_tx(bres, b_bytes * (uint32_t)(cchunks * boxes * tpb));
         uint8_t* dst = b_base;
@@ -580,10 +736,10 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int nsx = mode == 2 ? 3 : 1, nr = mode == 0 ? 1 : 3;
       const bool skip_a = (p.debug & 8) != 0, combined = p.combined != 0;
       const int b_stride = p.b_stride;
-      for (int i = blockIdx.x; i < p.items; i += gridDim.x) {
+      for (int i = first; i < p.items; i += stride_items) {
         const int nt = i % n_tiles, mp = i / n_tiles;
-        const int nrow = nt * block_n;
-        const int m0 = mp * mt, m1 = m0 + 1;
+        const int nrow = nt * block_n + b_row_off;
+        const int m0 = cg2 ? mp * 2 + cta_rank : mp * mt, m1 = m0 + 1;
         const int ax0 = (m0 % tiles_x) * sx_scale - org, ay0 = ((m0 / tiles_x) % tiles_y) * sy_scale - org;
         const int an0 = (m0 / tiles_xy) * p.tn;
         const int ax1 = (m1 % tiles_x) * sx_scale - org, ay1 = ((m1 / tiles_x) % tiles_y) * sy_scale - org;
@@ -597,6 +753,18 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int c0 = (mode == 0 ? in : o) * kchunk;
             if (mode != 0) dx = in;
             {
+              if (CG2) {
+                // CTA pair: both CTAs fill their own stage (own activation box, own half of the weight tile); all
+                // bytes are counted on the LEADER's barrier, which the leader's producer arms for both
+                mbar_wait(&emptyB[sb], pb ^ 1);
+                uint8_t* dst = b_base + (size_t)sb * b_stride;
+                const uint32_t lead_bar = mapa_u32(&fullB[sb], 0);
+                if (cta_rank == 0) mbar_arrive_expect_tx(&fullB[sb], 2u * (b_bytes + a_tx));
+                tma_load_4d_cg2(dst + b_tile_bytes, &tmA, lead_bar, c0, ax0 + dx, ay0 + dy, an0);
+                tma_load_3d_cg2(dst, &tmB, lead_bar, c0, nrow, dy * kw + dx);
+                if (++sb == stages_b) sb = 0, pb ^= 1;
+                continue;
+              }
               if (combined) {
                 // mode 0, streamed weights: one stage = weight tile + activation box(es), one barrier pair per tap
                 mbar_wait(&emptyB[sb], pb ^ 1);
@@ -645,6 +813,12 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     c.a_ring = smem_u32(a_ring), c.b_base = smem_u32(b_base);
     c.fullA = fullA, c.emptyA = emptyA, c.fullB = fullB, c.emptyB = emptyB, c.tfull = tfull, c.tempty = tempty, c.bres = bres;
     const int ks = p.kchunk >> 4;
+    if constexpr (CG2) {
+      c.peerB = peerB, c.peer_tempty = peer_tempty, c.rank = cta_rank;
+      if (ks == 4) mma_issuer_cg2<4>(p, c);
+      else if (ks == 2) mma_issuer_cg2<2>(p, c);
+      else mma_issuer_cg2<1>(p, c);
+    } else {
     const int variant = p.a_mode * 3 + (p.b_resident ? 0 : p.mt);     // (mode, {resident, streamed mt=1, streamed mt=2})
 #define B2F_MMA_CASE(MODE, V, MT, RES)                                         \
     case MODE * 3 + V:                                                           \
@@ -664,6 +838,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       B2F_MMA_CASE(2, 2, 2, false)
       default: break;
     }
+    }
 #undef B2F_MMA_CASE
   } else if (warp < 2 + 4 * p.groups) {
     // ================================ epilogue ================================
@@ -682,14 +857,15 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       c.stg = stg_base + (size_t)group * p.stg_bufs * p.stg_bytes;
       c.s_bias = s_bias, c.s_slope = s_slope, c.tmO = &tmO, c.tmR = &tmR;
       c.tiles_cta = tiles_cta, c.group = group, c.q = q, c.lane = lane, c.leader = leader;
+      c.first = first, c.stride = stride_items, c.rank = cta_rank, c.peer_tempty = peer_tempty;
       const int variant = p.act * 6 + (p.is_bf16 ? 3 : 0) + (p.res_smem ? 1 : (p.res_global ? 2 : 0));
 #define B2F_EPI_CASE(ACT)                                                   \
-      case ACT * 6 + 0: epilogue_tma<ACT, false, 0>(p, c); break;             \
-      case ACT * 6 + 1: epilogue_tma<ACT, false, 1>(p, c); break;             \
-      case ACT * 6 + 2: epilogue_tma<ACT, false, 2>(p, c); break;             \
-      case ACT * 6 + 3: epilogue_tma<ACT, true, 0>(p, c); break;              \
-      case ACT * 6 + 4: epilogue_tma<ACT, true, 1>(p, c); break;              \
-      case ACT * 6 + 5: epilogue_tma<ACT, true, 2>(p, c); break;
+      case ACT * 6 + 0: epilogue_tma<ACT, false, 0, CG2>(p, c); break;             \
+      case ACT * 6 + 1: epilogue_tma<ACT, false, 1, CG2>(p, c); break;             \
+      case ACT * 6 + 2: epilogue_tma<ACT, false, 2, CG2>(p, c); break;             \
+      case ACT * 6 + 3: epilogue_tma<ACT, true, 0, CG2>(p, c); break;              \
+      case ACT * 6 + 4: epilogue_tma<ACT, true, 1, CG2>(p, c); break;              \
+      case ACT * 6 + 5: epilogue_tma<ACT, true, 2, CG2>(p, c); break;
       switch (variant) {
         B2F_EPI_CASE(0)
         B2F_EPI_CASE(1)
@@ -702,7 +878,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // direct stores (fp32 outputs, up-sampled residual): each thread writes its pixel's channels
       const int esz = p.out_dtype == 2 ? 4 : 2;
       for (int seq = group; seq < tiles_cta; seq += G) {
-        const TileCoord t = tile_of(p, seq);
+        const TileCoord t = tile_of(p, first, stride_items, cta_rank, seq);
         const int ox = t.x0 + lx, oy = t.y0 + ly, on = t.n0 + lz;
         const bool valid = (lz < p.tn) && ox < p.Wo && oy < p.Ho && on < p.N;
         int cls = 0;
@@ -745,16 +921,21 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (lane == 0) {
+          if (CG2 && cta_rank) mbar_arrive_remote(&peer_tempty[acc], 0);
+          else mbar_arrive(&tempty[acc]);
+        }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG2) cluster_sync_all();  // the leader's MMAs read this CTA's shared memory until the very end
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (CG2) tmem_dealloc2(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -912,7 +1093,7 @@ int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream, in
   // wide tiles have two accumulators and two epilogue groups: with only a few tiles per SM the exposed epilogue of
   // the last tile costs more than the first persistent kernel's column-split epilogue
   // (both kernels accumulate wide tiles in the same order, so this batch-dependent choice does not change results)
-  if (optional && p.block_n > 128 && p.items < 8 * g_sms) return kTileDeclined;
+  if (optional && p.block_n > 128 && p.items < 4 * g_sms) return kTileDeclined;
   p.boxes_per_chunk = p.a_mode == 0 ? taps : (p.a_mode == 1 ? 3 : 1);
   p.taps_per_box = taps / p.boxes_per_chunk;
   const int box_w = p.a_mode == 0 ? p.tw * d->stride : (p.a_mode == 1 ? p.tw : p.tw + 2);
@@ -922,6 +1103,19 @@ int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream, in
   p.a_stage_bytes = p.a_box_bytes * p.mt;
   p.stg_box_bytes = p.tw * p.th * p.tn * p.ochunk * 2;
   p.combined = (p.a_mode == 0 && !p.b_resident) ? 1 : 0;
+  // CTA pair: the two CTAs of a cluster each take one of the item's two M tiles and half of every weight tile
+  p.cg2 = (g_tile_cg2 && p.combined && p.block_n % 32 == 0 && p.m_tiles >= 2 && (g_tile_cg2 == 2 || p.block_n > 128)) ? 1 : 0;
+  if (p.cg2) {
+    p.mt = 1;
+    p.a_stage_bytes = p.a_box_bytes;
+    p.b_tile_bytes = round_up(p.block_n / 2 * row_bytes, 1024);
+    p.items = n_tiles * ((p.m_tiles + 1) / 2);
+    if (p.groups > (1 << p.n_acc_log2)) p.groups = 1 << p.n_acc_log2;
+    const int staging = p.epi_tma ? p.groups * p.stg_bufs * p.stg_bytes : 0;
+    p.stages_b = (kSmemMax - fixed - staging) / (p.b_tile_bytes + p.a_stage_bytes);
+    if (p.stages_b > kTStages) p.stages_b = kTStages;
+    B2F_REQUIRE(p.stages_b >= 2, "conv (CTA pair): not enough shared memory for two stages");
+  }
   p.b_stride = p.combined ? p.b_tile_bytes + p.a_stage_bytes : p.b_tile_bytes;
   if (p.combined) p.stages_a = 0;                      // activation boxes live inside the weight stages
   p.off_b = p.stages_a * p.a_stage_bytes;
@@ -945,7 +1139,7 @@ int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream, in
   {
     uint64_t dims[3] = {(uint64_t)d->cin_p, (uint64_t)d->cout_p, (uint64_t)taps};
     uint64_t str[2] = {(uint64_t)d->cin_p * 2, (uint64_t)d->cout_p * d->cin_p * 2};
-    uint32_t box[3] = {(uint32_t)kchunk, (uint32_t)p.block_n, 1};
+    uint32_t box[3] = {(uint32_t)kchunk, (uint32_t)(p.cg2 ? p.block_n / 2 : p.block_n), 1};
     uint32_t es[3] = {1, 1, 1};
     int rc = make_tmap(&tmB, d->weight, 3, dims, str, box, es, row_bytes, p.is_bf16);
     if (rc) return rc;
@@ -966,17 +1160,33 @@ int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream, in
   static std::once_flag once;
   static cudaError_t attr_rc = cudaSuccess;
   std::call_once(once, [] {
-    attr_rc = cudaFuncSetAttribute(conv_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    attr_rc = cudaFuncSetAttribute(conv_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (attr_rc == cudaSuccess)
+      attr_rc = cudaFuncSetAttribute(conv_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
   });
   B2F_CHECK_CUDA(attr_rc);
   static const bool trace = getenv("B2F_PLAN_TRACE") != nullptr;
   if (trace)
     fprintf(stderr, "[b2f plan] n%d %dx%d %d->%d k%d s%d: mode %d tile %dx%dx%d mt %d groups %d resident %d stagesA %d stagesB %d "
-            "block_n %d kchunk %d epi_tma %d res_smem %d ochunk %d bufs %d smem %zu items %d\n", d->n, d->h, d->w, d->cin_p, d->cout_p, d->kh, d->stride,
+            "block_n %d kchunk %d epi_tma %d res_smem %d ochunk %d bufs %d cg2 %d smem %zu items %d\n", d->n, d->h, d->w, d->cin_p, d->cout_p, d->kh, d->stride,
             p.a_mode, p.tw, p.th, p.tn, p.mt, p.groups, p.b_resident, p.stages_a, p.stages_b, p.block_n, kchunk, p.epi_tma,
-            p.res_smem, p.ochunk, p.stg_bufs, smem, p.items);
+            p.res_smem, p.ochunk, p.stg_bufs, p.cg2, smem, p.items);
+  if (p.cg2) {
+    const int clusters = p.items < g_sms / 2 ? p.items : g_sms / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters), cfg.blockDim = dim3(64 + 128 * p.groups);
+    cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    B2F_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true>, tmA, tmB, tmO, tmR, p));
+    g_launches.fetch_add(1);
+    return 0;
+  }
   const int grid = p.items < g_sms ? p.items : g_sms;
-  conv_tile_kernel<<<grid, 64 + 128 * p.groups, smem, stream>>>(tmA, tmB, tmO, tmR, p);
+  conv_tile_kernel<false><<<grid, 64 + 128 * p.groups, smem, stream>>>(tmA, tmB, tmO, tmR, p);
   g_launches.fetch_add(1);
   B2F_LAUNCH_CHECK();
   return 0;

@@ -46,6 +46,7 @@ struct UmmaParams {
   int stages, b_tile_bytes, tmem_cols;
   int total_tiles, n_acc, acc_stride;   // persistent kernel: tiles = M tiles x N tiles, TMEM accumulator ring
   int a_stage_bytes, stages_a, stages_b, b_resident;   // vertical-halo kernel
+  int a_res;                // umma_conv_kernel: the M tile stays resident, only N tiles stream
   int halo2;                // 1: one (th+2) x (tw+2) box per channel chunk serves all nine taps (tw == 8)
   int is_bf16;
   int debug;                // bottleneck isolation (b2f_set_tuning key 4): 1 no stores, 2 no residual, 4 no MMA, 8 no A loads, 16 no epilogue math
@@ -91,13 +92,19 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
 
-  const int stage_bytes = kATileBytes + p.b_tile_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  // a_res: the CTA's M tile (all K chunks of it) stays resident in shared memory while the CTA walks its N tiles --
+  // the matching / clustering GEMMs re-use one 128 x K query tile against thousands of gallery tiles, and re-streaming
+  // it per N tile made them L2->SM bound; only the gallery tiles go through the ring then
+  const int a_res_bytes = p.a_res ? p.kh * p.kw * p.cchunks * kATileBytes : 0;
+  const int stage_bytes = (p.a_res ? 0 : kATileBytes) + p.b_tile_bytes;
+  uint8_t* ring = smem + a_res_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + p.stages * stage_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tfull_bar = bars + 2 * kMaxStages;
   uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  uint64_t* ares_bar = bars + 2 * kMaxStages + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -125,6 +132,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 8);
     }
+    mbar_init(ares_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -141,7 +149,17 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       const int kh = p.kh, kw = p.kw, cchunks = p.cchunks, kchunk = p.kchunk, block_n = p.block_n, stages = p.stages;
       const int ax = x0 * p.stride - p.pad, ay = y0 * p.stride - p.pad;
-      const uint32_t tx_bytes = (uint32_t)(p.tw * p.th * p.tn) * row_bytes + (uint32_t)block_n * row_bytes;
+      const bool a_res = p.a_res != 0;
+      const uint32_t a_bytes = (uint32_t)(p.tw * p.th * p.tn) * row_bytes;
+      const uint32_t tx_bytes = (a_res ? 0u : a_bytes) + (uint32_t)block_n * row_bytes;
+      if (a_res && nt_begin < nt_end) {
+        mbar_arrive_expect_tx(ares_bar, a_bytes * (uint32_t)(kh * kw * cchunks));
+        uint8_t* dst = smem;
+        for (int r = 0; r < kh; ++r)
+          for (int sx = 0; sx < kw; ++sx)
+            for (int cc = 0; cc < cchunks; ++cc, dst += kATileBytes)
+              tma_load_4d(dst, &tmA, ares_bar, cc * kchunk, ax + sx, ay + r, n0);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int nt = nt_begin; nt < nt_end; ++nt) {
@@ -150,10 +168,10 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int sx = 0; sx < kw; ++sx, ++tap) {
             for (int cc = 0; cc < cchunks; ++cc) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              uint8_t* a_dst = smem + stage * stage_bytes;
+              uint8_t* a_dst = ring + stage * stage_bytes;
               mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-              tma_load_4d(a_dst, &tmA, &full_bar[stage], cc * kchunk, ax + sx, ay + r, n0);
-              tma_load_3d(a_dst + kATileBytes, &tmB, &full_bar[stage], cc * kchunk, nt * block_n, tap);
+              if (!a_res) tma_load_4d(a_dst, &tmA, &full_bar[stage], cc * kchunk, ax + sx, ay + r, n0);
+              tma_load_3d(a_dst + (a_res ? 0 : kATileBytes), &tmB, &full_bar[stage], cc * kchunk, nt * block_n, tap);
               if (++stage == stages) {
                 stage = 0;
                 phase ^= 1;
@@ -168,12 +186,17 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t idesc = umma_idesc(128, (uint32_t)p.block_n, (uint32_t)p.is_bf16);
     const int ksteps = p.kchunk >> 4, stages = p.stages;
     const uint32_t block_n = (uint32_t)p.block_n;
-    const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem), row_bytes);
-    const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem) + kATileBytes, row_bytes);
-    const uint64_t stage_inc = (uint64_t)(stage_bytes >> 4);
+    const bool a_res = p.a_res != 0;
+    const uint64_t a_desc0 = umma_smem_desc(smem_u32(a_res ? smem : ring), row_bytes);
+    const uint64_t b_desc0 = umma_smem_desc(smem_u32(ring) + (a_res ? 0 : kATileBytes), row_bytes);
+    const uint64_t stage_inc = (uint64_t)(stage_bytes >> 4), a_res_inc = (uint64_t)(kATileBytes >> 4);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    if (a_res && nt_begin < nt_end) {
+      mbar_wait(ares_bar, 0);
+      tc_fence_after();
+    }
     for (int nt = nt_begin; nt < nt_end; ++nt, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -185,7 +208,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         if (elect_one()) {
           const uint64_t off = stage_inc * (uint64_t)stage;
-          issue_stage_rt(ksteps, d_tmem, a_desc0 + off, b_desc0 + off, idesc, kk != 0);
+          issue_stage_rt(ksteps, d_tmem, a_desc0 + (a_res ? a_res_inc * (uint64_t)kk : off), b_desc0 + off, idesc, kk != 0);
           umma_commit(&empty_bar[stage]);           // frees the smem slot when these MMAs retire
           if (kk == k_iters - 1) umma_commit(&tfull_bar[acc]);
         }
@@ -878,19 +901,23 @@ void pick_m_tile(int N, int Ho, int Wo, int stride, int* tw, int* th, int* tn) {
 int g_smem_budget_single = 100 * 1024;  // lets two CTAs share an SM when each owns one N tile
 int g_smem_budget_loop = 200 * 1024;
 int g_max_block_n = 256;
+int g_a_res = 1;
 
 template <int EPI>
 static int launch_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaParams& p, int m_tiles, int grid_y,
                        cudaStream_t stream) {
-  const int stage_bytes = kATileBytes + p.b_tile_bytes;
+  const int k_iters = p.kh * p.kw * p.cchunks;
   const int budget = p.n_per_cta > 1 ? g_smem_budget_loop : g_smem_budget_single;
-  int stages = (budget - 2048) / stage_bytes;
+  // resident M tile when a CTA walks many N tiles and the tile plus three weight stages fit
+  const int a_res_bytes = k_iters * kATileBytes;
+  p.a_res = (g_a_res && p.n_per_cta >= 4 && a_res_bytes + 3 * p.b_tile_bytes + 2048 <= 227 * 1024) ? 1 : 0;
+  const int stage_bytes = (p.a_res ? 0 : kATileBytes) + p.b_tile_bytes;
+  int stages = p.a_res ? (227 * 1024 - 2048 - a_res_bytes) / stage_bytes : (budget - 2048) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
-  const int k_iters = p.kh * p.kw * p.cchunks;
   if (stages > k_iters * p.n_per_cta && k_iters * p.n_per_cta >= 2) stages = k_iters * p.n_per_cta;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  const size_t smem = (size_t)(p.a_res ? a_res_bytes : 0) + (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static std::once_flag once;
   static cudaError_t attr_rc = cudaSuccess;
   std::call_once(once, [] {

@@ -230,22 +230,23 @@ def test_conv_kernel_variants_agree(lib, case):
     res = _q(torch.randn((n, cout, h, w), generator=g))
     ref = torch.relu(F.conv2d(x, wt, b, 1, 1) + res)
     # (generation, vhalo, a_mode, mt, groups, tma_epilogue): 0 = CTA per tile, 1 = first persistent kernels,
-    # 2 = default dispatch, 3 = conv_tile_kernel for every layer
-    variants = [(0, 0, -1, 0, 0, -1), (1, 0, -1, 0, 0, -1), (1, 1, -1, 0, 0, -1), (1, 2, -1, 0, 0, -1), (2, 1, -1, 0, 0, -1),
-                (3, 1, -1, 0, 0, -1)]
-    variants += [(3, 1, am, mt, gr, 1) for am in (0, 1, 2) for mt in (1, 2) for gr in (2, 4)]
-    variants += [(3, 1, 2, 1, 4, 0), (3, 1, 0, 2, 2, 0)]
+    # 2 = default dispatch, 3 = conv_tile_kernel for every layer; last field: CTA pairs 0 never / 1 wide tiles / 2 forced
+    variants = [(0, 0, -1, 0, 0, -1, 1), (1, 0, -1, 0, 0, -1, 1), (1, 1, -1, 0, 0, -1, 1), (1, 2, -1, 0, 0, -1, 1),
+                (2, 1, -1, 0, 0, -1, 1), (3, 1, -1, 0, 0, -1, 1), (3, 1, -1, 0, 0, -1, 0)]
+    variants += [(3, 1, am, mt, gr, 1, 0) for am in (0, 1, 2) for mt in (1, 2) for gr in (2, 4)]
+    variants += [(3, 1, 2, 1, 4, 0, 0), (3, 1, 0, 2, 2, 0, 0)]
+    variants += [(3, 1, 0, 0, 0, -1, 2), (3, 1, 0, 0, 2, 1, 2), (3, 1, 0, 0, 4, 0, 2)]      # CTA pairs (cta_group::2)
     try:
-        for persistent, vhalo, amode, mt, groups, epi in variants:
-            for key, val in ((2, persistent), (3, vhalo), (7, amode), (6, mt), (5, groups), (8, epi)):
+        for persistent, vhalo, amode, mt, groups, epi, cg2 in variants:
+            for key, val in ((2, persistent), (3, vhalo), (7, amode), (6, mt), (5, groups), (8, epi), (11, cg2)):
                 _lib.check(lib.b2f_set_tuning(key, val))
             for f32 in (True, False):
                 out = run_conv(lib, x, wt, b, 1, 1, act=1, residual=res, res_mode=1, out_f32=f32)
                 err = (out - ref).abs().max().item()
                 tol = (2e-3 if f32 else 4e-3) * max(1.0, ref.abs().max().item())
-                assert err <= tol, f"variant {(persistent, vhalo, amode, mt, groups, epi)} f32={f32}: {err}"
+                assert err <= tol, f"variant {(persistent, vhalo, amode, mt, groups, epi, cg2)} f32={f32}: {err}"
     finally:
-        for key, val in ((2, 2), (3, 1), (7, -1), (6, 0), (5, 0), (8, -1)):
+        for key, val in ((2, 2), (3, 1), (7, -1), (6, 0), (5, 0), (8, -1), (11, 1)):
             _lib.check(lib.b2f_set_tuning(key, val))
 
 

@@ -24,9 +24,10 @@ VARIANTS = {
     "old": {2: 1}, "auto": {}, "new": {2: 3}, "m0": {2: 3, 7: 0}, "m1": {2: 3, 7: 1}, "m2": {2: 3, 7: 2}, "mt1": {2: 3, 6: 1},
     "mt2": {2: 3, 6: 2}, "g2": {2: 3, 5: 2}, "g4": {2: 3, 5: 4}, "direct": {2: 3, 8: 0}, "m2g2": {2: 3, 7: 2, 5: 2},
     "m2g4": {2: 3, 7: 2, 5: 4}, "m1mt2": {2: 3, 7: 1, 6: 2}, "m2mt2": {2: 3, 7: 2, 6: 2}, "m0mt2": {2: 3, 7: 0, 6: 2},
+    "cg0": {2: 3, 11: 0}, "cg2": {2: 3, 11: 2}, "m0cg0": {2: 3, 7: 0, 11: 0}, "m0cg2": {2: 3, 7: 0, 11: 2},
     "m1mt1": {2: 3, 7: 1, 6: 1}, "m2mt1": {2: 3, 7: 2, 6: 1}, "m0mt1": {2: 3, 7: 0, 6: 1},
 }
-DEFAULTS = {2: 2, 3: 1, 4: 0, 5: 0, 6: 0, 7: -1, 8: -1}
+DEFAULTS = {2: 2, 3: 1, 4: 0, 5: 0, 6: 0, 7: -1, 8: -1, 11: 1}
 
 
 def bench(lib, shape, reps=30):
