@@ -36,7 +36,8 @@ int g_tile_groups = 0;   // 0 = auto, else 2 or 4 epilogue groups
 int g_tile_mt = 0;       // 0 = auto, else 1 or 2 M tiles per weight tile
 int g_tile_amode = -1;   // -1 = auto, else force A mode 0 / 1 / 2 where legal
 int g_tile_epi = -1;     // -1 = auto, 0 = direct global stores, 1 = TMA stores
-int g_tile_cg2 = 1;      // CTA pairs (cta_group::2): 0 = never, 1 = wide tiles with streamed weights, 2 = wherever legal
+int g_tile_cg2 = 1;      // CTA pairs (cta_group::2): 0 = never, 1 = tiles wider than g_tile_cg2_min_n, 2 = wherever legal
+int g_tile_cg2_min_n = 128;
 
 constexpr int kTStages = 16;
 constexpr int kTAcc = 4;
@@ -120,7 +121,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 23)) __trap();
   }
 }
 __device__ __forceinline__ uint32_t mapa_u32(const void* local, uint32_t rank) {
@@ -334,10 +335,10 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord tile_of(const TileParams& p, int first, int stride, int rank, int seq) {
   // an item = `pair` consecutive M tiles of one N tile: mt tiles of one CTA, or one tile for each CTA of a pair
-  const int l = p.cg2 ? seq : seq / p.mt, u = p.cg2 ? rank : seq - l * p.mt;
+  const int l = seq / p.mt, u = seq - l * p.mt;
   const int i = first + l * stride;
   const int nt = i % p.n_tiles, mp = i / p.n_tiles;
-  const int m_tile = mp * (p.cg2 ? 2 : p.mt) + u;
+  const int m_tile = p.cg2 ? (mp * 2 + rank) * p.mt + u : mp * p.mt + u;
   const int tiles_xy = p.tiles_x * p.tiles_y;
   TileCoord t;
   t.m_tile = m_tile;
@@ -466,11 +467,27 @@ struct MmaCtx {
   uint64_t *fullA, *emptyA, *fullB, *emptyB, *tfull, *tempty, *bres, *peerB, *peer_tempty;
 };
 
-template <int MODE, int MT, bool RES, int KSTEPS>
+template <int KSTEPS, bool CG2>
+__device__ __forceinline__ void issue_k(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t first_acc) {
+#pragma unroll
+  for (int k = 0; k < KSTEPS; ++k) {
+    if (CG2) umma_f16_cg2(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, k == 0 ? first_acc : 1u);
+    else umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, k == 0 ? first_acc : 1u);
+  }
+}
+template <bool CG2>
+__device__ __forceinline__ void commit_to(uint64_t* bar) {
+  if (CG2) umma_commit_cg2(bar);       // the barrier at this offset in both CTAs of the pair
+  else umma_commit(bar);
+}
+
+// CG2: only the pair's leader (rank 0) issues -- M = 256 MMAs over both CTAs' operands, commits multicast to both CTAs
+template <int MODE, int MT, bool RES, int KSTEPS, bool CG2>
 __device__ __forceinline__ void mma_issuer(const TileParams& p, const MmaCtx& c) {
+  if (CG2 && c.rank != 0) return;
   constexpr int TPB = MODE == 0 ? 1 : (MODE == 1 ? 3 : 9);
   const uint32_t row_bytes = p.kchunk * 2;
-  const uint32_t idesc = umma_idesc(128, (uint32_t)p.block_n, (uint32_t)p.is_bf16);
+  const uint32_t idesc = umma_idesc(CG2 ? 256 : 128, (uint32_t)p.block_n, (uint32_t)p.is_bf16);
   const int groups_per_item = p.cchunks * p.boxes_per_chunk;
   const int stages_a = p.stages_a, stages_b = p.stages_b, items_cta = c.items_cta;
   const int acc_mask = (1 << p.n_acc_log2) - 1, acc_log2 = p.n_acc_log2;
@@ -503,6 +520,10 @@ __device__ __forceinline__ void mma_issuer(const TileParams& p, const MmaCtx& c)
     const int acc0 = seq & acc_mask, acc1 = (seq + 1) & acc_mask;
     mbar_wait(&tempty[acc0], ((uint32_t)(seq >> acc_log2) & 1u) ^ 1u);
     if (MT == 2) mbar_wait(&tempty[acc1], ((uint32_t)((seq + 1) >> acc_log2) & 1u) ^ 1u);
+    if (CG2) {                                   // the other CTA's epilogue released its copy of the accumulator(s)
+      mbar_wait_cluster(&c.peer_tempty[acc0], ((uint32_t)(seq >> acc_log2) & 1u) ^ 1u);
+      if (MT == 2) mbar_wait_cluster(&c.peer_tempty[acc1], ((uint32_t)((seq + 1) >> acc_log2) & 1u) ^ 1u);
+    }
     tc_fence_after();
     const uint32_t d0 = tmem_base + (uint32_t)acc0 * acc_stride, d1 = tmem_base + (uint32_t)acc1 * acc_stride;
     uint64_t bd = b_desc0;                               // resident weights: consumed in load order
@@ -514,13 +535,13 @@ __device__ __forceinline__ void mma_issuer(const TileParams& p, const MmaCtx& c)
         if (elect_one()) {
           const uint64_t off = b_inc * (uint64_t)sb;
           if (do_mma) {
-            issue_stage<KSTEPS>(d0, a_in_b + off, b_desc0 + off, idesc, (uint32_t)(g != 0));
-            if (MT == 2) issue_stage<KSTEPS>(d1, a_in_b + off + u_inc, b_desc0 + off, idesc, (uint32_t)(g != 0));
+            issue_k<KSTEPS, CG2>(d0, a_in_b + off, b_desc0 + off, idesc, (uint32_t)(g != 0));
+            if (MT == 2) issue_k<KSTEPS, CG2>(d1, a_in_b + off + u_inc, b_desc0 + off, idesc, (uint32_t)(g != 0));
           }
-          umma_commit(&emptyB[sb]);
+          commit_to<CG2>(&emptyB[sb]);
           if (g == groups_per_item - 1) {
-            umma_commit(&tfull[acc0]);
-            if (MT == 2) umma_commit(&tfull[acc1]);
+            commit_to<CG2>(&tfull[acc0]);
+            if (MT == 2) commit_to<CG2>(&tfull[acc1]);
           }
         }
         if (++sb == stages_b) sb = 0, pb ^= 1;
@@ -536,11 +557,11 @@ __device__ __forceinline__ void mma_issuer(const TileParams& p, const MmaCtx& c)
             for (int j = 0; j < TPB; ++j) {
               const uint64_t aoff = MODE == 0 ? 0ull : (MODE == 1 ? r_inc * (uint64_t)j
                                                                   : s_inc * (uint64_t)(j / 3) + r_inc * (uint64_t)(j % 3));
-              issue_stage<KSTEPS>(d0, ad + aoff, bd + b_inc * (uint64_t)j, idesc, j == 0 ? (uint32_t)(g != 0) : 1u);
+              issue_k<KSTEPS, CG2>(d0, ad + aoff, bd + b_inc * (uint64_t)j, idesc, j == 0 ? (uint32_t)(g != 0) : 1u);
             }
           }
-          umma_commit(&emptyA[sa]);
-          if (g == groups_per_item - 1) umma_commit(&tfull[acc0]);
+          commit_to<CG2>(&emptyA[sa]);
+          if (g == groups_per_item - 1) commit_to<CG2>(&tfull[acc0]);
         }
         bd += b_inc * (uint64_t)TPB;
       } else {
@@ -554,15 +575,15 @@ __device__ __forceinline__ void mma_issuer(const TileParams& p, const MmaCtx& c)
             const uint64_t bdj = b_desc0 + b_inc * (uint64_t)sb;
             const uint32_t accum = j == 0 ? (uint32_t)(g != 0) : 1u;
             if (do_mma) {
-              issue_stage<KSTEPS>(d0, ad + aoff, bdj, idesc, accum);
-              if (MT == 2) issue_stage<KSTEPS>(d1, ad + aoff + u_inc, bdj, idesc, accum);
+              issue_k<KSTEPS, CG2>(d0, ad + aoff, bdj, idesc, accum);
+              if (MT == 2) issue_k<KSTEPS, CG2>(d1, ad + aoff + u_inc, bdj, idesc, accum);
             }
-            umma_commit(&emptyB[sb]);
+            commit_to<CG2>(&emptyB[sb]);
             if (j == TPB - 1) {
-              umma_commit(&emptyA[sa]);
+              commit_to<CG2>(&emptyA[sa]);
               if (g == groups_per_item - 1) {
-                umma_commit(&tfull[acc0]);
-                if (MT == 2) umma_commit(&tfull[acc1]);
+                commit_to<CG2>(&tfull[acc0]);
+                if (MT == 2) commit_to<CG2>(&tfull[acc1]);
               }
             }
           }
@@ -570,51 +591,6 @@ __device__ __forceinline__ void mma_issuer(const TileParams& p, const MmaCtx& c)
         }
       }
       if (++sa == stages_a) sa = 0, pa ^= 1;
-    }
-  }
-}
-
-// cta_group::2 issue loop (mode 0, combined stages).  The TMA loads of both CTAs count their bytes on the leader's
-// stage barrier; the leader (rank 0) issues one M = 256 MMA per K step for the pair and commits to the barriers
-// of both CTAs.  Each CTA's accumulator (its 128 rows) lives in its own TMEM at the same column.
-template <int KSTEPS>
-__device__ __forceinline__ void mma_issuer_cg2(const TileParams& p, const MmaCtx& c) {
-  const uint32_t row_bytes = p.kchunk * 2;
-  const int groups_per_item = p.cchunks * p.boxes_per_chunk, stages_b = p.stages_b, items_cta = c.items_cta;
-  uint64_t* const fullB = c.fullB;
-  uint64_t* const emptyB = c.emptyB;
-  int sb = 0;
-  uint32_t pb = 0;
-  if (c.rank != 0) return;          // only the leader issues; the peer's loads are counted on the leader's barriers
-  const uint32_t idesc = umma_idesc(256, (uint32_t)p.block_n, (uint32_t)p.is_bf16);
-  const int acc_mask = (1 << p.n_acc_log2) - 1, acc_log2 = p.n_acc_log2;
-  const uint32_t acc_stride = (uint32_t)p.acc_stride, tmem_base = c.tmem_base;
-  const uint64_t b_desc0 = umma_smem_desc(c.b_base, row_bytes);
-  const uint64_t a_in_b = umma_smem_desc(c.b_base + (uint32_t)p.b_tile_bytes, row_bytes);
-  const uint64_t b_inc = (uint64_t)(p.b_stride >> 4);
-  const bool do_mma = !(p.debug & 4);
-  for (int l = 0; l < items_cta; ++l) {
-    const int acc = l & acc_mask;
-    const uint32_t ph = ((uint32_t)(l >> acc_log2) & 1u) ^ 1u;
-    mbar_wait(&c.tempty[acc], ph);
-    mbar_wait_cluster(&c.peer_tempty[acc], ph);
-    tc_fence_after();
-    const uint32_t d0 = tmem_base + (uint32_t)acc * acc_stride;
-    for (int g = 0; g < groups_per_item; ++g) {
-      mbar_wait(&fullB[sb], pb);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint64_t off = b_inc * (uint64_t)sb;
-        if (do_mma) {
-#pragma unroll
-          for (int k = 0; k < KSTEPS; ++k)
-            umma_f16_cg2(d0, a_in_b + off + (uint64_t)(2 * k), b_desc0 + off + (uint64_t)(2 * k), idesc,
-                         k == 0 ? (uint32_t)(g != 0) : 1u);
-        }
-        umma_commit_cg2(&emptyB[sb]);
-        if (g == groups_per_item - 1) umma_commit_cg2(&c.tfull[acc]);
-      }
-      if (++sb == stages_b) sb = 0, pb ^= 1;
     }
   }
 }
@@ -660,7 +636,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int first = cg2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int stride_items = cg2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int items_cta = (p.items - first + stride_items - 1) / stride_items;
-  const int tiles_cta = items_cta * (cg2 ? 1 : p.mt);
+  const int tiles_cta = items_cta * p.mt;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -714,18 +690,32 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // cta_group::2: this CTA loads rows [rank * N/2, +N/2) of each weight tile
       const uint32_t b_bytes = (uint32_t)(cg2 ? block_n / 2 : block_n) * row_bytes;
       const int b_row_off = cg2 ? cta_rank * (block_n / 2) : 0;
+      // CTA pair: every load lands in this CTA's shared memory but is counted on the LEADER's barrier, which the
+      // leader's producer arms for both CTAs (so its MMA warp waits on one barrier per stage)
+      auto arm = [&](uint64_t* bar, uint32_t bytes) {
+        if (!CG2) mbar_arrive_expect_tx(bar, bytes);
+        else if (cta_rank == 0) mbar_arrive_expect_tx(bar, 2u * bytes);
+      };
+      auto load_a = [&](void* dst, uint64_t* bar, int c0, int x, int y, int n) {
+        if (CG2) tma_load_4d_cg2(dst, &tmA, mapa_u32(bar, 0), c0, x, y, n);
+        else tma_load_4d(dst, &tmA, bar, c0, x, y, n);
+      };
+      auto load_b = [&](void* dst, uint64_t* bar, int c0, int row, int tap) {
+        if (CG2) tma_load_3d_cg2(dst, &tmB, mapa_u32(bar, 0), c0, row, tap);
+        else tma_load_3d(dst, &tmB, bar, c0, row, tap);
+      };
       if (resident) {
-        mbar_arrive_expect_tx(bres, b_bytes * (uint32_t)(cchunks * boxes * tpb));
+        arm(bres, b_bytes * (uint32_t)(cchunks * boxes * tpb));
         uint8_t* dst = b_base;
         if (mode == 0) {
           for (int b = 0; b < boxes; ++b)                          // consumption order: tap-major, channel chunks inner
-            for (int cc = 0; cc < cchunks; ++cc, dst += b_tile_bytes) tma_load_3d(dst, &tmB, bres, cc * kchunk, 0, b);
+            for (int cc = 0; cc < cchunks; ++cc, dst += b_tile_bytes) load_b(dst, bres, cc * kchunk, b_row_off, b);
         } else {
           for (int cc = 0; cc < cchunks; ++cc)
             for (int b = 0; b < boxes; ++b)
               for (int j = 0; j < tpb; ++j, dst += b_tile_bytes) {
                 const int tap = mode == 1 ? j * 3 + b : (j % 3) * 3 + j / 3;
-                tma_load_3d(dst, &tmB, bres, cc * kchunk, 0, tap);
+                load_b(dst, bres, cc * kchunk, b_row_off, tap);
               }
         }
       }
@@ -739,7 +729,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int i = first; i < p.items; i += stride_items) {
         const int nt = i % n_tiles, mp = i / n_tiles;
         const int nrow = nt * block_n + b_row_off;
-        const int m0 = cg2 ? mp * 2 + cta_rank : mp * mt, m1 = m0 + 1;
+        const int m0 = cg2 ? (mp * 2 + cta_rank) * mt : mp * mt, m1 = m0 + 1;
         const int ax0 = (m0 % tiles_x) * sx_scale - org, ay0 = ((m0 / tiles_x) % tiles_y) * sy_scale - org;
         const int an0 = (m0 / tiles_xy) * p.tn;
         const int ax1 = (m1 % tiles_x) * sx_scale - org, ay1 = ((m1 / tiles_x) % tiles_y) * sy_scale - org;
@@ -753,39 +743,27 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int c0 = (mode == 0 ? in : o) * kchunk;
             if (mode != 0) dx = in;
             {
-              if (CG2) {
-                // CTA pair: both CTAs fill their own stage (own activation box, own half of the weight tile); all
-                // bytes are counted on the LEADER's barrier, which the leader's producer arms for both
-                mbar_wait(&emptyB[sb], pb ^ 1);
-                uint8_t* dst = b_base + (size_t)sb * b_stride;
-                const uint32_t lead_bar = mapa_u32(&fullB[sb], 0);
-                if (cta_rank == 0) mbar_arrive_expect_tx(&fullB[sb], 2u * (b_bytes + a_tx));
-                tma_load_4d_cg2(dst + b_tile_bytes, &tmA, lead_bar, c0, ax0 + dx, ay0 + dy, an0);
-                tma_load_3d_cg2(dst, &tmB, lead_bar, c0, nrow, dy * kw + dx);
-                if (++sb == stages_b) sb = 0, pb ^= 1;
-                continue;
-              }
               if (combined) {
                 // mode 0, streamed weights: one stage = weight tile + activation box(es), one barrier pair per tap
                 mbar_wait(&emptyB[sb], pb ^ 1);
                 uint8_t* dst = b_base + (size_t)sb * b_stride;
-                mbar_arrive_expect_tx(&fullB[sb], skip_a ? b_bytes : b_bytes + a_tx);
-                if (!skip_a) {
-                  tma_load_4d(dst + b_tile_bytes, &tmA, &fullB[sb], c0, ax0 + dx, ay0 + dy, an0);
-                  if (mt == 2) tma_load_4d(dst + b_tile_bytes + a_box_bytes, &tmA, &fullB[sb], c0, ax1 + dx, ay1 + dy, an1);
+                arm(&fullB[sb], (skip_a && !CG2) ? b_bytes : b_bytes + a_tx);
+                if (!skip_a || CG2) {
+                  load_a(dst + b_tile_bytes, &fullB[sb], c0, ax0 + dx, ay0 + dy, an0);
+                  if (mt == 2) load_a(dst + b_tile_bytes + a_box_bytes, &fullB[sb], c0, ax1 + dx, ay1 + dy, an1);
                 }
-                tma_load_3d(dst, &tmB, &fullB[sb], c0, nrow, dy * kw + dx);
+                load_b(dst, &fullB[sb], c0, nrow, dy * kw + dx);
                 if (++sb == stages_b) sb = 0, pb ^= 1;
                 continue;
               }
               mbar_wait(&emptyA[sa], pa ^ 1);
-              if (skip_a) {
+              if (skip_a && !CG2) {
                 mbar_arrive(&fullA[sa]);
               } else {
-                mbar_arrive_expect_tx(&fullA[sa], a_tx);
+                arm(&fullA[sa], a_tx);
                 uint8_t* dst = a_ring + (size_t)sa * a_stage_bytes;
-                tma_load_4d(dst, &tmA, &fullA[sa], c0, ax0 + dx, ay0 + dy, an0);
-                if (mt == 2) tma_load_4d(dst + a_box_bytes, &tmA, &fullA[sa], c0, ax1 + dx, ay1 + dy, an1);
+                load_a(dst, &fullA[sa], c0, ax0 + dx, ay0 + dy, an0);
+                if (mt == 2) load_a(dst + a_box_bytes, &fullA[sa], c0, ax1 + dx, ay1 + dy, an1);
               }
               if (++sa == stages_a) sa = 0, pa ^= 1;
               if (!resident) {
@@ -793,8 +771,8 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   for (int r = 0; r < nr; ++r) {
                     const int tap = r * 3 + dx + sxi;            // halo modes only (mode 0 streamed is combined)
                     mbar_wait(&emptyB[sb], pb ^ 1);
-                    mbar_arrive_expect_tx(&fullB[sb], b_bytes);
-                    tma_load_3d(b_base + (size_t)sb * b_stride, &tmB, &fullB[sb], c0, nrow, tap);
+                    arm(&fullB[sb], b_bytes);
+                    load_b(b_base + (size_t)sb * b_stride, &fullB[sb], c0, nrow, tap);
                     if (++sb == stages_b) sb = 0, pb ^= 1;
                   }
                 }
@@ -813,18 +791,13 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     c.a_ring = smem_u32(a_ring), c.b_base = smem_u32(b_base);
     c.fullA = fullA, c.emptyA = emptyA, c.fullB = fullB, c.emptyB = emptyB, c.tfull = tfull, c.tempty = tempty, c.bres = bres;
     const int ks = p.kchunk >> 4;
-    if constexpr (CG2) {
-      c.peerB = peerB, c.peer_tempty = peer_tempty, c.rank = cta_rank;
-      if (ks == 4) mma_issuer_cg2<4>(p, c);
-      else if (ks == 2) mma_issuer_cg2<2>(p, c);
-      else mma_issuer_cg2<1>(p, c);
-    } else {
+    c.peerB = peerB, c.peer_tempty = peer_tempty, c.rank = cta_rank;
     const int variant = p.a_mode * 3 + (p.b_resident ? 0 : p.mt);     // (mode, {resident, streamed mt=1, streamed mt=2})
 #define B2F_MMA_CASE(MODE, V, MT, RES)                                         \
     case MODE * 3 + V:                                                           \
-      if (ks == 4) mma_issuer<MODE, MT, RES, 4>(p, c);                           \
-      else if (ks == 2) mma_issuer<MODE, MT, RES, 2>(p, c);                      \
-      else mma_issuer<MODE, MT, RES, 1>(p, c);                                   \
+      if (ks == 4) mma_issuer<MODE, MT, RES, 4, CG2>(p, c);                      \
+      else if (ks == 2) mma_issuer<MODE, MT, RES, 2, CG2>(p, c);                 \
+      else mma_issuer<MODE, MT, RES, 1, CG2>(p, c);                              \
       break;
     switch (variant) {
       B2F_MMA_CASE(0, 0, 1, true)
@@ -837,7 +810,6 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       B2F_MMA_CASE(2, 1, 1, false)
       B2F_MMA_CASE(2, 2, 2, false)
       default: break;
-    }
     }
 #undef B2F_MMA_CASE
   } else if (warp < 2 + 4 * p.groups) {
@@ -955,7 +927,14 @@ struct TilePlan {
 };
 
 // returns kTileDeclined (nothing launched) when `optional` and the first persistent kernel is the better fit
+static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream, int optional, int pair);
+
 int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream, int optional) {
+  return conv_tile_plan_launch(d, kchunk, stream, optional, -1);
+}
+
+// pair: -1 = decide here (plan for single CTAs first, re-plan for CTA pairs when the layer qualifies), 0 / 1 = fixed
+static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream, int optional, int pair) {
   if (g_sms == 0) {
     int dev = 0;
     B2F_CHECK_CUDA(cudaGetDevice(&dev));
@@ -972,7 +951,11 @@ int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream, in
   while ((d->cout_p % n_tiles) != 0 || ((d->cout_p / n_tiles) % 16) != 0) ++n_tiles;
   p.n_tiles = n_tiles;
   p.block_n = d->cout_p / n_tiles;
-  p.b_tile_bytes = round_up(p.block_n * row_bytes, 1024);
+  // CTA pairs (cta_group::2): the two CTAs of a cluster run M = 256 MMAs; each holds half of the N rows of every weight
+  // tile, so weight traffic, resident-weight footprint and B operand reads per SM halve
+  const bool pair_legal = g_tile_cg2 != 0 && p.block_n % 32 == 0;
+  p.cg2 = (pair_legal && (pair == 1 || (pair < 0 && g_tile_cg2 == 2))) ? 1 : 0;
+  p.b_tile_bytes = round_up(p.block_n / (p.cg2 ? 2 : 1) * row_bytes, 1024);
   p.acc_stride = round_up(p.block_n, 32);
   p.n_acc_log2 = p.acc_stride <= 128 ? 2 : 1;
   p.is_bf16 = d->dtype == 1;
@@ -1003,7 +986,8 @@ int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream, in
 
   // ---- choose A mode, tile geometry, weight sharing and epilogue groups with a per-tile cycle model -----------
   const double kFabric = 64.0;                               // L2 -> SM bytes per clock per SM the rings can pull (measured 50-65)
-  const double mma_tap = ksteps * ((p.block_n / 2.0) > ((128 + p.block_n) / 4.0) ? (p.block_n / 2.0) : ((128 + p.block_n) / 4.0));
+  const double opnd = (128 + p.block_n / (p.cg2 ? 2.0 : 1.0)) / 4.0;      // operand reads per MMA, clocks at 128 B/clk
+  const double mma_tap = ksteps * ((p.block_n / 2.0) > opnd ? (p.block_n / 2.0) : opnd);
   // halo modes only for narrow tiles: wide ones keep one accumulation order across both kernel generations
   const bool halo_ok = g_vhalo && d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && p.block_n <= 128;
   const int b_all = taps * p.cchunks * p.b_tile_bytes;
@@ -1029,6 +1013,7 @@ int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream, in
         const int resident = (mt == 1 && n_tiles == 1 && b_all <= 100 * 1024) ? 1 : 0;   // sharing only pays when streaming
         if (f_mt && mt != f_mt && !(mt == 1 && (p.n_acc_log2 < 2 || m_tiles < 2))) continue;
         if (mt == 2 && (p.n_acc_log2 < 2 || m_tiles < 2)) continue;
+        if (p.cg2 && m_tiles < 2 * mt) continue;
         for (int groups = 4; groups >= 2; groups -= 2) {
           if (groups > (1 << p.n_acc_log2)) continue;          // a group must never be a whole accumulator phase ahead
           if (f_groups && groups != f_groups && f_groups <= (1 << p.n_acc_log2)) continue;
@@ -1057,7 +1042,7 @@ int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream, in
           // cycles per M tile: tensor pipe (operand reads from shared memory included), L2 -> SM traffic at the
           // rate the bytes in flight can sustain (Little: ~2000 cycles from issue to a reusable slot), epilogue
           const double mma = taps * p.cchunks * mma_tap;
-          const double b_bytes = (double)p.block_n * row_bytes;
+          const double b_bytes = (double)p.block_n * row_bytes / (p.cg2 ? 2.0 : 1.0);
           const double bytes = (double)p.cchunks * boxes * a_bytes + (resident ? 0.0 : (double)taps * p.cchunks * b_bytes / mt);
           const double inflight = (double)(stages_a - 1) * mt * a_bytes + (resident ? 0.0 : (double)(stages_b - 1) * b_bytes);
           double rate = inflight / 2000.0;
@@ -1082,6 +1067,16 @@ int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream, in
     }
   }
   }
+  if (best.cost < 0 && p.cg2)                     // a one-tile problem cannot be paired: plan for single CTAs
+    return conv_tile_plan_launch(d, kchunk, stream, optional, 0);
+  if (pair < 0 && g_tile_cg2 == 1 && pair_legal && !p.cg2 && best.cost >= 0) {
+    // CTA pairs pay when the pair's single issuing thread has long stages to issue (its barrier round trips cross
+    // the cluster) and the tile is MMA-heavy rather than epilogue-bound; measured in profiles/r01_conv_sweep_cta_pairs.log
+    const int tpb = best.mode == 0 ? 1 : (best.mode == 1 ? 3 : 9);
+    const double stage_cyc = tpb * mma_tap, tile_cyc = (double)taps * p.cchunks * mma_tap;
+    if (p.block_n > g_tile_cg2_min_n || (stage_cyc >= 500.0 && tile_cyc >= 1200.0))
+      return conv_tile_plan_launch(d, kchunk, stream, optional, 1);
+  }
   B2F_REQUIRE(best.cost >= 0, "conv: no tile plan fits in shared memory (cin_p %d cout_p %d k %d)", d->cin_p, d->cout_p, d->kh);
   if (best.mode == 0) pick_m_tile(d->n, Ho, Wo, d->stride, &best.tw, &best.th, &best.tn);   // geometry for the real batch
   p.a_mode = best.mode, p.tw = best.tw, p.th = best.th, p.tn = best.tn, p.mt = best.mt, p.groups = best.groups;
@@ -1103,19 +1098,7 @@ int conv_tile_launch(const b2f_conv_desc* d, int kchunk, cudaStream_t stream, in
   p.a_stage_bytes = p.a_box_bytes * p.mt;
   p.stg_box_bytes = p.tw * p.th * p.tn * p.ochunk * 2;
   p.combined = (p.a_mode == 0 && !p.b_resident) ? 1 : 0;
-  // CTA pair: the two CTAs of a cluster each take one of the item's two M tiles and half of every weight tile
-  p.cg2 = (g_tile_cg2 && p.combined && p.block_n % 32 == 0 && p.m_tiles >= 2 && (g_tile_cg2 == 2 || p.block_n > 128)) ? 1 : 0;
-  if (p.cg2) {
-    p.mt = 1;
-    p.a_stage_bytes = p.a_box_bytes;
-    p.b_tile_bytes = round_up(p.block_n / 2 * row_bytes, 1024);
-    p.items = n_tiles * ((p.m_tiles + 1) / 2);
-    if (p.groups > (1 << p.n_acc_log2)) p.groups = 1 << p.n_acc_log2;
-    const int staging = p.epi_tma ? p.groups * p.stg_bufs * p.stg_bytes : 0;
-    p.stages_b = (kSmemMax - fixed - staging) / (p.b_tile_bytes + p.a_stage_bytes);
-    if (p.stages_b > kTStages) p.stages_b = kTStages;
-    B2F_REQUIRE(p.stages_b >= 2, "conv (CTA pair): not enough shared memory for two stages");
-  }
+  if (p.cg2) p.items = n_tiles * ((p.m_tiles + 2 * p.mt - 1) / (2 * p.mt));      // an item = 2 x mt M tiles, mt per CTA
   p.b_stride = p.combined ? p.b_tile_bytes + p.a_stage_bytes : p.b_tile_bytes;
   if (p.combined) p.stages_a = 0;                      // activation boxes live inside the weight stages
   p.off_b = p.stages_a * p.a_stage_bytes;

@@ -236,6 +236,7 @@ def test_conv_kernel_variants_agree(lib, case):
     variants += [(3, 1, am, mt, gr, 1, 0) for am in (0, 1, 2) for mt in (1, 2) for gr in (2, 4)]
     variants += [(3, 1, 2, 1, 4, 0, 0), (3, 1, 0, 2, 2, 0, 0)]
     variants += [(3, 1, 0, 0, 0, -1, 2), (3, 1, 0, 0, 2, 1, 2), (3, 1, 0, 0, 4, 0, 2)]      # CTA pairs (cta_group::2)
+    variants += [(3, 1, am, mt, 2, 1, 2) for am in (1, 2) for mt in (1, 2)] + [(3, 1, -1, 0, 0, -1, 2), (3, 1, 2, 1, 4, 0, 2)]
     try:
         for persistent, vhalo, amode, mt, groups, epi, cg2 in variants:
             for key, val in ((2, persistent), (3, vhalo), (7, amode), (6, mt), (5, groups), (8, epi), (11, cg2)):
