@@ -21,7 +21,8 @@ for l in launch.values():
 print(f"{'kernel':58s} {'n':>5s} {'us':>10s} {'share':>7s} {'dram MB':>10s}")
 for k, (n, t, b) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{k[:58]:58s} {n:5d} {t:10.1f} {100*t/tot_t:6.1f}% {b/1e6:10.1f}")
-conv = [(n, t, b) for k, (n, t, b) in agg.items() if ("umma_conv" in k or "conv_tile" in k) and "ILi1" not in k and "<1>" not in k and "<2>" not in k]
+conv = [(n, t, b) for k, (n, t, b) in agg.items()
+        if "conv_tile" in k or ("umma_conv" in k and "umma_conv_kernel<1>" not in k and "umma_conv_kernel<2>" not in k)]
 if out_json and conv:
     n = sum(c[0] for c in conv); b = sum(c[2] for c in conv); t = sum(c[1] for c in conv)
     json.dump({"source": path, "conv_launches": n, "dram_bytes_per_launch": b / n, "conv_us_total": t,
