@@ -508,7 +508,7 @@ def conv_roofline(a, det, rec, frames, pipe, B, F):
     tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")
     if os.path.exists(tpath):                       # dram bytes per conv launch from the committed ncu capture
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-    return {"bound": "tensor", "kernel": "umma_conv_*_kernel (all conv/FC launches of SCRFD-10G + R50)",
+    return {"bound": "tensor", "kernel": "conv_tile_kernel<CG2> + umma_conv_persistent_kernel (all conv/FC launches of SCRFD-10G + R50)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
             "flops_per_launch": flops / max(len(rows), 1), "ms_per_launch": ms / max(len(rows), 1),
             "peak_source": src, "launches_per_step": len(rows), "flops_per_step": flops, "conv_ms_per_step": ms}
