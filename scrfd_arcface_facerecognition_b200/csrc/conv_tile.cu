@@ -38,6 +38,7 @@ int g_tile_amode = -1;   // -1 = auto, else force A mode 0 / 1 / 2 where legal
 int g_tile_epi = -1;     // -1 = auto, 0 = direct global stores, 1 = TMA stores
 int g_tile_cg2 = 1;      // CTA pairs (cta_group::2): 0 = never, 1 = tiles wider than g_tile_cg2_min_n, 2 = wherever legal
 int g_tile_cg2_min_n = 128;
+int g_tile_pdl = 1;      // programmatic dependent launch between consecutive layers
 
 constexpr int kTStages = 16;
 constexpr int kTAcc = 4;
@@ -57,6 +58,7 @@ struct TileParams {
   int b_tile_bytes, stages_b, b_resident;
   int b_stride;             // bytes between weight stages; mode 0 streamed: the stage also holds its activation box(es)
   int combined;             // 1: one barrier pair per tap covers the weight tile and the activation boxes (mode 0, streamed)
+  int pdl;                  // launched with programmatic stream serialization
   int cg2;                  // 1: CTA pair (cluster of 2, tcgen05 cta_group::2): M = 256 over two SMs, each loads half of B
   int n_acc_log2, acc_stride;
   int groups;
@@ -93,6 +95,11 @@ __device__ __forceinline__ void bar_sync_named(int id, int threads) {
 // CTA-pair (cta_group::2) pieces: the two CTAs of a cluster run one M = 256 MMA; each holds its own 128 rows of A and
 // half of the N rows of B, so the weight traffic and the B operand reads per SM halve
 // ------------------------------------------------------------------------------------------
+// programmatic dependent launch: let the next kernel in the stream start its prologue while this one drains, and
+// hold this kernel's first read of the previous kernel's output until that kernel has completed and flushed
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -675,6 +682,12 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if constexpr (CG2) cluster_sync_all();  // the peer's barriers and TMEM exist before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only weights-side constants (bias table, slopes, tensor maps): it may overlap the tail of
+  // the previous layer; activations and residuals are read below
+  if (p.pdl) {
+    pdl_launch_dependents();
+    pdl_wait_primary();
+  }
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -1154,24 +1167,31 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
             "block_n %d kchunk %d epi_tma %d res_smem %d ochunk %d bufs %d cg2 %d smem %zu items %d\n", d->n, d->h, d->w, d->cin_p, d->cout_p, d->kh, d->stride,
             p.a_mode, p.tw, p.th, p.tn, p.mt, p.groups, p.b_resident, p.stages_a, p.stages_b, p.block_n, kchunk, p.epi_tma,
             p.res_smem, p.ochunk, p.stg_bufs, p.cg2, smem, p.items);
+  p.pdl = g_tile_pdl ? 1 : 0;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[2];
+  int n_attr = 0;
+  if (p.pdl) {
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
+  cfg.blockDim = dim3(64 + 128 * p.groups), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
   if (p.cg2) {
     const int clusters = p.items < g_sms / 2 ? p.items : g_sms / 2;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * clusters), cfg.blockDim = dim3(64 + 128 * p.groups);
-    cfg.dynamicSmemBytes = smem, cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
+    cfg.gridDim = dim3(2 * clusters);
+    attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attr[n_attr].val.clusterDim.x = 2, attr[n_attr].val.clusterDim.y = 1, attr[n_attr].val.clusterDim.z = 1;
+    ++n_attr;
+    cfg.attrs = attr, cfg.numAttrs = n_attr;
     B2F_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true>, tmA, tmB, tmO, tmR, p));
-    g_launches.fetch_add(1);
-    return 0;
+  } else {
+    cfg.gridDim = dim3(p.items < g_sms ? p.items : g_sms);
+    cfg.attrs = attr, cfg.numAttrs = n_attr;
+    B2F_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tile_kernel<false>, tmA, tmB, tmO, tmR, p));
   }
-  const int grid = p.items < g_sms ? p.items : g_sms;
-  conv_tile_kernel<false><<<grid, 64 + 128 * p.groups, smem, stream>>>(tmA, tmB, tmO, tmR, p);
   g_launches.fetch_add(1);
-  B2F_LAUNCH_CHECK();
   return 0;
 }
 
