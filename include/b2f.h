@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define B2F_ABI_VERSION 1
+#define B2F_ABI_VERSION 2
 
 /* dtype codes */
 #define B2F_F16 0
@@ -134,6 +134,12 @@ typedef struct b2f_conv_desc {
   const float* slope;       /* [cout_p] for PReLU */
   const void* residual;
   void* out;
+  /* optional projection shortcut fused as extra K (ResNet down-sampling blocks: out += conv1x1_stride_s(sc_in)):
+   * sc_in [n][sc_h][sc_w][sc_cin_p], sc_weight [1][cout_p][sc_cin_p], no padding, stride sc_stride, same output size;
+   * its bias is expected to be folded into `bias`.  NULL = none. */
+  const void* sc_in;
+  const void* sc_weight;
+  int sc_cin_p, sc_stride, sc_h, sc_w;
 } b2f_conv_desc;
 int b2f_conv2d(const b2f_conv_desc* desc, void* stream);
 

@@ -59,6 +59,7 @@ struct TileParams {
   int b_stride;             // bytes between weight stages; mode 0 streamed: the stage also holds its activation box(es)
   int combined;             // 1: one barrier pair per tap covers the weight tile and the activation boxes (mode 0, streamed)
   int pdl;                  // launched with programmatic stream serialization
+  int sc_cchunks, sc_stride; // fused projection shortcut: extra K chunks from a second tensor (mode 0 only), its stride
   int cg2;                  // 1: CTA pair (cluster of 2, tcgen05 cta_group::2): M = 256 over two SMs, each loads half of B
   int n_acc_log2, acc_stride;
   int groups;
@@ -495,7 +496,7 @@ __device__ __forceinline__ void mma_issuer(const TileParams& p, const MmaCtx& c)
   constexpr int TPB = MODE == 0 ? 1 : (MODE == 1 ? 3 : 9);
   const uint32_t row_bytes = p.kchunk * 2;
   const uint32_t idesc = umma_idesc(CG2 ? 256 : 128, (uint32_t)p.block_n, (uint32_t)p.is_bf16);
-  const int groups_per_item = p.cchunks * p.boxes_per_chunk;
+  const int groups_per_item = p.cchunks * p.boxes_per_chunk + p.sc_cchunks;      // shortcut chunks ride as extra taps
   const int stages_a = p.stages_a, stages_b = p.stages_b, items_cta = c.items_cta;
   const int acc_mask = (1 << p.n_acc_log2) - 1, acc_log2 = p.n_acc_log2;
   const uint32_t acc_stride = (uint32_t)p.acc_stride, tmem_base = c.tmem_base;
@@ -608,7 +609,8 @@ __device__ __forceinline__ void mma_issuer(const TileParams& p, const MmaCtx& c)
 template <bool CG2>
 __global__ void __launch_bounds__(64 + 128 * kTGroups, 1)
 conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const TileParams p) {
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const TileParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -709,20 +711,24 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (!CG2) mbar_arrive_expect_tx(bar, bytes);
         else if (cta_rank == 0) mbar_arrive_expect_tx(bar, 2u * bytes);
       };
-      auto load_a = [&](void* dst, uint64_t* bar, int c0, int x, int y, int n) {
-        if (CG2) tma_load_4d_cg2(dst, &tmA, mapa_u32(bar, 0), c0, x, y, n);
-        else tma_load_4d(dst, &tmA, bar, c0, x, y, n);
+      auto load_a_from = [&](const CUtensorMap* tm, void* dst, uint64_t* bar, int c0, int x, int y, int n) {
+        if (CG2) tma_load_4d_cg2(dst, tm, mapa_u32(bar, 0), c0, x, y, n);
+        else tma_load_4d(dst, tm, bar, c0, x, y, n);
       };
-      auto load_b = [&](void* dst, uint64_t* bar, int c0, int row, int tap) {
-        if (CG2) tma_load_3d_cg2(dst, &tmB, mapa_u32(bar, 0), c0, row, tap);
-        else tma_load_3d(dst, &tmB, bar, c0, row, tap);
+      auto load_b_from = [&](const CUtensorMap* tm, void* dst, uint64_t* bar, int c0, int row, int tap) {
+        if (CG2) tma_load_3d_cg2(dst, tm, mapa_u32(bar, 0), c0, row, tap);
+        else tma_load_3d(dst, tm, bar, c0, row, tap);
       };
+      auto load_a = [&](void* dst, uint64_t* bar, int c0, int x, int y, int n) { load_a_from(&tmA, dst, bar, c0, x, y, n); };
+      auto load_b = [&](void* dst, uint64_t* bar, int c0, int row, int tap) { load_b_from(&tmB, dst, bar, c0, row, tap); };
+      const int sc_cchunks = p.sc_cchunks;
       if (resident) {
-        arm(bres, b_bytes * (uint32_t)(cchunks * boxes * tpb));
+        arm(bres, b_bytes * (uint32_t)(cchunks * boxes * tpb + sc_cchunks));
         uint8_t* dst = b_base;
         if (mode == 0) {
           for (int b = 0; b < boxes; ++b)                          // consumption order: tap-major, channel chunks inner
             for (int cc = 0; cc < cchunks; ++cc, dst += b_tile_bytes) load_b(dst, bres, cc * kchunk, b_row_off, b);
+          for (int cc = 0; cc < sc_cchunks; ++cc, dst += b_tile_bytes) load_b_from(&tmB2, dst, bres, cc * kchunk, b_row_off, 0);
         } else {
           for (int cc = 0; cc < cchunks; ++cc)
             for (int b = 0; b < boxes; ++b)
@@ -793,6 +799,28 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if (mode == 0 && ++dx == nbx) dx = 0, ++dy;
+        }
+        // fused projection shortcut: extra K chunks whose activation boxes come from the block input (1x1, no padding)
+        for (int cc = 0; cc < sc_cchunks; ++cc) {
+          const int c0 = cc * kchunk;
+          const int sx0 = (ax0 + org) / p.stride * p.sc_stride, sy0 = (ay0 + org) / p.stride * p.sc_stride;
+          const int sx1 = (ax1 + org) / p.stride * p.sc_stride, sy1 = (ay1 + org) / p.stride * p.sc_stride;
+          if (combined) {
+            mbar_wait(&emptyB[sb], pb ^ 1);
+            uint8_t* dst = b_base + (size_t)sb * b_stride;
+            arm(&fullB[sb], b_bytes + a_tx);
+            load_a_from(&tmA2, dst + b_tile_bytes, &fullB[sb], c0, sx0, sy0, an0);
+            if (mt == 2) load_a_from(&tmA2, dst + b_tile_bytes + a_box_bytes, &fullB[sb], c0, sx1, sy1, an1);
+            load_b_from(&tmB2, dst, &fullB[sb], c0, nrow, 0);
+            if (++sb == stages_b) sb = 0, pb ^= 1;
+          } else {                                   // resident weights: only the activation box streams
+            mbar_wait(&emptyA[sa], pa ^ 1);
+            arm(&fullA[sa], a_tx);
+            uint8_t* dst = a_ring + (size_t)sa * a_stage_bytes;
+            load_a_from(&tmA2, dst, &fullA[sa], c0, sx0, sy0, an0);
+            if (mt == 2) load_a_from(&tmA2, dst + a_box_bytes, &fullA[sa], c0, sx1, sy1, an1);
+            if (++sa == stages_a) sa = 0, pa ^= 1;
+          }
         }
       }
     }
@@ -959,6 +987,13 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   p.N = d->n, p.Ho = Ho, p.Wo = Wo, p.H = d->h, p.W = d->w, p.cout_p = d->cout_p;
   p.kh = d->kh, p.kw = d->kw, p.stride = d->stride, p.pad = d->pad;
   p.kchunk = kchunk, p.cchunks = d->cin_p / kchunk;
+  if (d->sc_in != nullptr) {
+    B2F_REQUIRE(d->sc_weight != nullptr && d->sc_cin_p > 0 && d->sc_cin_p % kchunk == 0 && d->sc_stride >= 1,
+                "b2f_conv2d: fused shortcut needs sc_weight and sc_cin_p (%d) divisible by the K chunk (%d)", d->sc_cin_p, kchunk);
+    B2F_REQUIRE((d->sc_h - 1) / d->sc_stride + 1 == d->ho && (d->sc_w - 1) / d->sc_stride + 1 == d->wo,
+                "b2f_conv2d: fused shortcut output size mismatch");
+    p.sc_cchunks = d->sc_cin_p / kchunk, p.sc_stride = d->sc_stride;
+  }
   const int row_bytes = kchunk * 2, ksteps = kchunk / 16, taps = d->kh * d->kw;
   int n_tiles = (d->cout_p + g_max_block_n - 1) / g_max_block_n;
   while ((d->cout_p % n_tiles) != 0 || ((d->cout_p / n_tiles) % 16) != 0) ++n_tiles;
@@ -1002,8 +1037,9 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   const double opnd = (128 + p.block_n / (p.cg2 ? 2.0 : 1.0)) / 4.0;      // operand reads per MMA, clocks at 128 B/clk
   const double mma_tap = ksteps * ((p.block_n / 2.0) > opnd ? (p.block_n / 2.0) : opnd);
   // halo modes only for narrow tiles: wide ones keep one accumulation order across both kernel generations
-  const bool halo_ok = g_vhalo && d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && p.block_n <= 128;
-  const int b_all = taps * p.cchunks * p.b_tile_bytes;
+  const bool halo_ok = g_vhalo && d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && p.block_n <= 128 &&
+                       p.sc_cchunks == 0;
+  const int b_all = (taps * p.cchunks + p.sc_cchunks) * p.b_tile_bytes;
   // The plan (A mode, weight sharing) fixes the order in which taps are accumulated; it is chosen for a batch of
   // at least 128 images so that an image's result does not depend on how many others share its launch.
   const int n_plan = d->n < 128 ? 128 : d->n;
@@ -1054,9 +1090,10 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
           if (stages_a < 2) continue;
           // cycles per M tile: tensor pipe (operand reads from shared memory included), L2 -> SM traffic at the
           // rate the bytes in flight can sustain (Little: ~2000 cycles from issue to a reusable slot), epilogue
-          const double mma = taps * p.cchunks * mma_tap;
+          const double mma = (taps * p.cchunks + p.sc_cchunks) * mma_tap;
           const double b_bytes = (double)p.block_n * row_bytes / (p.cg2 ? 2.0 : 1.0);
-          const double bytes = (double)p.cchunks * boxes * a_bytes + (resident ? 0.0 : (double)taps * p.cchunks * b_bytes / mt);
+          const double bytes = (double)(p.cchunks * boxes + p.sc_cchunks) * a_bytes +
+                               (resident ? 0.0 : (double)(taps * p.cchunks + p.sc_cchunks) * b_bytes / mt);
           const double inflight = (double)(stages_a - 1) * mt * a_bytes + (resident ? 0.0 : (double)(stages_b - 1) * b_bytes);
           double rate = inflight / 2000.0;
           if (rate > kFabric) rate = kFabric;
@@ -1101,7 +1138,7 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   // wide tiles have two accumulators and two epilogue groups: with only a few tiles per SM the exposed epilogue of
   // the last tile costs more than the first persistent kernel's column-split epilogue
   // (both kernels accumulate wide tiles in the same order, so this batch-dependent choice does not change results)
-  if (optional && p.block_n > 128 && p.items < 4 * g_sms) return kTileDeclined;
+  if (optional && p.block_n > 128 && p.items < 4 * g_sms && p.sc_cchunks == 0) return kTileDeclined;
   p.boxes_per_chunk = p.a_mode == 0 ? taps : (p.a_mode == 1 ? 3 : 1);
   p.taps_per_box = taps / p.boxes_per_chunk;
   const int box_w = p.a_mode == 0 ? p.tw * d->stride : (p.a_mode == 1 ? p.tw : p.tw + 2);
@@ -1122,7 +1159,7 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   B2F_REQUIRE(smem <= (size_t)kSmemMax, "conv tile kernel: %zu bytes of shared memory requested", smem);
   if (smem < 120 * 1024) smem = 120 * 1024;      // one CTA per SM: it owns all 512 TMEM columns
 
-  CUtensorMap tmA, tmB, tmO, tmR;
+  CUtensorMap tmA, tmB, tmO, tmR, tmA2, tmB2;
   {
     uint64_t dims[4] = {(uint64_t)d->cin_p, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
     uint64_t str[3] = {(uint64_t)d->cin_p * 2, (uint64_t)d->w * d->cin_p * 2, (uint64_t)d->h * d->w * d->cin_p * 2};
@@ -1138,6 +1175,21 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
     uint32_t box[3] = {(uint32_t)kchunk, (uint32_t)(p.cg2 ? p.block_n / 2 : p.block_n), 1};
     uint32_t es[3] = {1, 1, 1};
     int rc = make_tmap(&tmB, d->weight, 3, dims, str, box, es, row_bytes, p.is_bf16);
+    if (rc) return rc;
+  }
+  tmA2 = tmA, tmB2 = tmB;
+  if (p.sc_cchunks) {
+    uint64_t dims[4] = {(uint64_t)d->sc_cin_p, (uint64_t)d->sc_w, (uint64_t)d->sc_h, (uint64_t)d->n};
+    uint64_t str[3] = {(uint64_t)d->sc_cin_p * 2, (uint64_t)d->sc_w * d->sc_cin_p * 2, (uint64_t)d->sc_h * d->sc_w * d->sc_cin_p * 2};
+    uint32_t box[4] = {(uint32_t)kchunk, (uint32_t)(p.tw * d->sc_stride), (uint32_t)(p.th * d->sc_stride), (uint32_t)p.tn};
+    uint32_t es[4] = {1, (uint32_t)d->sc_stride, (uint32_t)d->sc_stride, 1};
+    int rc = make_tmap(&tmA2, d->sc_in, 4, dims, str, box, es, row_bytes, p.is_bf16);
+    if (rc) return rc;
+    uint64_t dimsb[3] = {(uint64_t)d->sc_cin_p, (uint64_t)d->cout_p, 1};
+    uint64_t strb[2] = {(uint64_t)d->sc_cin_p * 2, (uint64_t)d->cout_p * d->sc_cin_p * 2};
+    uint32_t boxb[3] = {(uint32_t)kchunk, (uint32_t)(p.cg2 ? p.block_n / 2 : p.block_n), 1};
+    uint32_t esb[3] = {1, 1, 1};
+    rc = make_tmap(&tmB2, d->sc_weight, 3, dimsb, strb, boxb, esb, row_bytes, p.is_bf16);
     if (rc) return rc;
   }
   tmO = tmA, tmR = tmA;
@@ -1185,11 +1237,11 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
     attr[n_attr].val.clusterDim.x = 2, attr[n_attr].val.clusterDim.y = 1, attr[n_attr].val.clusterDim.z = 1;
     ++n_attr;
     cfg.attrs = attr, cfg.numAttrs = n_attr;
-    B2F_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true>, tmA, tmB, tmO, tmR, p));
+    B2F_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tile_kernel<true>, tmA, tmB, tmO, tmR, tmA2, tmB2, p));
   } else {
     cfg.gridDim = dim3(p.items < g_sms ? p.items : g_sms);
     cfg.attrs = attr, cfg.numAttrs = n_attr;
-    B2F_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tile_kernel<false>, tmA, tmB, tmO, tmR, p));
+    B2F_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tile_kernel<false>, tmA, tmB, tmO, tmR, tmA2, tmB2, p));
   }
   g_launches.fetch_add(1);
   return 0;

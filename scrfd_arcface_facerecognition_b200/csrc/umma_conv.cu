@@ -1053,6 +1053,7 @@ extern "C" int b2f_conv2d(const b2f_conv_desc* d, void* stream_) {
     const int rc = conv_tile_launch(d, p.kchunk, stream, g_persistent == 2);
     if (rc != -1000) return rc;
   }
+  B2F_REQUIRE(d->sc_in == nullptr, "b2f_conv2d: the fused shortcut needs conv_tile_kernel (tuning key 2 >= 2)");
   p.cchunks = d->cin_p / p.kchunk;
   pick_m_tile(d->n, Ho, Wo, d->stride, &p.tw, &p.th, &p.tn);
   p.tiles_x = (Wo + p.tw - 1) / p.tw;

@@ -58,7 +58,7 @@ class NetEngine:
             dev: Dict[str, torch.Tensor] = {}
             for k, arr in op.arrays.items():
                 t = torch.from_numpy(np.ascontiguousarray(arr))
-                if op.kind == "conv" and k == "weight":
+                if op.kind == "conv" and k in ("weight", "sc_weight"):
                     t = t.to(tdt)
                 dev[k] = t.to(self.device).contiguous()
             self._weights.append(dev)
@@ -69,6 +69,8 @@ class NetEngine:
             self._last_use[op.src] = i
             if op.residual:
                 self._last_use[op.residual] = i
+            if op.sc_src:
+                self._last_use[op.sc_src] = i
         self._out_tensors = {o[1] for o in plan.outputs}
 
     # ------------------------------------------------------------------------------------------
@@ -103,7 +105,7 @@ class NetEngine:
             view = raw[:nbytes].view(torch.float32 if spec.f32 else torch_dtype(self.dtype))
             tens[op.dst] = view.view(n, spec.h, spec.w, spec.cp)
             bound.append(self._bind_op(i, op, n, tens))
-            for name in (op.src, op.residual):
+            for name in (op.src, op.residual, op.sc_src):
                 if name and name in backing and self._last_use.get(name) == i and name not in self._out_tensors:
                     free.append(backing.pop(name))
         return bound, tens, all_bufs
@@ -133,7 +135,11 @@ class NetEngine:
             d.slope = _ptr(w.get("slope"))
             d.residual = _ptr(res)
             d.out = dst.data_ptr()
-            return _Bound(lib.b2f_conv2d, (C.byref(d),), (d, src, dst, res))
+            sc = tens[op.sc_src] if op.sc_src else None
+            if sc is not None:                      # projection shortcut fused as extra K
+                d.sc_in, d.sc_weight = sc.data_ptr(), w["sc_weight"].data_ptr()
+                d.sc_cin_p, d.sc_stride, d.sc_h, d.sc_w = self.plan.tensors[op.sc_src].cp, a["sc_stride"], a["sc_h"], a["sc_w"]
+            return _Bound(lib.b2f_conv2d, (C.byref(d),), (d, src, dst, res, sc))
         if op.kind == "im2col":
             return _Bound(lib.b2f_im2col3x3,
                           (src.data_ptr(), n, a["h"], a["w"], a["stride"], a["ho"], a["wo"], self.dtype, dst.data_ptr()),

@@ -57,6 +57,7 @@ class FusedOp:
     attrs: Dict[str, int] = field(default_factory=dict)
     arrays: Dict[str, np.ndarray] = field(default_factory=dict)   # kernel-layout host arrays
     order: int = 0
+    sc_src: Optional[str] = None    # fused projection shortcut: second input tensor (arrays['sc_weight'], attrs sc_*)
 
 
 @dataclass
@@ -130,7 +131,8 @@ def _infer_shapes(g: Graph, in_hw: Tuple[int, int]) -> Dict[str, Tuple[int, ...]
     return shapes
 
 
-def compile_graph(g: Graph, in_hw: Tuple[int, int], stem_im2col: bool = True, merge_heads: bool = True) -> Plan:
+def compile_graph(g: Graph, in_hw: Tuple[int, int], stem_im2col: bool = True, merge_heads: bool = True,
+                  fuse_shortcuts: bool = True) -> Plan:
     nodes = g.nodes
     init = g.initializers
     shapes = _infer_shapes(g, in_hw)
@@ -447,6 +449,61 @@ def compile_graph(g: Graph, in_hw: Tuple[int, int], stem_im2col: bool = True, me
                              dict(weight=wk, bias=bias), min(m.order for m in members))
             ops = [o for o in ops if o not in members] + [merged]
 
+    # ---- projection shortcuts ride as extra K of the convolution they are added to ----------------------------
+    # ResNet down-sampling block: out = conv_kxk(y) + conv_1x1_stride_s(x).  The 1x1 launch, its output tensor and the
+    # residual read disappear: the kernel appends the shortcut's K chunks (activation boxes from x) after the taps.
+    if fuse_shortcuts:
+        def kchunk_of(cp: int) -> int:
+            return 64 if cp % 64 == 0 else (32 if cp % 32 == 0 else 16)
+        readers: Dict[str, int] = {}
+        for op in ops:
+            for t in (op.src, op.residual):
+                if t:
+                    readers[t] = readers.get(t, 0) + 1
+        by_dst = {op.dst: op for op in ops}
+
+        def is_projection(o: FusedOp) -> bool:
+            b = o.attrs
+            return o.kind == "conv" and b.get("kh") == 1 and b.get("kw") == 1 and b.get("pad") == 0 \
+                and b.get("bias_classes") == 1 and o.sc_src is None
+
+        for op in list(ops):
+            if op not in ops or op.kind != "conv" or op.res_mode != 1 or not op.residual or op.residual not in by_dst:
+                continue
+            other = by_dst[op.residual]
+            if other is op or other.kind != "conv" or other.residual or other.act != ACT_NONE or other.sc_src \
+                    or readers.get(other.dst, 0) != 1 or other.dst in out_names:
+                continue
+            a, b = op.attrs, other.attrs
+            if (b["ho"], b["wo"]) != (a["ho"], a["wo"]) or b["cout"] != a["cout"]:
+                continue
+            # the Add may have been absorbed by either convolution: `main` keeps its taps, `proj` becomes extra K
+            if is_projection(other) and not (is_projection(op) and a["cin"] < b["cin"]):
+                main, proj = op, other
+            elif is_projection(op):
+                main, proj = other, op
+            else:
+                continue
+            ma = main.attrs
+            if ma["kh"] == 3 and ma["kw"] == 3 and ma["stride"] == 1 and ma["pad"] == 1:
+                continue                            # stride-1 3x3 layers run on halo boxes, which extra per-tap chunks would forfeit
+            cin_p, sc_cin_p = main.arrays["weight"].shape[2], proj.arrays["weight"].shape[2]
+            if sc_cin_p % kchunk_of(cin_p) != 0:
+                continue
+            pa = proj.attrs
+            main.arrays["sc_weight"] = proj.arrays["weight"]
+            main.arrays["bias"] = main.arrays["bias"] + proj.arrays["bias"][0][None, :]
+            main.attrs.update(sc_cin=pa["cin"], sc_stride=pa["stride"], sc_h=pa["h"], sc_w=pa["w"],
+                              macs_per_image=main.attrs["macs_per_image"] + pa["macs_per_image"])
+            main.sc_src = proj.src
+            if main is other:                       # the fused op takes over the Add's output, activation and position
+                main.dst, main.act, main.order = op.dst, op.act, max(op.order, other.order)
+                if "slope" in op.arrays:
+                    main.arrays["slope"] = op.arrays["slope"]
+                by_dst[main.dst] = main
+            main.residual, main.res_mode = None, 0
+            ops.remove(proj)
+
     # ---- topological order over fused ops ------------------------------------------------------------
     inp = g.real_inputs()[0].name
     produced_by = {op.dst: op for op in ops}
@@ -456,14 +513,14 @@ def compile_graph(g: Graph, in_hw: Tuple[int, int], stem_im2col: bool = True, me
     while pending:
         progressed = False
         for op in list(pending):
-            deps = [op.src] + ([op.residual] if op.residual else [])
+            deps = [op.src] + ([op.residual] if op.residual else []) + ([op.sc_src] if op.sc_src else [])
             if all(d in done for d in deps):
                 ordered.append(op)
                 done.add(op.dst)
                 pending.remove(op)
                 progressed = True
         if not progressed:
-            missing = {d for op in pending for d in [op.src, op.residual] if d and d not in done and d not in produced_by}
+            missing = {d for op in pending for d in [op.src, op.residual, op.sc_src] if d and d not in done and d not in produced_by}
             raise RuntimeError(f"graph compile: unresolved tensors {sorted(missing)[:5]}")
 
     # ---- tensor table ----------------------------------------------------------------------------------

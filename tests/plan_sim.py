@@ -46,6 +46,9 @@ def run_plan(plan: Plan, x_nchw: np.ndarray, quantize=None):
                 wk = op.arrays["weight"]                                   # (taps, cout_p, cin_p)
                 w = torch.from_numpy(wk[:, :cout, :a["cin"]]).permute(1, 2, 0).reshape(cout, a["cin"], a["kh"], a["kw"])
                 y = F.conv2d(x, qz(w.contiguous()), None, a["stride"], a["pad"])
+                if op.sc_src:                                               # fused projection shortcut (1x1, no padding)
+                    ws = torch.from_numpy(op.arrays["sc_weight"][0, :cout, :a["sc_cin"]]).reshape(cout, a["sc_cin"], 1, 1)
+                    y = y + F.conv2d(env[op.sc_src], qz(ws.contiguous()), None, a["sc_stride"], 0)
                 bias = torch.from_numpy(op.arrays["bias"])[:, :cout]      # (classes, cout)
                 if bias.shape[0] == 1:
                     y = y + bias[0].view(1, -1, 1, 1)

@@ -217,6 +217,52 @@ def test_conv2d_epilogue_variants(lib):
     assert (got - ref).abs().max().item() <= 2e-3 * scale
 
 
+@pytest.mark.parametrize("case", [(3, 56, 56, 64, 64, 64, 2), (3, 28, 28, 128, 128, 64, 2), (5, 14, 14, 256, 256, 128, 2),
+                                  (9, 14, 14, 256, 512, 256, 2), (2, 33, 47, 64, 96, 64, 2), (2, 20, 20, 64, 64, 128, 1), (2, 24, 24, 32, 48, 96, 2)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_conv2d_fused_projection_shortcut(lib, case):
+    """out = conv3x3_stride_s(y) + conv1x1_stride_s(x): the shortcut rides as extra K chunks of the main convolution
+    (ResNet down-sampling blocks, reference models/arcface.py:51 graph); single CTAs and CTA pairs"""
+    n, h, w, cin, cout, sc_cin, stride = case
+    g = torch.Generator().manual_seed(sum(case))
+    y = _q(torch.randn((n, cin, h, w), generator=g))
+    x = _q(torch.randn((n, sc_cin, h, w), generator=g))
+    wt = _q(torch.randn((cout, cin, 3, 3), generator=g) * (2.0 / (cin * 9)) ** 0.5)
+    ws = _q(torch.randn((cout, sc_cin, 1, 1), generator=g) * (2.0 / sc_cin) ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.1
+    ref = F.conv2d(y, wt, b, stride, 1) + F.conv2d(x, ws, None, stride, 0)
+    ho, wo = ref.shape[2], ref.shape[3]
+    cin_p, cout_p, sc_p = _pad16(cin), _pad16(cout), _pad16(sc_cin)
+    keep = {}
+    keep["y"] = torch.zeros((n, h, w, cin_p), dtype=torch.float16); keep["y"][..., :cin] = y.permute(0, 2, 3, 1).half()
+    keep["x"] = torch.zeros((n, h, w, sc_p), dtype=torch.float16); keep["x"][..., :sc_cin] = x.permute(0, 2, 3, 1).half()
+    keep["w"] = torch.zeros((9, cout_p, cin_p), dtype=torch.float16)
+    keep["w"][:, :cout, :cin] = wt.permute(2, 3, 0, 1).reshape(9, cout, cin).half()
+    keep["ws"] = torch.zeros((1, cout_p, sc_p), dtype=torch.float16); keep["ws"][0, :cout, :sc_cin] = ws[:, :, 0, 0].half()
+    keep["b"] = torch.zeros((1, cout_p)); keep["b"][0, :cout] = b
+    dev_t = {k: v.cuda() for k, v in keep.items()}
+    try:
+        for pairs in (0, 1, 2):
+            _lib.check(lib.b2f_set_tuning(11, pairs))
+            for f32 in (True, False):
+                out = torch.full((n, ho, wo, cout_p), float("nan"), dtype=torch.float32 if f32 else torch.float16, device="cuda")
+                d = _lib.ConvDesc()
+                d.n, d.h, d.w, d.cin_p, d.ho, d.wo, d.cout_p = n, h, w, cin_p, ho, wo, cout_p
+                d.kh, d.kw, d.stride, d.pad = 3, 3, stride, 1
+                d.dtype, d.out_dtype, d.act, d.bias_classes = 0, 2 if f32 else 0, 0, 1
+                d.in_, d.weight, d.bias, d.out = dev_t["y"].data_ptr(), dev_t["w"].data_ptr(), dev_t["b"].data_ptr(), out.data_ptr()
+                d.sc_in, d.sc_weight = dev_t["x"].data_ptr(), dev_t["ws"].data_ptr()
+                d.sc_cin_p, d.sc_stride, d.sc_h, d.sc_w = sc_p, stride, h, w
+                _lib.check(lib.b2f_conv2d(C.byref(d), sp()), "b2f_conv2d")
+                torch.cuda.synchronize()
+                got = out.float().cpu()[..., :cout].permute(0, 3, 1, 2)
+                err = (got - ref).abs().max().item()
+                tol = (2e-3 if f32 else 6e-3) * max(1.0, ref.abs().max().item())
+                assert err <= tol, f"pairs={pairs} f32={f32}: {err}"
+    finally:
+        _lib.check(lib.b2f_set_tuning(11, 1))
+
+
 @pytest.mark.parametrize("case", [(2, 64, 64, 64, 64), (2, 48, 80, 96, 96), (1, 32, 32, 128, 128), (3, 24, 40, 32, 32),
                                   (2, 56, 56, 64, 128), (2, 20, 20, 224, 224), (1, 33, 47, 64, 32), (2, 40, 24, 80, 80)],
                          ids=lambda c: "x".join(map(str, c)))

@@ -48,8 +48,12 @@ def test_arcface_mbf_plan_matches_oracle():
 def test_arcface_r50_plan_matches_oracle_and_uses_border_tables():
     plan = _check("arcface_r50", (112, 112), n=1)
     assert sum(o.attrs.get("bias_classes") == 9 for o in plan.ops) == 24        # one pre-BN per IBasicBlock
-    assert all(o.kind in ("conv", "im2col") for o in plan.ops) and len(plan.ops) == 55
+    # 55 fused launches, minus the four projection shortcuts that ride as extra K of their block's stride-2 conv
+    assert all(o.kind in ("conv", "im2col") for o in plan.ops) and len(plan.ops) == 51
+    assert sum(1 for o in plan.ops if o.sc_src) == 4
     assert abs(plan.conv_flops() / 1e9 - 12.62) < 0.01                            # SURVEY 8d per-face figure
+    g = archs.build_arch("arcface_r50")
+    assert len(graph.compile_graph(g, (112, 112), fuse_shortcuts=False).ops) == 55
 
 
 def test_unfused_variants_still_match_oracle():

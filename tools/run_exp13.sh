@@ -1,7 +1,8 @@
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider 2>&1 | tail -3
-for t in "13=0" "13=1" "13=0" "13=1"; do
-B2F_TUNE=$t timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('$t', d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['top1_correct'])"
+timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider 2>&1 | tail -6
+for i in 1 2 3; do
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --layer-report gpurun_out/layers_v3.csv 2>gpurun_out/bench_v3.err | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['top1_correct'], d['kernels_per_step'])"
 done
+tail -3 gpurun_out/bench_v3.err
