@@ -92,6 +92,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// pure polling (mbarrier.test_wait never suspends the thread): lower wake-up latency than try_wait's time-sliced sleep
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if (++spins > (1u << 28)) __trap();
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // TMA
 // ------------------------------------------------------------------------------------------

@@ -412,7 +412,7 @@ __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& 
     }
     const int acc = seq & n_acc_mask;
     const uint32_t ph = (uint32_t)(seq >> p.n_acc_log2) & 1u;
-    mbar_wait(&c.tfull[acc], ph);
+    if (p.debug & 64) mbar_wait_poll(&c.tfull[acc], ph); else mbar_wait(&c.tfull[acc], ph);
     tc_fence_after();
     const uint32_t t_addr = c.tmem_base + ((uint32_t)(c.q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
     for (int j = 0; j < n_sub; ++j, ++k) {
