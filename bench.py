@@ -241,7 +241,7 @@ def run_b200(a):
     import torch.distributed as dist
     from models import SCRFD, ArcFace
     from scrfd_arcface_facerecognition_b200 import _lib
-    from scrfd_arcface_facerecognition_b200.gallery import Gallery, merge_shard_topk, shard_range
+    from scrfd_arcface_facerecognition_b200.gallery import Gallery, merge_shard_top1, shard_range
     from scrfd_arcface_facerecognition_b200.pipeline import FacePipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -282,18 +282,19 @@ def run_b200(a):
     resident = [h.to(dev) for h in host]
 
     def match_sharded(emb):
-        """multi-GPU tail: all ranks see all queries, match their gallery shard, exchange top-1"""
-        allq = [torch.empty_like(emb) for _ in range(world)]
-        dist.all_gather(allq, emb.contiguous())
-        q = torch.cat(allq)
-        s, i = gal.match_local(q, 1, 0.4, strict=True)
-        gs = [torch.empty_like(s) for _ in range(world)]
-        gi = [torch.empty_like(i) for _ in range(world)]
-        dist.all_gather(gs, s.contiguous())
-        dist.all_gather(gi, i.contiguous())
-        ms, mi = merge_shard_topk(torch.stack(gs), torch.stack(gi), 1)
+        """multi-GPU tail: all ranks see all queries, match their gallery shard, exchange top-1.
+        One all_gather of the embeddings, one of the packed (score, global index) pairs; for k = 1 the merge by
+        (score desc, index asc) is a max and a masked min."""
         n = emb.shape[0]
-        return ms[rank * n:(rank + 1) * n], mi[rank * n:(rank + 1) * n]
+        q = torch.empty((world * n, emb.shape[1]), dtype=emb.dtype, device=dev)
+        dist.all_gather_into_tensor(q, emb.contiguous())
+        s, i = gal.match_local(q, 1, 0.4, strict=True)
+        mine = torch.stack([s.reshape(-1).double(), i.reshape(-1).double()], dim=1)      # indices < 2^53: exact in f64
+        flat = torch.empty((world * mine.shape[0], 2), dtype=mine.dtype, device=dev)
+        dist.all_gather_into_tensor(flat, mine)
+        both = flat.view(world, mine.shape[0], 2)
+        score, idx = merge_shard_top1(both[:, :, 0].float(), both[:, :, 1].long())
+        return score[rank * n:(rank + 1) * n].reshape(n, 1), idx[rank * n:(rank + 1) * n].reshape(n, 1)
 
     use_graph = not a.no_graph
     if use_graph:

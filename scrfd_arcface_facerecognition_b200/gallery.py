@@ -41,6 +41,33 @@ def merge_shard_topk(scores: torch.Tensor, idx: torch.Tensor, k: int) -> Tuple[t
     return torch.where(i < 0, torch.zeros_like(s), s), i
 
 
+def merge_shard_top1(scores: torch.Tensor, idx: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """k = 1 special case of merge_shard_topk ([P,Q] -> [Q]): a max and a masked min instead of two sorts.
+    Winner = highest score, lowest global index among equals; empty slots (-1) never win."""
+    s = torch.where(idx < 0, torch.full_like(scores, float("-inf")), scores)
+    best = s.max(dim=0).values
+    big = torch.iinfo(torch.int64).max
+    win = torch.where((s == best[None, :]) & (idx >= 0), idx, torch.full_like(idx, big)).min(dim=0).values
+    win = torch.where(win == big, torch.full_like(win, -1), win)
+    return torch.where(win >= 0, best, torch.zeros_like(best)), win
+
+
+def exchange_shard_topk(s: torch.Tensor, i: torch.Tensor, k: int, world_size: int, group=None):
+    """The one collective of sharded matching: every rank contributes its shard's top-k (score [Q,k] f32, global
+    index [Q,k] i64, -1 = empty) packed as float64 pairs (indices < 2^53 are exact), then merges locally by
+    (score desc, index asc).  Identical on every rank and to the unsharded answer."""
+    import torch.distributed as dist
+    mine = torch.stack([s.double(), i.double()], dim=-1).contiguous()
+    flat = torch.empty((world_size * mine.shape[0],) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+    dist.all_gather_into_tensor(flat, mine, group=group)          # concatenated along dim 0 (gloo and NCCL agree on this)
+    both = flat.view((world_size,) + tuple(mine.shape))
+    gs, gi = both[..., 0].float(), both[..., 1].long()
+    if k == 1:
+        ms, mi = merge_shard_top1(gs[..., 0], gi[..., 0])
+        return ms[:, None], mi[:, None]
+    return merge_shard_topk(gs, gi, k)
+
+
 class Gallery:
     def __init__(self, dim: int = 512, device: Optional[torch.device] = None, dtype: Optional[int] = None,
                  rank: int = 0, world_size: int = 1, process_group=None):
@@ -160,13 +187,7 @@ class Gallery:
         s, i = self.match_local(queries, k, threshold, strict)
         if self.world_size == 1:
             return s, i
-        import torch.distributed as dist
-        s, i = s.contiguous(), i.contiguous()
-        gs = [torch.empty_like(s) for _ in range(self.world_size)]
-        gi = [torch.empty_like(i) for _ in range(self.world_size)]
-        dist.all_gather(gs, s, group=self.group)
-        dist.all_gather(gi, i, group=self.group)
-        return merge_shard_topk(torch.stack(gs), torch.stack(gi), k)
+        return exchange_shard_topk(s, i, k, self.world_size, self.group)
 
     # ---- reference-shaped conveniences ------------------------------------------------------------
     def best_match(self, embedding: np.ndarray, similarity_thresh: float) -> Tuple[int, float]:

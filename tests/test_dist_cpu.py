@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from scrfd_arcface_facerecognition_b200.gallery import merge_shard_topk, row_blocks, shard_range
+from scrfd_arcface_facerecognition_b200.gallery import exchange_shard_topk, merge_shard_topk, row_blocks, shard_range
 from tests.golden import inputs
 
 
@@ -25,11 +25,7 @@ def _worker(rank, world, port, q_np, g_np, k, ret):
     q, g = torch.from_numpy(q_np), torch.from_numpy(g_np)
     b, e = shard_range(len(g), rank, world)
     s, i = _topk_rows(q, g[b:e], k, b)
-    gs = [torch.empty_like(s) for _ in range(world)]
-    gi = [torch.empty_like(i) for _ in range(world)]
-    dist.all_gather(gs, s)
-    dist.all_gather(gi, i)
-    ms, mi = merge_shard_topk(torch.stack(gs), torch.stack(gi), k)
+    ms, mi = exchange_shard_topk(s, i, k, world)              # the collective Gallery.match runs (NCCL on the GPU box)
     if rank == 0:
         ret["s"], ret["i"] = ms.numpy(), mi.numpy()
     dist.barrier()
@@ -55,6 +51,10 @@ def test_sharded_topk_equals_single_shard():
     np.testing.assert_array_equal(ret["i"], i.numpy())
     np.testing.assert_array_equal(ret["s"], s.numpy())
     np.testing.assert_array_equal(ret["i"][:, 0], ids)
+    ret1 = mgr.dict()                                   # k = 1 goes through the max / masked-min merge
+    mp.spawn(_worker, args=(2, _free_port(), q, g, 1, ret1), nprocs=2, join=True)
+    np.testing.assert_array_equal(ret1["i"][:, 0], ids)
+    np.testing.assert_array_equal(ret1["s"][:, 0], s.numpy()[:, 0])
 
 
 def test_merge_handles_empty_slots_and_ties():
@@ -64,6 +64,21 @@ def test_merge_handles_empty_slots_and_ties():
     assert mi.tolist() == [[2, 7]] and torch.allclose(ms, torch.tensor([[0.9, 0.9]]))          # equal scores: lower index first
     ms, mi = merge_shard_topk(s, i, 4)
     assert mi.tolist() == [[2, 7, 3, -1]]
+
+
+def test_top1_merge_equals_general_merge():
+    from scrfd_arcface_facerecognition_b200.gallery import merge_shard_top1, merge_shard_topk
+    g = torch.Generator().manual_seed(5)
+    p, q = 8, 500
+    s = torch.rand((p, q), generator=g)
+    i = torch.randint(0, 10_000, (p, q), generator=g)
+    s[:, 10:60] = s[0, 10:60]                           # equal scores across shards: lowest index wins
+    i[torch.rand((p, q), generator=g) < 0.2] = -1       # empty slots never win
+    i[:, 100:110] = -1                                  # queries with no match anywhere
+    s1, i1 = merge_shard_top1(s, i)
+    sk, ik = merge_shard_topk(s[:, :, None], i[:, :, None], 1)
+    assert torch.equal(i1, ik[:, 0]) and torch.equal(s1, sk[:, 0])
+    assert (i1[100:110] == -1).all() and (s1[100:110] == 0).all()
 
 
 def test_row_blocks_partition():
