@@ -14,7 +14,8 @@ __version__ = "0.1.0"
 
 _LAZY = {"SCRFD": ".scrfd", "ArcFace": ".arcface", "Gallery": ".gallery", "FacePipeline": ".pipeline",
          "helpers": ".helpers", "FaceAnalysis": ".face_analysis", "Face": ".face_analysis",
-         "QdrantManager": ".vector_store", "GalleryManager": ".vector_store"}
+         "QdrantManager": ".vector_store", "GalleryManager": ".vector_store",
+         "VideoRunner": ".video", "FrameFeeder": ".video"}
 
 
 def __getattr__(name):

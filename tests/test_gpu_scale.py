@@ -201,3 +201,51 @@ def test_qdrant_manager_surface():
     got = qm.find_duplicate_leaders(0.8)
     assert got == {f"id{i}": f"id{int(l)}" for i, l in enumerate(want) if int(l) != i}
     assert qm.get_collection_info()["points_count"] == 60
+
+
+def test_video_runner_matches_the_per_frame_reference_loop():
+    """section 8(f) rank 3: batched, double-buffered video loop == reference frame_processor (main.py:108-150) per frame"""
+    from models import SCRFD, ArcFace
+    from oracle import restate
+    from scrfd_arcface_facerecognition_b200.video import FrameFeeder, VideoRunner
+    det, rec = SCRFD("weights/det_500m.onnx"), ArcFace("weights/w600k_mbf.onnx")
+    frames = [inputs.frame(120 + i, 480, 640) for i in range(10)]
+
+    class FakeCapture:                                   # cv2.VideoCapture surface: read() -> (ok, frame)
+        def __init__(self, fr):
+            self.fr, self.i = fr, 0
+
+        def read(self):
+            self.i += 1
+            return (True, self.fr[self.i - 1].copy()) if self.i <= len(self.fr) else (False, None)
+
+    runner = VideoRunner(det, rec, max_num=3, similarity_thresh=0.4, batch=4)
+    names = runner.enroll([(frames[i], f"person{i}") for i in range(3)])
+    assert names == ["person0", "person1", "person2"]
+    targets = []
+    for i in range(3):                                    # reference build_targets (main.py:78-105)
+        _, k = det.detect(frames[i], max_num=1)
+        targets.append(rec(frames[i], k[0]))
+    seen = []
+    got = runner.run(FakeCapture(frames), on_frame=lambda fr, faces: seen.append(len(faces)))
+    assert len(got) == 10 and seen == [len(g) for g in got]
+    for f, faces in zip(frames, got):
+        boxes, kpss = det.detect(f, max_num=3)
+        assert len(faces) == len(boxes)
+        for (bbox, name, sim), b, k in zip(faces, boxes, kpss):
+            np.testing.assert_array_equal(bbox, b[:4].astype(np.int32))
+            idx, best = restate.best_match(rec(f, k), np.stack(targets), 0.4)     # strict '>' scan, main.py:136-142
+            assert name == (f"person{idx}" if idx >= 0 else "Unknown")
+            assert abs(sim - best) <= 1e-5
+    assert got[0][0][1] == "person0" and got[1][0][1] == "person1" and got[2][0][1] == "person2"
+    # drawing touches the host frames like the reference's draw_bbox / draw_bbox_info
+    drawn = [f.copy() for f in frames[:4]]
+    runner.run(drawn, draw=True)
+    assert any((d != f).any() for d, f in zip(drawn, frames[:4]))
+    # the feeder alone: batches of 4, 4, 2 with the frames intact
+    sizes = []
+    for dev_batch, n, kept in FrameFeeder(frames, 4):
+        sizes.append(n)
+        torch.cuda.current_stream().synchronize()
+        np.testing.assert_array_equal(dev_batch[:n].cpu().numpy(), np.stack(kept))
+    assert sizes == [4, 4, 2]
