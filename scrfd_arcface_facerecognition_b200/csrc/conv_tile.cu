@@ -566,10 +566,17 @@ __device__ __forceinline__ void mma_issuer(const TileParams& p, const MmaCtx& c)
               const uint64_t aoff = MODE == 0 ? 0ull : (MODE == 1 ? r_inc * (uint64_t)j
                                                                   : s_inc * (uint64_t)(j / 3) + r_inc * (uint64_t)(j % 3));
               issue_k<KSTEPS, CG2>(d0, ad + aoff, bd + b_inc * (uint64_t)j, idesc, j == 0 ? (uint32_t)(g != 0) : 1u);
+              // two tiles per item: their accumulation chains are independent, so alternating them hides the
+              // MMA -> MMA accumulate latency that bounds narrow tiles
+              if (MT == 2)
+                issue_k<KSTEPS, CG2>(d1, ad + aoff + u_inc, bd + b_inc * (uint64_t)j, idesc, j == 0 ? (uint32_t)(g != 0) : 1u);
             }
           }
           commit_to<CG2>(&emptyA[sa]);
-          if (g == groups_per_item - 1) commit_to<CG2>(&tfull[acc0]);
+          if (g == groups_per_item - 1) {
+            commit_to<CG2>(&tfull[acc0]);
+            if (MT == 2) commit_to<CG2>(&tfull[acc1]);
+          }
         }
         bd += b_inc * (uint64_t)TPB;
       } else {
@@ -833,9 +840,9 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     c.fullA = fullA, c.emptyA = emptyA, c.fullB = fullB, c.emptyB = emptyB, c.tfull = tfull, c.tempty = tempty, c.bres = bres;
     const int ks = p.kchunk >> 4;
     c.peerB = peerB, c.peer_tempty = peer_tempty, c.rank = cta_rank;
-    const int variant = p.a_mode * 3 + (p.b_resident ? 0 : p.mt);     // (mode, {resident, streamed mt=1, streamed mt=2})
+    const int variant = p.a_mode * 4 + (p.b_resident ? (p.mt == 2 ? 3 : 0) : p.mt);   // (mode, {res, stream mt1, stream mt2, res mt2})
 #define B2F_MMA_CASE(MODE, V, MT, RES)                                         \
-    case MODE * 3 + V:                                                           \
+    case MODE * 4 + V:                                                           \
       if (ks == 4) mma_issuer<MODE, MT, RES, 4, CG2>(p, c);                      \
       else if (ks == 2) mma_issuer<MODE, MT, RES, 2, CG2>(p, c);                 \
       else mma_issuer<MODE, MT, RES, 1, CG2>(p, c);                              \
@@ -844,12 +851,15 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       B2F_MMA_CASE(0, 0, 1, true)
       B2F_MMA_CASE(0, 1, 1, false)
       B2F_MMA_CASE(0, 2, 2, false)
+      B2F_MMA_CASE(0, 3, 2, true)
       B2F_MMA_CASE(1, 0, 1, true)
       B2F_MMA_CASE(1, 1, 1, false)
       B2F_MMA_CASE(1, 2, 2, false)
+      B2F_MMA_CASE(1, 3, 2, true)
       B2F_MMA_CASE(2, 0, 1, true)
       B2F_MMA_CASE(2, 1, 1, false)
       B2F_MMA_CASE(2, 2, 2, false)
+      B2F_MMA_CASE(2, 3, 2, true)
       default: break;
     }
 #undef B2F_MMA_CASE
@@ -1059,9 +1069,12 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
       const int a_bytes = (mode == 0 ? gw * gh * gn : (mode == 1 ? gw * (gh + 2) : (gw + 2) * (gh + 2))) * row_bytes;
       const int a_box = round_up(a_bytes, 1024);
       for (int mt = 1; mt <= 2; ++mt) {
-        const int resident = (mt == 1 && n_tiles == 1 && b_all <= 100 * 1024) ? 1 : 0;   // sharing only pays when streaming
+        const int resident = (n_tiles == 1 && b_all <= 100 * 1024) ? 1 : 0;
         if (f_mt && mt != f_mt && !(mt == 1 && (p.n_acc_log2 < 2 || m_tiles < 2))) continue;
         if (mt == 2 && (p.n_acc_log2 < 2 || m_tiles < 2)) continue;
+        // two interleaved tiles over resident weights hide the MMA -> MMA accumulate latency of short-K layers (1x1,
+        // per-tap boxes, N = 32); on 64-channel halo-box layers the doubled activation stage costs more than it hides
+        if (mt == 2 && resident && !f_mt && !(mode == 0 || p.block_n <= 32)) continue;
         if (p.cg2 && m_tiles < 2 * mt) continue;
         for (int groups = 4; groups >= 2; groups -= 2) {
           if (groups > (1 << p.n_acc_log2)) continue;          // a group must never be a whole accumulator phase ahead
