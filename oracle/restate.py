@@ -314,3 +314,27 @@ def merge_duplicates(emb: np.ndarray, thr: float) -> np.ndarray:
         leader[hit] = i
         alive[hit] = False
     return leader
+
+
+def online_clusters(emb: np.ndarray, grouping_thr: float, search_thr: float = 0.0) -> np.ndarray:
+    """Online leader clustering in visit order: each embedding searches the persons created so far (one stored
+    embedding per person = its first visit) and joins the BEST match when its similarity >= grouping_thr, else
+    becomes a new person.  Semantics of the per-visit decision at reference duplicate.py:1853-1949 (JSON variant
+    :2166-2262) over `search_person` (:1619-1643, cosine top-k with score >= search_thr, best first), made
+    deterministic by processing visits in index order instead of thread-pool order.
+    Ties between equally similar persons go to the earliest person.  Returns the person (leader index) of every row."""
+    g = normalize_rows(emb).astype(np.float64)
+    n = len(g)
+    label = np.full(n, -1, np.int64)
+    leaders: list = []
+    for i in range(n):
+        if leaders:
+            s = g[leaders] @ g[i]
+            s = np.where(s >= search_thr, s, -np.inf)
+            j = int(np.argmax(s))                       # first maximum = earliest person among equals
+            if np.isfinite(s[j]) and s[j] >= grouping_thr:
+                label[i] = leaders[j]
+                continue
+        leaders.append(i)
+        label[i] = i
+    return label

@@ -259,6 +259,35 @@ class Gallery:
             pairs = torch.sort(torch.cat([b[:int(c.item())] for b, c in zip(bufs, cnts)])).values
         return self.resolve_pairs(pairs)
 
+    def online_clusters(self, grouping_threshold: float) -> np.ndarray:
+        """person (leader row) of every row under the reference's online decision (duplicate.py:1853-1949, processed in
+        row order): a row joins the most similar earlier person when cos >= threshold, else founds a new person.
+        The founders are exactly the survivors of the greedy leader merge (a row founds a person iff no earlier
+        founder reaches the threshold), so: thresholded pairs (tcgen05 GEMM) -> founders (cluster_resolve) -> every
+        other row picks its most similar founder among its pairs (exact fp32 dot, earliest founder on ties)."""
+        n = len(self)
+        if n == 0:
+            return np.empty(0, np.int64)
+        pairs = self.duplicate_pairs(grouping_threshold)
+        lowest = torch.from_numpy(self.resolve_pairs(pairs).astype(np.int64)).to(self.device)
+        rows = torch.arange(n, device=self.device)
+        founder = lowest == rows
+        a, b = pairs >> 32, pairs & 0xFFFFFFFF                          # a < b, cos(a, b) >= threshold
+        keep = founder[a] & ~founder[b]
+        a, b = a[keep], b[keep]
+        label = rows.clone()
+        if a.numel():
+            sim = (self.f32[a] * self.f32[b]).sum(dim=1)
+            # per b: highest similarity, then lowest founder index
+            order = torch.argsort(a, stable=True)
+            order = order[torch.argsort(sim[order], descending=True, stable=True)]
+            order = order[torch.argsort(b[order], stable=True)]
+            b_s, a_s = b[order], a[order]
+            first = torch.ones_like(b_s, dtype=torch.bool)
+            first[1:] = b_s[1:] != b_s[:-1]
+            label[b_s[first]] = a_s[first]
+        return label.cpu().numpy()
+
     def resolve_pairs(self, pairs: torch.Tensor) -> np.ndarray:
         """Greedy one-hop leader merge (ascending id order) over a sorted pair list -> leader[i] per row."""
         n = len(self)

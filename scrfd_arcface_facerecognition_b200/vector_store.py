@@ -133,4 +133,12 @@ class GalleryManager:
         return {ids[i]: ids[int(l)] for i, l in enumerate(leader) if int(l) != i}
 
 
+    def online_person_labels(self, grouping_threshold: float) -> Dict[Any, Any]:
+        """{person_id: person it joins} under the per-visit decision of duplicate.py:1853-1949 taken in insertion order
+        (join the most similar earlier person at >= grouping_threshold, else found a new person)."""
+        label = self.gallery.online_clusters(grouping_threshold)
+        ids = self.gallery.ids
+        return {ids[i]: ids[int(l)] for i, l in enumerate(label)}
+
+
 QdrantManager = GalleryManager

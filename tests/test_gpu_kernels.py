@@ -700,3 +700,16 @@ def test_duplicate_merge_matches_oracle(lib, centres, members):
     G2 = Gallery()
     G2.add(np.stack([a, b, c]))
     assert list(G2.merge_duplicates(0.8)) == [0, 0, 2]
+
+
+@pytest.mark.parametrize("centres,members,noise", [(60, 4, 0.35), (300, 3, 0.5), (5, 40, 0.62)])
+def test_online_clusters_match_oracle(lib, centres, members, noise):
+    """row a20: the online per-visit decision (reference duplicate.py:1853-1949) == sequential oracle, bit for bit"""
+    from scrfd_arcface_facerecognition_b200.gallery import Gallery
+    emb = inputs.clustered(33, centres, members, noise=noise)
+    G = Gallery()
+    G.add(emb)
+    got = G.online_clusters(0.8 if noise < 0.6 else 0.7)
+    want = restate.online_clusters(emb, 0.8 if noise < 0.6 else 0.7)
+    np.testing.assert_array_equal(got, want)
+    assert Gallery().online_clusters(0.8).shape == (0,)

@@ -155,3 +155,18 @@ def test_full_detect_oracle_path_matches_reference_outputs(golden):
         det, kps = restate.scrfd_postprocess([out[n] for n in tg.output_names], 640, 640, ds, 0.5, 0.4)
         np.testing.assert_array_equal(det, golden[f"detect_500m_{fi}_det"])
         np.testing.assert_array_equal(kps, golden[f"detect_500m_{fi}_kps"])
+
+
+def test_online_clusters_semantics():
+    """reference duplicate.py:1853-1949: join the best earlier person at >= grouping threshold, else found a new one"""
+    a = np.zeros(8, np.float32); a[0] = 1
+    b = np.zeros(8, np.float32); b[0], b[1] = 0.8, 0.6          # cos(a,b) = 0.8
+    c = np.zeros(8, np.float32); c[0], c[1] = 0.28, 0.96        # cos(b,c) = 0.8, cos(a,c) = 0.28
+    d = np.zeros(8, np.float32); d[0], d[1] = 0.6, 0.8          # cos(a,d) = 0.6, cos(c,d) = 0.936
+    lab = restate.online_clusters(np.stack([a, b, c, d]), 0.8)
+    assert list(lab) == [0, 0, 2, 2]                              # b joins a; c founds (only b is close, b is no person); d joins c
+    emb = inputs.clustered(31, 40, 3)
+    lab = restate.online_clusters(emb, 0.8)
+    founders = restate.merge_duplicates(emb, 0.8) == np.arange(len(emb))
+    assert ((lab == np.arange(len(emb))) == founders).all()      # same founders as the greedy merge
+    assert len(np.unique(lab)) == 40
