@@ -20,9 +20,9 @@ def _cos(a, b):
     return (a * b).sum(-1) / np.linalg.norm(a, axis=-1) / np.linalg.norm(b, axis=-1)
 
 
-def _engine_outputs(key, hw, frames_u8, mean, scale):
+def _engine_outputs(key, hw, frames_u8, mean, scale, dtype=None):
     g = archs.build_arch(key)
-    eng = NetEngine(compile_graph(g, hw))
+    eng = NetEngine(compile_graph(g, hw), dtype=dtype)
     n = len(frames_u8)
     x = eng.input_buffer(n)
     blob = restate.blob_from_bgr(frames_u8, scale, mean)                       # exact f32 NCHW RGB
@@ -46,6 +46,17 @@ def test_embedder_matches_oracle(key):
     print(f"{key}: cosine {cos}, max rel err {rel:.2e}")
     assert cos.min() >= 0.999                                                    # north-star embedding bar
     assert rel <= 2e-2
+
+
+@pytest.mark.parametrize("key", ["arcface_r50", "arcface_mbf"])
+def test_embedder_bf16_activations_meet_the_cosine_bar(key):
+    """B2F_DTYPE=bf16 path (bf16 operands / activations, fp32 accumulation): SURVEY 7.4 measured 0.99994 on the simulator"""
+    crops = np.stack([inputs.smooth_frame(45 + i, 112, 112) for i in range(3)] + [inputs.frame(49, 112, 112)])
+    eng, outs, ref = _engine_outputs(key, (112, 112), crops, 127.5, 1 / 127.5, dtype=1)
+    (name, got), = outs.items()
+    cos = _cos(got.reshape(4, -1)[:, :512].cpu().numpy(), ref[name])
+    print(f"{key} bf16: cosine {cos}")
+    assert cos.min() >= 0.999
 
 
 @pytest.mark.parametrize("key,hw", [("scrfd_10g", (640, 640)), ("scrfd_2.5g", (320, 352)), ("scrfd_500m", (640, 640))])
