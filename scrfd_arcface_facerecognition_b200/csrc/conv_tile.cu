@@ -39,6 +39,7 @@ int g_tile_epi = -1;     // -1 = auto, 0 = direct global stores, 1 = TMA stores
 int g_tile_cg2 = 1;      // CTA pairs (cta_group::2): 0 = never, 1 = tiles wider than g_tile_cg2_min_n, 2 = wherever legal
 int g_tile_cg2_min_n = 128;
 int g_tile_pdl = 1;      // programmatic dependent launch between consecutive layers
+int g_tile_wide_res = 2; // wide tiles on CTA pairs: TMA-fed residual through the staging ring
 
 constexpr int kTStages = 16;
 constexpr int kTAcc = 4;
@@ -1031,7 +1032,10 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   p.epi_tma = (d->out_dtype == d->dtype && p.res_mode != 2) ? 1 : 0;
   if (g_tile_epi >= 0) p.epi_tma = p.epi_tma && g_tile_epi;
   if (p.epi_tma) {
-    const bool wide = p.block_n > 128;
+    // wide tiles on CTA pairs stream half-size weight tiles, which leaves room for the narrow-tile epilogue (32-channel
+    // slices, ring of three, TMA-fed residual) next to five operand stages; g_tile_wide_res = 0 keeps the lean one
+    const bool wide = p.block_n > 128 &&
+                      !(p.cg2 && (p.res_mode == 1 || g_tile_wide_res == 2) && g_tile_wide_res && p.block_n % 32 == 0);
     p.ochunk = (!wide && p.block_n % 32 == 0) ? 32 : 16;
     p.n_sub = p.block_n / p.ochunk;
     p.stg_bytes = round_up(128 * p.ochunk * 2, 1024);
