@@ -1137,11 +1137,11 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   if (best.cost < 0 && p.cg2)                     // a one-tile problem cannot be paired: plan for single CTAs
     return conv_tile_plan_launch(d, kchunk, stream, optional, 0);
   if (pair < 0 && g_tile_cg2 == 1 && pair_legal && !p.cg2 && best.cost >= 0) {
-    // CTA pairs pay when the pair's single issuing thread has long stages to issue (its barrier round trips cross
-    // the cluster) and the tile is MMA-heavy rather than epilogue-bound; measured in profiles/r01_conv_sweep_cta_pairs.log
-    const int tpb = best.mode == 0 ? 1 : (best.mode == 1 ? 3 : 9);
-    const double stage_cyc = tpb * mma_tap, tile_cyc = (double)taps * p.cchunks * mma_tap;
-    if (p.block_n > g_tile_cg2_min_n || (stage_cyc >= 500.0 && tile_cyc >= 1200.0))
+    // CTA pairs pay when the tile is MMA-heavy rather than epilogue- or hand-shake-bound (1x1 and other short-K layers
+    // stay single: the pair's one issuing thread would carry twice the per-tile hand-shakes); measured in
+    // profiles/r01_conv_sweep_cta_pairs.log
+    const double tile_cyc = (double)(taps * p.cchunks + p.sc_cchunks) * mma_tap;
+    if (p.block_n > g_tile_cg2_min_n || tile_cyc >= 1200.0)
       return conv_tile_plan_launch(d, kchunk, stream, optional, 1);
   }
   B2F_REQUIRE(best.cost >= 0, "conv: no tile plan fits in shared memory (cin_p %d cout_p %d k %d)", d->cin_p, d->cout_p, d->kh);

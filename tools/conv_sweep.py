@@ -12,6 +12,8 @@ SHAPES = {
             (1024, 28, 28, 128, 128, 3, 1, 0, 1, 0), (1024, 28, 28, 128, 256, 3, 1, 2, 0, 1), (1024, 28, 28, 256, 256, 3, 2, 0, 1, 0),
             (1024, 14, 14, 256, 256, 3, 1, 2, 0, 1), (1024, 14, 14, 256, 256, 3, 1, 0, 1, 0), (1024, 14, 14, 256, 512, 3, 1, 2, 0, 1),
             (1024, 14, 14, 512, 512, 3, 2, 0, 1, 0), (1024, 7, 7, 512, 512, 3, 1, 2, 0, 1), (1024, 7, 7, 512, 512, 7, 1, 0, 0, 0)],
+    "sc": [(1024, 112, 112, 64, 64, 3, 2, 0, 0, 0, 64), (1024, 56, 56, 128, 128, 3, 2, 0, 0, 0, 64),
+           (1024, 28, 28, 256, 256, 3, 2, 0, 0, 0, 128), (1024, 14, 14, 512, 512, 3, 2, 0, 0, 0, 256)],
     "det": [(64, 320, 320, 27, 28, 1, 1, 1, 0, 0), (64, 320, 320, 28, 28, 3, 1, 1, 0, 0), (64, 320, 320, 28, 56, 3, 1, 1, 0, 0),
             (64, 160, 160, 56, 56, 3, 1, 1, 0, 0), (64, 160, 160, 56, 56, 3, 1, 1, 1, 0), (64, 160, 160, 56, 88, 3, 2, 1, 0, 0),
             (64, 80, 80, 88, 88, 3, 1, 1, 1, 0), (64, 80, 80, 56, 88, 1, 1, 0, 0, 0), (64, 80, 80, 88, 88, 3, 2, 1, 0, 0),
@@ -31,7 +33,8 @@ DEFAULTS = {2: 2, 3: 1, 4: 0, 5: 0, 6: 0, 7: -1, 8: -1, 11: 1}
 
 
 def bench(lib, shape, reps=30):
-    n, h, w, cin, cout, k, stride, act, res, bias9 = shape
+    n, h, w, cin, cout, k, stride, act, res, bias9 = shape[:10]
+    sc_cin = shape[10] if len(shape) > 10 else 0
     pad = k // 2 if k == 3 else 0
     ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
     pc = lambda c: (c + 15) // 16 * 16
@@ -49,6 +52,11 @@ def bench(lib, shape, reps=30):
     d.in_, d.weight, d.bias, d.slope, d.out = x.data_ptr(), wt.data_ptr(), bias.data_ptr(), slope.data_ptr(), out.data_ptr()
     if res:
         d.residual, d.res_mode = r.data_ptr(), 1
+    if sc_cin:                                          # fused projection shortcut: 1x1, same stride, from a second tensor
+        sc_p = pc(sc_cin)
+        xs = torch.randn((n, h, w, sc_p), device="cuda").half()
+        ws = (torch.randn((1, cout_p, sc_p), device="cuda") * 0.05).half()
+        d.sc_in, d.sc_weight, d.sc_cin_p, d.sc_stride, d.sc_h, d.sc_w = xs.data_ptr(), ws.data_ptr(), sc_p, stride, h, w
     sp = torch.cuda.current_stream().cuda_stream
     for _ in range(6):
         _lib.check(lib.b2f_conv2d(C.byref(d), sp))
@@ -90,7 +98,7 @@ def main():
                 except Exception as e:  # a variant that cannot be planned for this shape
                     row.append("      n/a")
                     torch.cuda.synchronize()
-            n, h, w, cin, cout, k, s, act, res, b9 = shape
+            n, h, w, cin, cout, k, s, act, res, b9 = shape[:10]
             tag = f"{st} n{n} {h}x{w} {cin}->{cout} k{k}s{s} a{act}r{res}b{b9}"
             print(tag.ljust(44) + "".join(row) + (f"   {best[3]} {best[1]:.0f} TF {best[2]:.0f} GB/s" if best else ""), flush=True)
 
