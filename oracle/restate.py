@@ -338,3 +338,23 @@ def online_clusters(emb: np.ndarray, grouping_thr: float, search_thr: float = 0.
         leaders.append(i)
         label[i] = i
     return label
+
+
+def online_similarities(emb: np.ndarray, label: np.ndarray, search_thr: float = 0.0) -> np.ndarray:
+    """The similarity the reference records with each visit of the online loop (duplicate.py:1854-1855:
+    `search_results[0]['similarity'] if search_results else 0.0`): for a visit that joined a person its cosine to that
+    person, for a visit that founded one the best cosine to the persons existing before it (0.0 when the search
+    returned nothing, i.e. no person yet or none >= search_thr).  `label` as returned by `online_clusters`."""
+    g = normalize_rows(emb).astype(np.float32)
+    out = np.zeros(len(g), np.float32)
+    leaders: list = []
+    for i in range(len(g)):
+        if label[i] != i:
+            out[i] = np.float32(g[i] @ g[label[i]])
+            continue
+        if leaders:
+            s = g[leaders] @ g[i]
+            s = s[s >= search_thr]
+            out[i] = s.max() if len(s) else 0.0
+        leaders.append(i)
+    return out

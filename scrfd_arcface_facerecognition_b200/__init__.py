@@ -15,7 +15,8 @@ __version__ = "0.1.0"
 _LAZY = {"SCRFD": ".scrfd", "ArcFace": ".arcface", "Gallery": ".gallery", "FacePipeline": ".pipeline",
          "helpers": ".helpers", "FaceAnalysis": ".face_analysis", "Face": ".face_analysis",
          "QdrantManager": ".vector_store", "GalleryManager": ".vector_store",
-         "VideoRunner": ".video", "FrameFeeder": ".video"}
+         "VideoRunner": ".video", "FrameFeeder": ".video",
+         "PersonDatabase": ".result_store", "save_clustering_results": ".result_store"}
 
 
 def __getattr__(name):

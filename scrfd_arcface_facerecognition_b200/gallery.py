@@ -288,6 +288,32 @@ class Gallery:
             label[b_s[first]] = a_s[first]
         return label.cpu().numpy()
 
+    def online_similarities(self, label: np.ndarray, search_threshold: float = 0.0) -> np.ndarray:
+        """The cosine each online decision was taken on, as the reference records it per visit
+        (duplicate.py:1854-1855 `search_results[0]['similarity'] if search_results else 0.0`): a joining row's similarity
+        to its person, a founding row's best similarity to the persons founded before it (0 when none reaches
+        `search_threshold`, 0 for the first).  Exact fp32 dots of the stored unit rows; the founder-vs-founder maxima
+        are a bookkeeping statistic for the result files, computed block-wise with a plain matmul."""
+        n = len(self)
+        label_t = torch.as_tensor(np.asarray(label, np.int64), device=self.device)
+        rows = torch.arange(n, device=self.device)
+        sim = (self.f32 * self.f32[label_t]).sum(dim=1)
+        founders = rows[label_t == rows]
+        fm = self.f32[founders]
+        best = torch.zeros(len(founders), dtype=torch.float32, device=self.device)
+        block = 4096
+        for start in range(0, len(founders), block):
+            stop = min(start + block, len(founders))
+            if stop <= 1:
+                continue
+            s = fm[start:stop] @ fm[:stop].T                                       # [rows of this block, earlier founders]
+            earlier = torch.arange(stop, device=self.device)[None, :] < torch.arange(start, stop, device=self.device)[:, None]
+            s = torch.where(earlier & (s >= search_threshold), s, torch.full_like(s, -1.0e30))
+            m = s.max(dim=1).values
+            best[start:stop] = torch.where(m > -1.0e29, m, torch.zeros_like(m))
+        sim[founders] = best
+        return sim.cpu().numpy()
+
     def resolve_pairs(self, pairs: torch.Tensor) -> np.ndarray:
         """Greedy one-hop leader merge (ascending id order) over a sorted pair list -> leader[i] per row."""
         n = len(self)

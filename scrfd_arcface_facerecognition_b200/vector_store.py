@@ -140,5 +140,16 @@ class GalleryManager:
         ids = self.gallery.ids
         return {ids[i]: ids[int(l)] for i, l in enumerate(label)}
 
+    def write_clustering_results(self, visits, grouping_threshold: float, db, output_dir: Optional[str] = None, **kw):
+        """Cluster the stored embeddings (one per visit, in insertion order) on the GPU and persist the job in the
+        reference's two on-disk formats (`result_store.write_online_clustering`: SQLite person / visit rows and the
+        clustering_results JSON of json_storage.py:192-245)."""
+        from .result_store import write_online_clustering
+        if len(visits) != len(self.gallery):
+            raise ValueError(f"{len(visits)} visits for {len(self.gallery)} stored embeddings")
+        label = self.gallery.online_clusters(grouping_threshold)
+        sim = self.gallery.online_similarities(label, float(self.config.get("similarity_threshold", 0.0)))
+        return write_online_clustering(visits, label, sim, db, output_dir, **kw)
+
 
 QdrantManager = GalleryManager

@@ -713,3 +713,39 @@ def test_online_clusters_match_oracle(lib, centres, members, noise):
     want = restate.online_clusters(emb, 0.8 if noise < 0.6 else 0.7)
     np.testing.assert_array_equal(got, want)
     assert Gallery().online_clusters(0.8).shape == (0,)
+
+
+@pytest.mark.gpu
+def test_clustering_results_written_from_gpu_labels(lib, tmp_path):
+    """GPU labels -> the reference's SQLite rows and clustering_results JSON; identical to the same
+    writer fed by the sequential CPU oracle, similarities within fp32 dot-order noise (1e-6)."""
+    import json
+    import sqlite3
+    from scrfd_arcface_facerecognition_b200 import result_store as rs
+    from scrfd_arcface_facerecognition_b200.vector_store import GalleryManager
+    emb = inputs.clustered(35, 40, 5, noise=0.4)
+    n = len(emb)
+    visits = [{"id": f"v{i}", "customerId": f"c{i}", "image": f"http://example.invalid/{i}.jpg", "entryTime": f"t{i}"} for i in range(n)]
+    mgr = GalleryManager({"vector_database": {}})
+    for i in range(n):
+        assert mgr.add_embedding(i, emb[i], {"name": f"p{i}"})
+    want_label = restate.online_clusters(emb, 0.75)
+    want_sim = restate.online_similarities(emb, want_label)
+    got_sim = mgr.gallery.online_similarities(mgr.gallery.online_clusters(0.75))
+    np.testing.assert_allclose(got_sim, want_sim, rtol=0, atol=2e-6)
+    conn_g, conn_o = sqlite3.connect(":memory:"), sqlite3.connect(":memory:")
+    clock = lambda: 1767261600.0
+    out_g = mgr.write_clustering_results(visits, 0.75, rs.PersonDatabase(connection=conn_g), str(tmp_path / "gpu"), clock=clock)
+    out_o = rs.write_online_clustering(visits, want_label, want_sim, rs.PersonDatabase(connection=conn_o), str(tmp_path / "cpu"), clock=clock)
+    assert out_g["results"] == out_o["results"] and out_g["person_ids"] == out_o["person_ids"]
+    assert out_g["results"]["new_persons"] == 40 and out_g["results"]["recognized"] == n - 40
+    q = "SELECT person_id, visit_id, customer_id, entry_time, image_url FROM person_visits ORDER BY id"
+    assert conn_g.execute(q).fetchall() == conn_o.execute(q).fetchall()
+    q = "SELECT id, name, image_path, match_count FROM persons ORDER BY id"
+    assert conn_g.execute(q).fetchall() == conn_o.execute(q).fetchall()
+    pg, po = (json.load(open(o["json_path"])) for o in (out_g, out_o))
+    assert len(pg["groups"]) == n
+    for a, b in zip(pg["groups"], po["groups"]):
+        assert {k: v for k, v in a.items() if k not in ("group_score", "visits")} == {k: v for k, v in b.items() if k not in ("group_score", "visits")}
+        assert abs(a["group_score"] - b["group_score"]) <= 1e-3 + 1e-9
+        assert abs(a["visits"][0]["similarity"] - b["visits"][0]["similarity"]) <= 2e-6
