@@ -12,6 +12,8 @@ SHAPES = {
             (1024, 28, 28, 128, 128, 3, 1, 0, 1, 0), (1024, 28, 28, 128, 256, 3, 1, 2, 0, 1), (1024, 28, 28, 256, 256, 3, 2, 0, 1, 0),
             (1024, 14, 14, 256, 256, 3, 1, 2, 0, 1), (1024, 14, 14, 256, 256, 3, 1, 0, 1, 0), (1024, 14, 14, 256, 512, 3, 1, 2, 0, 1),
             (1024, 14, 14, 512, 512, 3, 2, 0, 1, 0), (1024, 7, 7, 512, 512, 3, 1, 2, 0, 1), (1024, 7, 7, 512, 512, 7, 1, 0, 0, 0)],
+    "w14": [(1024, 14, 14, 256, 256, 3, 1, 2, 0, 1)],
+    "w28": [(1024, 28, 28, 128, 128, 3, 1, 2, 0, 1)],
     "r2": [(1024, 112, 112, 64, 64, 3, 1, 2, 0, 1), (1024, 56, 56, 64, 64, 3, 1, 2, 0, 1), (1024, 56, 56, 64, 64, 3, 1, 0, 1, 0)],
     "sc": [(1024, 112, 112, 64, 64, 3, 2, 0, 0, 0, 64), (1024, 56, 56, 128, 128, 3, 2, 0, 0, 0, 64),
            (1024, 28, 28, 256, 256, 3, 2, 0, 0, 0, 128), (1024, 14, 14, 512, 512, 3, 2, 0, 0, 0, 256)],
@@ -33,7 +35,7 @@ VARIANTS = {
 DEFAULTS = {2: 2, 3: 1, 4: 0, 5: 0, 6: 0, 7: -1, 8: -1, 11: 1}
 
 
-def bench(lib, shape, reps=30):
+def bench(lib, shape, reps=int(os.environ.get('B2F_SWEEP_REPS', '30'))):
     n, h, w, cin, cout, k, stride, act, res, bias9 = shape[:10]
     sc_cin = shape[10] if len(shape) > 10 else 0
     pad = k // 2 if k == 3 else 0
