@@ -1077,8 +1077,8 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
         if (f_mt && mt != f_mt && !(mt == 1 && (p.n_acc_log2 < 2 || m_tiles < 2))) continue;
         if (mt == 2 && (p.n_acc_log2 < 2 || m_tiles < 2)) continue;
         // two interleaved tiles over resident weights hide the MMA -> MMA accumulate latency of short-K layers (1x1,
-        // per-tap boxes, N = 32); on 64-channel halo-box layers the doubled activation stage costs more than it hides
-        if (mt == 2 && resident && !f_mt && !(mode == 0 || p.block_n <= 32)) continue;
+        // per-tap boxes, N = 32, Cin <= 32); on 64-channel halo-box layers the doubled activation stage costs more than it hides
+        if (mt == 2 && resident && !f_mt && !(mode == 0 || p.block_n <= 32 || kchunk <= 32)) continue;
         if (p.cg2 && m_tiles < 2 * mt) continue;
         for (int groups = 4; groups >= 2; groups -= 2) {
           if (groups > (1 << p.n_acc_log2)) continue;          // a group must never be a whole accumulator phase ahead
