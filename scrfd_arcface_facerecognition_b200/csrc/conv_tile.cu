@@ -1155,13 +1155,17 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   // wide tiles have two accumulators and two epilogue groups: with only a few tiles per SM the exposed epilogue of
   // the last tile costs more than the first persistent kernel's column-split epilogue
   // (both kernels accumulate wide tiles in the same order, so this batch-dependent choice does not change results)
-  if (optional && p.block_n > 128 && p.items < 4 * g_sms && p.sc_cchunks == 0) return kTileDeclined;
+  // -- except when a tile is hundreds of K chunks long (the 7x7x512 embedding layer): there the epilogue is noise and
+  // the deeper operand ring wins (138 -> 118 us sustained)
+  if (optional && p.block_n > 128 && p.items < 4 * g_sms && p.sc_cchunks == 0 && taps * p.cchunks < 100) return kTileDeclined;
   p.boxes_per_chunk = p.a_mode == 0 ? taps : (p.a_mode == 1 ? 3 : 1);
   p.taps_per_box = taps / p.boxes_per_chunk;
   const int box_w = p.a_mode == 0 ? p.tw * d->stride : (p.a_mode == 1 ? p.tw : p.tw + 2);
   const int box_h = p.a_mode == 0 ? p.th * d->stride : p.th + 2;
   p.a_bytes = (p.a_mode == 0 ? p.tw * p.th * p.tn : box_w * box_h) * row_bytes;
-  p.a_box_bytes = round_up(p.a_bytes, 1024);
+  // the slot always holds the 128 rows an MMA reads, also when the whole problem has fewer output pixels than one tile
+  // (a short box would let the last stage's operand read run past the end of the shared-memory allocation)
+  p.a_box_bytes = round_up(p.a_mode == 0 && p.a_bytes < 128 * row_bytes ? 128 * row_bytes : p.a_bytes, 1024);
   p.a_stage_bytes = p.a_box_bytes * p.mt;
   p.stg_box_bytes = p.tw * p.th * p.tn * p.ochunk * 2;
   p.combined = (p.a_mode == 0 && !p.b_resident) ? 1 : 0;

@@ -749,3 +749,22 @@ def test_clustering_results_written_from_gpu_labels(lib, tmp_path):
         assert {k: v for k, v in a.items() if k not in ("group_score", "visits")} == {k: v for k, v in b.items() if k not in ("group_score", "visits")}
         assert abs(a["group_score"] - b["group_score"]) <= 1e-3 + 1e-9
         assert abs(a["visits"][0]["similarity"] - b["visits"][0]["similarity"]) <= 2e-6
+
+
+@pytest.mark.parametrize("n,cin,k,f32", [(4, 64, 7, True), (4, 64, 7, False), (3, 512, 3, True), (1, 128, 1, True)],
+                         ids=lambda v: str(v))
+def test_tile_kernel_problem_smaller_than_one_tile(lib, n, cin, k, f32):
+    """fewer output pixels than the 128 rows of one MMA tile (the embedding layer at batch 4): the operand slot must
+    still span 128 rows -- a short slot let the last stage's read run off the end of shared memory"""
+    g = torch.Generator().manual_seed(n * 100 + cin + k)
+    x = _q(torch.randn((n, cin, k, k), generator=g))
+    w = _q(torch.randn((512, cin, k, k), generator=g) * (1.0 / (cin * k * k)) ** 0.5)
+    b = torch.randn(512, generator=g) * 0.1
+    ref = F.conv2d(x, w, b)
+    try:
+        for gen in (3, 2):                                   # conv_tile_kernel forced, then default dispatch
+            _lib.check(lib.b2f_set_tuning(2, gen))
+            out = run_conv(lib, x, w, b, 1, 0, out_f32=f32)
+            assert (out - ref).abs().max().item() <= (2e-3 if f32 else 4e-3) * max(1.0, ref.abs().max().item())
+    finally:
+        _lib.check(lib.b2f_set_tuning(2, 2))
