@@ -12,6 +12,7 @@ SHAPES = {
             (1024, 28, 28, 128, 128, 3, 1, 0, 1, 0), (1024, 28, 28, 128, 256, 3, 1, 2, 0, 1), (1024, 28, 28, 256, 256, 3, 2, 0, 1, 0),
             (1024, 14, 14, 256, 256, 3, 1, 2, 0, 1), (1024, 14, 14, 256, 256, 3, 1, 0, 1, 0), (1024, 14, 14, 256, 512, 3, 1, 2, 0, 1),
             (1024, 14, 14, 512, 512, 3, 2, 0, 1, 0), (1024, 7, 7, 512, 512, 3, 1, 2, 0, 1), (1024, 7, 7, 512, 512, 7, 1, 0, 0, 0)],
+    "fc": [(1024, 7, 7, 512, 512, 7, 1, 0, 0, 0), (64, 7, 7, 512, 512, 7, 1, 0, 0, 0), (1, 7, 7, 512, 512, 3, 1, 2, 0, 1)],
     "w14": [(1024, 14, 14, 256, 256, 3, 1, 2, 0, 1)],
     "w28": [(1024, 28, 28, 128, 128, 3, 1, 2, 0, 1)],
     "r2": [(1024, 112, 112, 64, 64, 3, 1, 2, 0, 1), (1024, 56, 56, 64, 64, 3, 1, 2, 0, 1), (1024, 56, 56, 64, 64, 3, 1, 0, 1, 0)],
