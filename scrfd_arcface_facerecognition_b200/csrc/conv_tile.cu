@@ -39,7 +39,8 @@ int g_tile_epi = -1;     // -1 = auto, 0 = direct global stores, 1 = TMA stores
 int g_tile_cg2 = 1;      // CTA pairs (cta_group::2): 0 = never, 1 = tiles wider than g_tile_cg2_min_n, 2 = wherever legal
 int g_tile_cg2_min_n = 128;
 int g_tile_pdl = 1;      // programmatic dependent launch between consecutive layers
-int g_tile_wide_res = 2; // wide tiles on CTA pairs: TMA-fed residual through the staging ring
+int g_tile_wide_res = 2;
+int g_tile_big_res = 1;  // pairs keep up to 150 KB of weights resident (lean staging ring) // wide tiles on CTA pairs: TMA-fed residual through the staging ring
 
 constexpr int kTStages = 16;
 constexpr int kTAcc = 4;
@@ -1031,12 +1032,18 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   // four operand stages: 16-channel slices, a ring of two, residual read straight from global memory.
   p.epi_tma = (d->out_dtype == d->dtype && p.res_mode != 2) ? 1 : 0;
   if (g_tile_epi >= 0) p.epi_tma = p.epi_tma && g_tile_epi;
+  // A pair's half of all weight tiles of a 128-channel 3x3 layer is 147 KB: it stays resident next to two activation
+  // boxes when the staging ring shrinks to 16-channel slices for two epilogue groups (g_tile_big_res = 0 streams it).
+  // Layers with a residual need the four-group 32-channel ring more than the resident weights (326 vs 267 us).
+  const int b_all_bytes = (taps * p.cchunks + p.sc_cchunks) * p.b_tile_bytes;
+  const bool big_res = g_tile_big_res && p.cg2 && n_tiles == 1 && p.epi_tma && p.res_mode == 0 && b_all_bytes > 100 * 1024 &&
+                       b_all_bytes <= 150 * 1024;
   if (p.epi_tma) {
     // wide tiles on CTA pairs stream half-size weight tiles, which leaves room for the narrow-tile epilogue (32-channel
     // slices, ring of three, TMA-fed residual) next to five operand stages; g_tile_wide_res = 0 keeps the lean one
     const bool wide = p.block_n > 128 &&
                       !(p.cg2 && (p.res_mode == 1 || g_tile_wide_res == 2) && g_tile_wide_res && p.block_n % 32 == 0);
-    p.ochunk = (!wide && p.block_n % 32 == 0) ? 32 : 16;
+    p.ochunk = (!wide && !big_res && p.block_n % 32 == 0) ? 32 : 16;
     p.n_sub = p.block_n / p.ochunk;
     p.stg_bytes = round_up(128 * p.ochunk * 2, 1024);
     p.stg_bufs = wide ? 2 : 3;
@@ -1073,7 +1080,7 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
       const int a_bytes = (mode == 0 ? gw * gh * gn : (mode == 1 ? gw * (gh + 2) : (gw + 2) * (gh + 2))) * row_bytes;
       const int a_box = round_up(a_bytes, 1024);
       for (int mt = 1; mt <= 2; ++mt) {
-        const int resident = (n_tiles == 1 && b_all <= 100 * 1024) ? 1 : 0;
+        const int resident = (n_tiles == 1 && (b_all <= 100 * 1024 || big_res)) ? 1 : 0;
         if (f_mt && mt != f_mt && !(mt == 1 && (p.n_acc_log2 < 2 || m_tiles < 2))) continue;
         if (mt == 2 && (p.n_acc_log2 < 2 || m_tiles < 2)) continue;
         // two interleaved tiles over resident weights hide the MMA -> MMA accumulate latency of short-K layers (1x1,

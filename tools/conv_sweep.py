@@ -14,7 +14,7 @@ SHAPES = {
             (1024, 14, 14, 512, 512, 3, 2, 0, 1, 0), (1024, 7, 7, 512, 512, 3, 1, 2, 0, 1), (1024, 7, 7, 512, 512, 7, 1, 0, 0, 0)],
     "fc": [(1024, 7, 7, 512, 512, 7, 1, 0, 0, 0), (64, 7, 7, 512, 512, 7, 1, 0, 0, 0), (1, 7, 7, 512, 512, 3, 1, 2, 0, 1)],
     "w14": [(1024, 14, 14, 256, 256, 3, 1, 2, 0, 1)],
-    "w28": [(1024, 28, 28, 128, 128, 3, 1, 2, 0, 1)],
+    "w28": [(1024, 28, 28, 128, 128, 3, 1, 2, 0, 1), (1024, 28, 28, 128, 128, 3, 1, 0, 1, 0), (64, 28, 28, 128, 128, 3, 1, 0, 1, 0)],
     "r2": [(1024, 112, 112, 64, 64, 3, 1, 2, 0, 1), (1024, 56, 56, 64, 64, 3, 1, 2, 0, 1), (1024, 56, 56, 64, 64, 3, 1, 0, 1, 0)],
     "sc": [(1024, 112, 112, 64, 64, 3, 2, 0, 0, 0, 64), (1024, 56, 56, 128, 128, 3, 2, 0, 0, 0, 64),
            (1024, 28, 28, 256, 256, 3, 2, 0, 0, 0, 128), (1024, 14, 14, 512, 512, 3, 2, 0, 0, 0, 256)],
@@ -31,9 +31,9 @@ VARIANTS = {
     "mt2": {2: 3, 6: 2}, "g2": {2: 3, 5: 2}, "g4": {2: 3, 5: 4}, "direct": {2: 3, 8: 0}, "m2g2": {2: 3, 7: 2, 5: 2},
     "m2g4": {2: 3, 7: 2, 5: 4}, "m1mt2": {2: 3, 7: 1, 6: 2}, "m2mt2": {2: 3, 7: 2, 6: 2}, "m0mt2": {2: 3, 7: 0, 6: 2},
     "cg0": {2: 3, 11: 0}, "cg2": {2: 3, 11: 2}, "m0cg0": {2: 3, 7: 0, 11: 0}, "m0cg2": {2: 3, 7: 0, 11: 2},
-    "m1mt1": {2: 3, 7: 1, 6: 1}, "m2mt1": {2: 3, 7: 2, 6: 1}, "m0mt1": {2: 3, 7: 0, 6: 1},
+    "br0": {15: 0}, "br1": {15: 1}, "m1mt1": {2: 3, 7: 1, 6: 1}, "m2mt1": {2: 3, 7: 2, 6: 1}, "m0mt1": {2: 3, 7: 0, 6: 1},
 }
-DEFAULTS = {2: 2, 3: 1, 4: 0, 5: 0, 6: 0, 7: -1, 8: -1, 11: 1}
+DEFAULTS = {2: 2, 3: 1, 4: 0, 5: 0, 6: 0, 7: -1, 8: -1, 11: 1, 15: 1}
 
 
 def bench(lib, shape, reps=int(os.environ.get('B2F_SWEEP_REPS', '30'))):
