@@ -132,7 +132,9 @@ typedef struct b2f_conv_desc {
   const void* weight;
   const float* bias;        /* [bias_classes][cout_p] */
   const float* slope;       /* [cout_p] for PReLU */
-  const void* residual;
+  const void* residual;     /* may be the same buffer as `out` (res_mode 1): the block output replaces its identity input in
+                             * place; with act == NONE and a 16-bit output, tiles of <= 128 channels then add through a TMA
+                             * reduce-store (the sum is a 16-bit add of the rounded conv result and the stored value) */
   void* out;
   /* optional projection shortcut fused as extra K (ResNet down-sampling blocks: out += conv1x1_stride_s(sc_in)):
    * sc_in [n][sc_h][sc_w][sc_cin_p], sc_weight [1][cout_p][sc_cin_p], no padding, stride sc_stride, same output size;

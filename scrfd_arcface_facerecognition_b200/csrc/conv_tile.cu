@@ -40,6 +40,7 @@ int g_tile_cg2 = 1;      // CTA pairs (cta_group::2): 0 = never, 1 = tiles wider
 int g_tile_cg2_min_n = 128;
 int g_tile_pdl = 1;      // programmatic dependent launch between consecutive layers
 int g_tile_wide_res = 2;
+int g_tile_reduce = 1;   // in-place residual layers add through the TMA reduce-store
 int g_tile_big_res = 1;  // pairs keep up to 150 KB of weights resident (lean staging ring) // wide tiles on CTA pairs: TMA-fed residual through the staging ring
 
 constexpr int kTStages = 16;
@@ -65,6 +66,7 @@ struct TileParams {
   int cg2;                  // 1: CTA pair (cluster of 2, tcgen05 cta_group::2): M = 256 over two SMs, each loads half of B
   int n_acc_log2, acc_stride;
   int groups;
+  int res_reduce;   // residual == out and no activation: the epilogue reduce-adds into the output instead of loading it
   int is_bf16, debug;
   int epi_tma, res_smem, res_global, ochunk, n_sub, stg_bytes, stg_box_bytes, stg_bufs;
   void* out;
@@ -83,6 +85,13 @@ struct TileParams {
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// TMA reduce-store: global[tile] += shared[tile], element-wise in the tensor map's data type (fp16 / bf16), done in L2
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
@@ -365,6 +374,9 @@ __device__ __forceinline__ TileCoord tile_of(const TileParams& p, int first, int
 // its own 16-byte pieces of it.
 template <int ACT, bool BF16, int RES, bool CG2>
 __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& c) {
+  // RES: 0 none, 1 residual through the staging ring, 2 residual from global memory, 3 the output buffer already holds
+  // the residual (in-place block output, no activation after the add): plain arithmetic, then a TMA reduce-add store
+  constexpr int MR = RES == 3 ? 0 : RES;
   const int G = p.groups, n_sub = p.n_sub, och = p.ochunk, group = c.group;
   const int n_acc_mask = (1 << p.n_acc_log2) - 1;
   const uint32_t orow = (uint32_t)och * 2;                           // staging row bytes: 64 / 32
@@ -443,10 +455,10 @@ __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& 
       if (!skip_math) {
         const int cl = j * och;
         const uint4* g0 = (RES == 2 && gres_row) ? reinterpret_cast<const uint4*>(gres_row + cl * 2) : nullptr;
-        epi_slice16<ACT, BF16, RES>(r, bias_row + cl, slope_row + cl, reinterpret_cast<uint4*>(bufp + off[0]),
-                                    reinterpret_cast<uint4*>(bufp + off[1]), t.cbase + cl, sig_hi, g0);
+        epi_slice16<ACT, BF16, MR>(r, bias_row + cl, slope_row + cl, reinterpret_cast<uint4*>(bufp + off[0]),
+                                   reinterpret_cast<uint4*>(bufp + off[1]), t.cbase + cl, sig_hi, g0);
         if (och == 32)
-          epi_slice16<ACT, BF16, RES>(r + 16, bias_row + cl + 16, slope_row + cl + 16, reinterpret_cast<uint4*>(bufp + off[2]),
+          epi_slice16<ACT, BF16, MR>(r + 16, bias_row + cl + 16, slope_row + cl + 16, reinterpret_cast<uint4*>(bufp + off[2]),
                                       reinterpret_cast<uint4*>(bufp + off[3]), t.cbase + cl + 16, sig_hi, g0 ? g0 + 2 : nullptr);
       }
       fence_proxy_async();
@@ -458,7 +470,8 @@ __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& 
       }
       bar_sync_named(1 + group, 128);
       if (c.leader && !skip_store) {
-        tma_store_4d(c.tmO, bufp, t.cbase + j * och, t.x0, t.y0, t.n0);
+        if (RES == 3) tma_reduce_add_4d(c.tmO, bufp, t.cbase + j * och, t.x0, t.y0, t.n0);
+        else tma_store_4d(c.tmO, bufp, t.cbase + j * och, t.x0, t.y0, t.n0);
         bulk_commit();
       }
     }
@@ -883,7 +896,8 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       c.s_bias = s_bias, c.s_slope = s_slope, c.tmO = &tmO, c.tmR = &tmR;
       c.tiles_cta = tiles_cta, c.group = group, c.q = q, c.lane = lane, c.leader = leader;
       c.first = first, c.stride = stride_items, c.rank = cta_rank, c.peer_tempty = peer_tempty;
-      const int variant = p.act * 6 + (p.is_bf16 ? 3 : 0) + (p.res_smem ? 1 : (p.res_global ? 2 : 0));
+      const int variant = p.res_reduce ? 24 + (p.is_bf16 ? 1 : 0)
+                                       : p.act * 6 + (p.is_bf16 ? 3 : 0) + (p.res_smem ? 1 : (p.res_global ? 2 : 0));
 #define B2F_EPI_CASE(ACT)                                                   \
       case ACT * 6 + 0: epilogue_tma<ACT, false, 0, CG2>(p, c); break;             \
       case ACT * 6 + 1: epilogue_tma<ACT, false, 1, CG2>(p, c); break;             \
@@ -896,6 +910,8 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         B2F_EPI_CASE(1)
         B2F_EPI_CASE(2)
         B2F_EPI_CASE(3)
+        case 24: epilogue_tma<0, false, 3, CG2>(p, c); break;
+        case 25: epilogue_tma<0, true, 3, CG2>(p, c); break;
         default: break;
       }
 #undef B2F_EPI_CASE
@@ -1036,19 +1052,24 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   // boxes when the staging ring shrinks to 16-channel slices for two epilogue groups (g_tile_big_res = 0 streams it).
   // Layers with a residual need the four-group 32-channel ring more than the resident weights (326 vs 267 us).
   const int b_all_bytes = (taps * p.cchunks + p.sc_cchunks) * p.b_tile_bytes;
-  const bool big_res = g_tile_big_res && p.cg2 && n_tiles == 1 && p.epi_tma && p.res_mode == 0 && b_all_bytes > 100 * 1024 &&
+  // in-place block output (engine.py aliases the residual's buffer to the output when nothing else reads it): the add
+  // happens in L2.  Narrow tiles only -- wide tiles may be declined to the first persistent kernel depending on the
+  // batch, and the two ways of adding round differently (fp16 add of two rounded values vs one rounding of the fp32 sum)
+  p.res_reduce = (g_tile_reduce && p.epi_tma && p.res_mode == 1 && d->residual == d->out && d->act == 0 && p.block_n <= 128) ? 1 : 0;
+  const int res_eff = p.res_reduce ? 0 : p.res_mode;                 // what the epilogue still has to read
+  const bool big_res = g_tile_big_res && p.cg2 && n_tiles == 1 && p.epi_tma && res_eff == 0 && b_all_bytes > 100 * 1024 &&
                        b_all_bytes <= 150 * 1024;
   if (p.epi_tma) {
     // wide tiles on CTA pairs stream half-size weight tiles, which leaves room for the narrow-tile epilogue (32-channel
     // slices, ring of three, TMA-fed residual) next to five operand stages; g_tile_wide_res = 0 keeps the lean one
     const bool wide = p.block_n > 128 &&
-                      !(p.cg2 && (p.res_mode == 1 || g_tile_wide_res == 2) && g_tile_wide_res && p.block_n % 32 == 0);
+                      !(p.cg2 && (res_eff == 1 || g_tile_wide_res == 2) && g_tile_wide_res && p.block_n % 32 == 0);
     p.ochunk = (!wide && !big_res && p.block_n % 32 == 0) ? 32 : 16;
     p.n_sub = p.block_n / p.ochunk;
     p.stg_bytes = round_up(128 * p.ochunk * 2, 1024);
     p.stg_bufs = wide ? 2 : 3;
-    p.res_smem = (p.res_mode == 1 && !wide) ? 1 : 0;
-    p.res_global = (p.res_mode == 1 && wide) ? 1 : 0;
+    p.res_smem = (res_eff == 1 && !wide) ? 1 : 0;
+    p.res_global = (res_eff == 1 && wide) ? 1 : 0;
   }
   const int tab_bytes = round_up((p.bias_classes + 1) * p.cout_p * 4, 256);
   const int fixed = 1024 /*align*/ + 1024 /*barriers*/ + tab_bytes;

@@ -72,6 +72,7 @@ class NetEngine:
             if op.sc_src:
                 self._last_use[op.sc_src] = i
         self._out_tensors = {o[1] for o in plan.outputs}
+        self.in_place = os.environ.get("B2F_IN_PLACE", "1") != "0"
 
     # ------------------------------------------------------------------------------------------
     def _bind(self, n: int):
@@ -100,7 +101,10 @@ class NetEngine:
         for i, op in enumerate(plan.ops):
             spec = plan.tensors[op.dst]
             nbytes = n * spec.h * spec.w * spec.cp * (4 if spec.f32 else esz)
-            raw = alloc((nbytes + 255) // 256 * 256)
+            if self._in_place(i, op, backing):
+                raw = backing.pop(op.residual)          # the block output overwrites its identity input
+            else:
+                raw = alloc((nbytes + 255) // 256 * 256)
             backing[op.dst] = raw
             view = raw[:nbytes].view(torch.float32 if spec.f32 else torch_dtype(self.dtype))
             tens[op.dst] = view.view(n, spec.h, spec.w, spec.cp)
@@ -109,6 +113,16 @@ class NetEngine:
                 if name and name in backing and self._last_use.get(name) == i and name not in self._out_tensors:
                     free.append(backing.pop(name))
         return bound, tens, all_bufs
+
+    def _in_place(self, i: int, op: FusedOp, backing: Dict[str, torch.Tensor]) -> bool:
+        """A residual convolution without an activation after the add (every IResNet block output) may write over its
+        residual when this op is the residual's last reader: `b2f_conv2d` then adds through a TMA reduce-store instead
+        of loading the residual (include/b2f.h, `residual`).  B2F_IN_PLACE=0 keeps separate buffers."""
+        if not self.in_place or op.kind != "conv" or not op.residual or op.res_mode != 1 or op.act != 0:
+            return False
+        r, d = self.plan.tensors[op.residual], self.plan.tensors[op.dst]
+        return (op.residual in backing and op.residual not in (op.src, op.sc_src) and self._last_use.get(op.residual) == i
+                and op.residual not in self._out_tensors and not d.f32 and not r.f32 and (r.h, r.w, r.cp) == (d.h, d.w, d.cp))
 
     def _bind_op(self, i: int, op: FusedOp, n: int, tens: Dict[str, torch.Tensor]) -> _Bound:
         a, w = op.attrs, self._weights[i]

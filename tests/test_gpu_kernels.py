@@ -93,7 +93,7 @@ def _pad16(c):
 
 
 def run_conv(lib, x_nchw, w_oihw, bias, stride, pad, act=0, slope=None, residual=None, res_mode=0,
-             out_f32=False, bias_tab=None, dtype=0, force_kchunk=0):
+             out_f32=False, bias_tab=None, dtype=0, force_kchunk=0, in_place=False):
     """x (N,C,H,W) f32 torch cpu; returns (N,Cout,Ho,Wo) f32 cpu computed by b2f_conv2d."""
     tdt = torch.bfloat16 if dtype == 1 else torch.float16
     n, cin, h, w = x_nchw.shape
@@ -129,6 +129,9 @@ def run_conv(lib, x_nchw, w_oihw, bias, stride, pad, act=0, slope=None, residual
         keep.append(r.cuda())
         d.residual, d.res_mode, d.res_h, d.res_w = keep[-1].data_ptr(), res_mode, rh, rw
     out = torch.full((n, ho, wo, cout_p), float("nan"), dtype=torch.float32 if out_f32 else tdt, device="cuda")
+    if in_place:                                  # the output buffer holds the residual and is overwritten by the sum
+        out = keep[-1]
+        d.residual = out.data_ptr()
     d.out = out.data_ptr()
     _lib.check(lib.b2f_conv2d(C.byref(d), sp()), "b2f_conv2d")
     torch.cuda.synchronize()
@@ -767,4 +770,32 @@ def test_tile_kernel_problem_smaller_than_one_tile(lib, n, cin, k, f32):
             out = run_conv(lib, x, w, b, 1, 0, out_f32=f32)
             assert (out - ref).abs().max().item() <= (2e-3 if f32 else 4e-3) * max(1.0, ref.abs().max().item())
     finally:
+        _lib.check(lib.b2f_set_tuning(2, 2))
+
+
+@pytest.mark.parametrize("case", [(2, 56, 56, 64, 64, 0), (3, 28, 28, 128, 128, 0), (2, 14, 14, 256, 256, 0), (2, 33, 21, 96, 80, 0),
+                                  (2, 28, 28, 128, 128, 1), (1, 7, 7, 512, 512, 0), (130, 7, 7, 64, 64, 0)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_conv2d_in_place_block_output(lib, case):
+    """residual == out (the engine's in-place block outputs): narrow tiles without activation add through the TMA
+    reduce-store (16-bit add of the rounded conv result), everything else reads and overwrites its own elements;
+    both must equal conv + residual within fp16 rounding of the sum (tolerance 4e-3 * max|ref|)."""
+    n, h, w, cin, cout, act = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = _q(torch.randn((n, cin, h, w), generator=g))
+    wt = _q(torch.randn((cout, cin, 3, 3), generator=g) * (2.0 / (cin * 9)) ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.1
+    res = _q(torch.randn((n, cout, h, w), generator=g))
+    ref = F.conv2d(x, wt, b, 1, 1) + res
+    if act:
+        ref = torch.relu(ref)
+    tol = 4e-3 * max(1.0, ref.abs().max().item())
+    try:
+        for key16, gen in ((1, 2), (0, 2), (1, 3), (1, 1)):          # reduce-store on / off, forced tile kernel, first persistent kernel
+            _lib.check(lib.b2f_set_tuning(16, key16))
+            _lib.check(lib.b2f_set_tuning(2, gen))
+            out = run_conv(lib, x, wt, b, 1, 1, act=act, residual=res, res_mode=1, in_place=True)
+            assert (out - ref).abs().max().item() <= tol, (key16, gen)
+    finally:
+        _lib.check(lib.b2f_set_tuning(16, 1))
         _lib.check(lib.b2f_set_tuning(2, 2))
