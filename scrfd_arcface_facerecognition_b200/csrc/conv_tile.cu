@@ -1053,9 +1053,10 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   // Layers with a residual need the four-group 32-channel ring more than the resident weights (326 vs 267 us).
   const int b_all_bytes = (taps * p.cchunks + p.sc_cchunks) * p.b_tile_bytes;
   // in-place block output (engine.py aliases the residual's buffer to the output when nothing else reads it): the add
-  // happens in L2.  Narrow tiles only -- wide tiles may be declined to the first persistent kernel depending on the
-  // batch, and the two ways of adding round differently (fp16 add of two rounded values vs one rounding of the fp32 sum)
-  p.res_reduce = (g_tile_reduce && p.epi_tma && p.res_mode == 1 && d->residual == d->out && d->act == 0 && p.block_n <= 128) ? 1 : 0;
+  // happens in L2, as a 16-bit add of the rounded conv result and the stored value.  The first-generation kernels, which
+  // still take wide layers with few tiles, round the same way (`res_round` in umma_conv.cu), so the dispatch between
+  // the kernels does not change a bit.
+  p.res_reduce = (g_tile_reduce && p.epi_tma && p.res_mode == 1 && d->residual == d->out && d->act == 0) ? 1 : 0;
   const int res_eff = p.res_reduce ? 0 : p.res_mode;                 // what the epilogue still has to read
   const bool big_res = g_tile_big_res && p.cg2 && n_tiles == 1 && p.epi_tma && res_eff == 0 && b_all_bytes > 100 * 1024 &&
                        b_all_bytes <= 150 * 1024;

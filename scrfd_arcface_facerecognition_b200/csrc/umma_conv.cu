@@ -60,6 +60,8 @@ struct UmmaParams {
   int sig_hi;               // sigmoid only on channels [0, sig_hi); 0 = all
   const void* residual;     // same dtype as activations
   int res_mode;             // 0 none, 1 same-size, 2 nearest 2x upsample of a (res_h,res_w) map
+  int res_round;            // in-place block output without activation: round the conv result to 16 bits before the add,
+                            // which is what conv_tile_kernel's TMA reduce-store computes (same bits from either kernel)
   int res_h, res_w;
   // EPI_TOPK
   int topk;                 // <= kTopKMax
@@ -270,6 +272,10 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               float rs[16];
               load16_as_float(reinterpret_cast<const uint8_t*>(p.residual) + (res_pix * p.cout_p + c) * 2, p.is_bf16,
                               rs);
+              if (p.res_round) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = round16(f[i], p.is_bf16);
+              }
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] += rs[i];
             }
@@ -443,6 +449,10 @@ __device__ __forceinline__ void epilogue_store16(const UmmaParams& p, const uint
   if (p.res_mode && !(p.debug & 2)) {
     float rs[16];
     load16_as_float(reinterpret_cast<const uint8_t*>(p.residual) + (res_pix * p.cout_p + c) * 2, p.is_bf16, rs);
+    if (p.res_round) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = round16(f[i], p.is_bf16);
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) f[i] += rs[i];
   }
@@ -875,6 +885,7 @@ static int pow2_cols(int n) {
   return c;
 }
 
+extern int g_tile_reduce;   // conv_tile.cu
 void pick_m_tile(int N, int Ho, int Wo, int stride, int* tw, int* th, int* tn) {
   long long best = -1;
   int bw = 1, bh = 1, bn = 1;
@@ -1073,6 +1084,7 @@ extern "C" int b2f_conv2d(const b2f_conv_desc* d, void* stream_) {
   p.slope = d->slope, p.act = d->act, p.sig_hi = d->sig_hi;
   B2F_REQUIRE(d->act != 2 || d->slope != nullptr, "b2f_conv2d: PReLU needs a slope vector");
   p.residual = d->residual, p.res_mode = d->residual ? d->res_mode : 0;
+  p.res_round = (g_tile_reduce && p.res_mode == 1 && d->residual == d->out && d->act == 0 && d->out_dtype != 2) ? 1 : 0;
   p.res_h = d->res_h, p.res_w = d->res_w;
   p.debug = g_debug;
 

@@ -84,6 +84,11 @@ __device__ __forceinline__ void load16_as_float(const void* p, int is_bf16, floa
   }
 }
 
+// fp32 -> the 16-bit activation type and back (round to nearest even)
+__device__ __forceinline__ float round16(float v, int is_bf16) {
+  return is_bf16 ? __bfloat162float(__float2bfloat16_rn(v)) : __half2float(__float2half_rn(v));
+}
+
 __device__ __forceinline__ void store16(void* p, int dtype, const float (&f)[16]) {
   if (dtype == 2) {
     float4* q = reinterpret_cast<float4*>(p);
