@@ -1,5 +1,7 @@
 """Sweep b2f_conv2d over layer shapes x tuning variants in ONE process (device-resident, CUDA events).
-usage: python tools/conv_sweep.py [shape-set]      shapes: N H W CIN COUT K STRIDE ACT RES BIAS9"""
+usage: python tools/conv_sweep.py [shape-set] [variants]      shapes: N H W CIN COUT K STRIDE ACT RES BIAS9 [SC_CIN]
+RES: 0 none, 1 separate residual tensor, 2 in place (residual == out).  B2F_SWEEP_REPS=1500 holds each case long enough
+for the power cap to settle (the default 30 repetitions measure the first, un-capped milliseconds)."""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -12,6 +14,9 @@ SHAPES = {
             (1024, 28, 28, 128, 128, 3, 1, 0, 1, 0), (1024, 28, 28, 128, 256, 3, 1, 2, 0, 1), (1024, 28, 28, 256, 256, 3, 2, 0, 1, 0),
             (1024, 14, 14, 256, 256, 3, 1, 2, 0, 1), (1024, 14, 14, 256, 256, 3, 1, 0, 1, 0), (1024, 14, 14, 256, 512, 3, 1, 2, 0, 1),
             (1024, 14, 14, 512, 512, 3, 2, 0, 1, 0), (1024, 7, 7, 512, 512, 3, 1, 2, 0, 1), (1024, 7, 7, 512, 512, 7, 1, 0, 0, 0)],
+    "inplace": [(1024, 56, 56, 64, 64, 3, 1, 0, 1, 0), (1024, 56, 56, 64, 64, 3, 1, 0, 2, 0), (1024, 28, 28, 128, 128, 3, 1, 0, 1, 0),
+                (1024, 28, 28, 128, 128, 3, 1, 0, 2, 0), (1024, 14, 14, 256, 256, 3, 1, 0, 1, 0), (1024, 14, 14, 256, 256, 3, 1, 0, 2, 0),
+                (1024, 7, 7, 512, 512, 3, 1, 0, 1, 0), (1024, 7, 7, 512, 512, 3, 1, 0, 2, 0)],
     "fc": [(1024, 7, 7, 512, 512, 7, 1, 0, 0, 0), (64, 7, 7, 512, 512, 7, 1, 0, 0, 0), (1, 7, 7, 512, 512, 3, 1, 2, 0, 1)],
     "w14": [(1024, 14, 14, 256, 256, 3, 1, 2, 0, 1)],
     "w28": [(1024, 28, 28, 128, 128, 3, 1, 2, 0, 1), (1024, 28, 28, 128, 128, 3, 1, 0, 1, 0), (64, 28, 28, 128, 128, 3, 1, 0, 1, 0)],
@@ -54,7 +59,9 @@ def bench(lib, shape, reps=int(os.environ.get('B2F_SWEEP_REPS', '30'))):
     d.kh, d.kw, d.stride, d.pad = k, k, stride, pad
     d.dtype, d.out_dtype, d.act, d.bias_classes = 0, 0, act, 9 if bias9 else 1
     d.in_, d.weight, d.bias, d.slope, d.out = x.data_ptr(), wt.data_ptr(), bias.data_ptr(), slope.data_ptr(), out.data_ptr()
-    if res:
+    if res == 2:                                        # in-place block output: the output buffer holds the residual
+        d.residual, d.res_mode = out.data_ptr(), 1
+    elif res:
         d.residual, d.res_mode = r.data_ptr(), 1
     if sc_cin:                                          # fused projection shortcut: 1x1, same stride, from a second tensor
         sc_p = pc(sc_cin)
