@@ -219,6 +219,16 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sbo(uint32_t saddr, uint32_t 
   d |= layout << 61;
   return d;
 }
+// no-swizzle K-major operand: core matrices of 8 rows x 16 B; `lbo` = byte distance between core matrices adjacent in
+// K, `sbo` = between 8-row groups (verified on sm_100a by tools/experiments/umma_noswz_test.cu)
+__device__ __forceinline__ uint64_t umma_smem_desc_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
 // instruction descriptor for kind::f16: fp32 accumulate, A/B K-major, M x N tile
 //   [4,6) c_format=1(F32) | [7,10) a_format | [10,13) b_format (0=F16, 1=BF16) | [17,23) N>>3 | [24,29) M>>4
 __device__ __forceinline__ uint32_t umma_idesc(uint32_t m, uint32_t n, uint32_t is_bf16) {

@@ -625,6 +625,40 @@ __device__ __forceinline__ void mma_issuer(const TileParams& p, const MmaCtx& c)
   }
 }
 
+// A mode 3, the 8-channel stem (3x3 over an image of 16-byte pixels): a stage holds ten 2 KB slots, slot t = the
+// {8 ch, tw, th, tn} box of filter tap t (slot 9 stays zero), laid out as no-swizzle core matrices, so one K = 16 step
+// spans two taps: five MMAs per tile against ten resident weight slots [slot][N rows][8 ch]
+constexpr int kStemSlots = 10, kStemSlotBytes = 128 * 16;
+__device__ __forceinline__ void mma_issuer_stem(const TileParams& p, const MmaCtx& c) {
+  const uint32_t idesc = umma_idesc(128, (uint32_t)p.block_n, (uint32_t)p.is_bf16);
+  const uint32_t b_slot = (uint32_t)p.b_tile_bytes;
+  const int acc_mask = (1 << p.n_acc_log2) - 1, acc_log2 = p.n_acc_log2, stages_a = p.stages_a;
+  const bool do_mma = !(p.debug & 4);
+  mbar_wait(c.bres, 0);
+  tc_fence_after();
+  int sa = 0;
+  uint32_t pa = 0;
+  for (int seq = 0; seq < c.items_cta; ++seq) {
+    const int acc = seq & acc_mask;
+    mbar_wait(&c.tempty[acc], ((uint32_t)(seq >> acc_log2) & 1u) ^ 1u);
+    mbar_wait(&c.fullA[sa], pa);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t a0 = c.a_ring + (uint32_t)(sa * p.a_stage_bytes);
+      const uint32_t d = c.tmem_base + (uint32_t)acc * (uint32_t)p.acc_stride;
+      if (do_mma) {
+#pragma unroll
+        for (int s = 0; s < kStemSlots / 2; ++s)
+          umma_f16(d, umma_smem_desc_noswz(a0 + (uint32_t)(s * 2 * kStemSlotBytes), kStemSlotBytes, 128),
+                   umma_smem_desc_noswz(c.b_base + (uint32_t)s * 2u * b_slot, b_slot, 128), idesc, s ? 1u : 0u);
+      }
+      umma_commit(&c.emptyA[sa]);
+      umma_commit(&c.tfull[acc]);
+    }
+    if (++sa == stages_a) sa = 0, pa ^= 1;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
@@ -699,6 +733,11 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tmem_relinquish();
     }
   }
+  if (p.a_mode == 3) {                         // the tenth slot of every stage is the zero half of the last K step
+    for (int i = threadIdx.x; i < p.stages_a * 128; i += blockDim.x)
+      *reinterpret_cast<uint4*>(a_ring + (size_t)(i >> 7) * p.a_stage_bytes + 9 * kStemSlotBytes + (i & 127) * 16) = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+  }
   for (int i = threadIdx.x; i < p.bias_classes * p.cout_p; i += blockDim.x) s_bias[i] = p.bias[i];
   for (int i = threadIdx.x; i < p.cout_p; i += blockDim.x) s_slope[i] = p.act == 2 ? p.slope[i] : 0.f;
   tc_fence_before();
@@ -744,6 +783,26 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       auto load_a = [&](void* dst, uint64_t* bar, int c0, int x, int y, int n) { load_a_from(&tmA, dst, bar, c0, x, y, n); };
       auto load_b = [&](void* dst, uint64_t* bar, int c0, int row, int tap) { load_b_from(&tmB, dst, bar, c0, row, tap); };
       const int sc_cchunks = p.sc_cchunks;
+      if (mode == 3) {
+        if constexpr (!CG2) {
+          mbar_arrive_expect_tx(bres, (uint32_t)(kStemSlots * block_n * 16));      // the bytes that land; slots are b_tile_bytes apart
+          for (int j = 0; j < kStemSlots; ++j) tma_load_3d(b_base + (size_t)j * b_tile_bytes, &tmB, bres, 0, 0, j);
+          const int sxs = p.tw * p.stride, sys = p.th * p.stride, kw3 = p.kw;
+          const uint32_t tx = (uint32_t)p.a_bytes * (uint32_t)(p.kh * p.kw);
+          int sa = 0;
+          uint32_t pa = 0;
+          for (int i = first; i < p.items; i += stride_items) {
+            const int ax = (i % tiles_x) * sxs - p.pad, ay = ((i / tiles_x) % tiles_y) * sys - p.pad, an = (i / tiles_xy) * p.tn;
+            mbar_wait(&emptyA[sa], pa ^ 1);
+            mbar_arrive_expect_tx(&fullA[sa], tx);
+            uint8_t* dst = a_ring + (size_t)sa * a_stage_bytes;
+            for (int ky = 0; ky < p.kh; ++ky)
+              for (int kx = 0; kx < kw3; ++kx)
+                tma_load_4d(dst + (ky * kw3 + kx) * kStemSlotBytes, &tmA, &fullA[sa], 0, ax + kx, ay + ky, an);
+            if (++sa == stages_a) sa = 0, pa ^= 1;
+          }
+        }
+      } else {
       if (resident) {
         arm(bres, b_bytes * (uint32_t)(cchunks * boxes * tpb + sc_cchunks));
         uint8_t* dst = b_base;
@@ -845,6 +904,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      }   // mode != 3
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
@@ -855,6 +915,9 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     c.fullA = fullA, c.emptyA = emptyA, c.fullB = fullB, c.emptyB = emptyB, c.tfull = tfull, c.tempty = tempty, c.bres = bres;
     const int ks = p.kchunk >> 4;
     c.peerB = peerB, c.peer_tempty = peer_tempty, c.rank = cta_rank;
+    if (p.a_mode == 3) {
+      if constexpr (!CG2) mma_issuer_stem(p, c);
+    } else {
     const int variant = p.a_mode * 4 + (p.b_resident ? (p.mt == 2 ? 3 : 0) : p.mt);   // (mode, {res, stream mt1, stream mt2, res mt2})
 #define B2F_MMA_CASE(MODE, V, MT, RES)                                         \
     case MODE * 4 + V:                                                           \
@@ -876,6 +939,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       B2F_MMA_CASE(2, 2, 2, false)
       B2F_MMA_CASE(2, 3, 2, true)
       default: break;
+    }
     }
 #undef B2F_MMA_CASE
   } else if (warp < 2 + 4 * p.groups) {
@@ -1029,7 +1093,12 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   p.block_n = d->cout_p / n_tiles;
   // CTA pairs (cta_group::2): the two CTAs of a cluster run M = 256 MMAs; each holds half of the N rows of every weight
   // tile, so weight traffic, resident-weight footprint and B operand reads per SM halve
-  const bool pair_legal = g_tile_cg2 != 0 && p.block_n % 32 == 0;
+  // the 8-channel stem (A mode 3): cin_p == 8, weights [10][cout_p][8] (slot = filter tap, slot 9 zero)
+  const bool stem8 = kchunk == 8;
+  if (stem8)
+    B2F_REQUIRE(d->cin_p == 8 && d->kh == 3 && d->kw == 3 && n_tiles == 1 && d->sc_in == nullptr && d->residual == nullptr,
+                "b2f_conv2d: the 8-channel stem form needs a 3x3 kernel, cout_p <= %d and no residual / shortcut", g_max_block_n);
+  const bool pair_legal = g_tile_cg2 != 0 && p.block_n % 32 == 0 && !stem8;
   p.cg2 = (pair_legal && (pair == 1 || (pair < 0 && g_tile_cg2 == 2))) ? 1 : 0;
   p.b_tile_bytes = round_up(p.block_n / (p.cg2 ? 2 : 1) * row_bytes, 1024);
   p.acc_stride = round_up(p.block_n, 32);
@@ -1082,13 +1151,23 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   // halo modes only for narrow tiles: wide ones keep one accumulation order across both kernel generations
   const bool halo_ok = g_vhalo && d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && p.block_n <= 128 &&
                        p.sc_cchunks == 0;
-  const int b_all = (taps * p.cchunks + p.sc_cchunks) * p.b_tile_bytes;
+  const int b_all = (stem8 ? kStemSlots : taps * p.cchunks + p.sc_cchunks) * p.b_tile_bytes;
   // The plan (A mode, weight sharing) fixes the order in which taps are accumulated; it is chosen for a batch of
   // at least 128 images so that an image's result does not depend on how many others share its launch.
   const int n_plan = d->n < 128 ? 128 : d->n;
   TilePlan best;
   best.cost = -1;
-  for (int relax = 0; relax < 2 && best.cost < 0; ++relax) {      // forced knobs that cannot fit are dropped
+  if (stem8) {
+    // one plan: a stage = ten 2 KB tap slots, weights resident, as many stages and epilogue groups as fit
+    for (int groups = 4; groups >= 2 && best.cost < 0; groups -= 2) {
+      const int staging = p.epi_tma ? groups * p.stg_bufs * p.stg_bytes : 0;
+      int stages_a = (kSmemMax - fixed - staging - b_all) / (kStemSlots * kStemSlotBytes);
+      if (stages_a > kTStages) stages_a = kTStages;
+      if (stages_a < 2) continue;
+      best.cost = 1.0, best.mode = 3, best.mt = 1, best.groups = groups, best.resident = 1, best.stages_a = stages_a, best.stages_b = 0;
+    }
+  }
+  for (int relax = 0; relax < 2 && best.cost < 0 && !stem8; ++relax) {      // forced knobs that cannot fit are dropped
   const int f_groups = relax ? 0 : g_tile_groups, f_mt = relax ? 0 : g_tile_mt;
   for (int mode = 0; mode <= (halo_ok ? 2 : 0); ++mode) {
     if (g_tile_amode >= 0 && halo_ok && mode != g_tile_amode) continue;
@@ -1174,7 +1253,7 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
       return conv_tile_plan_launch(d, kchunk, stream, optional, 1);
   }
   B2F_REQUIRE(best.cost >= 0, "conv: no tile plan fits in shared memory (cin_p %d cout_p %d k %d)", d->cin_p, d->cout_p, d->kh);
-  if (best.mode == 0) pick_m_tile(d->n, Ho, Wo, d->stride, &best.tw, &best.th, &best.tn);   // geometry for the real batch
+  if (best.mode == 0 || best.mode == 3) pick_m_tile(d->n, Ho, Wo, d->stride, &best.tw, &best.th, &best.tn);   // geometry for the real batch
   p.a_mode = best.mode, p.tw = best.tw, p.th = best.th, p.tn = best.tn, p.mt = best.mt, p.groups = best.groups;
   p.b_resident = best.resident, p.stages_a = best.stages_a, p.stages_b = best.stages_b;
   p.tiles_x = (Wo + p.tw - 1) / p.tw;
@@ -1187,15 +1266,17 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   // -- except when a tile is hundreds of K chunks long (the 7x7x512 embedding layer): there the epilogue is noise and
   // the deeper operand ring wins (138 -> 118 us sustained)
   if (optional && p.block_n > 128 && p.items < 4 * g_sms && p.sc_cchunks == 0 && taps * p.cchunks < 100) return kTileDeclined;
-  p.boxes_per_chunk = p.a_mode == 0 ? taps : (p.a_mode == 1 ? 3 : 1);
+  const bool per_tap = p.a_mode == 0 || p.a_mode == 3;
+  p.boxes_per_chunk = per_tap ? taps : (p.a_mode == 1 ? 3 : 1);
   p.taps_per_box = taps / p.boxes_per_chunk;
-  const int box_w = p.a_mode == 0 ? p.tw * d->stride : (p.a_mode == 1 ? p.tw : p.tw + 2);
-  const int box_h = p.a_mode == 0 ? p.th * d->stride : p.th + 2;
-  p.a_bytes = (p.a_mode == 0 ? p.tw * p.th * p.tn : box_w * box_h) * row_bytes;
+  const int box_w = per_tap ? p.tw * d->stride : (p.a_mode == 1 ? p.tw : p.tw + 2);
+  const int box_h = per_tap ? p.th * d->stride : p.th + 2;
+  p.a_bytes = (per_tap ? p.tw * p.th * p.tn : box_w * box_h) * row_bytes;
   // the slot always holds the 128 rows an MMA reads, also when the whole problem has fewer output pixels than one tile
   // (a short box would let the last stage's operand read run past the end of the shared-memory allocation)
   p.a_box_bytes = round_up(p.a_mode == 0 && p.a_bytes < 128 * row_bytes ? 128 * row_bytes : p.a_bytes, 1024);
   p.a_stage_bytes = p.a_box_bytes * p.mt;
+  if (p.a_mode == 3) p.a_box_bytes = kStemSlotBytes, p.a_stage_bytes = kStemSlots * kStemSlotBytes;
   p.stg_box_bytes = p.tw * p.th * p.tn * p.ochunk * 2;
   p.combined = (p.a_mode == 0 && !p.b_resident) ? 1 : 0;
   if (p.cg2) p.items = n_tiles * ((p.m_tiles + 2 * p.mt - 1) / (2 * p.mt));      // an item = 2 x mt M tiles, mt per CTA
@@ -1215,12 +1296,12 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
     uint64_t str[3] = {(uint64_t)d->cin_p * 2, (uint64_t)d->w * d->cin_p * 2, (uint64_t)d->h * d->w * d->cin_p * 2};
     uint32_t box[4] = {(uint32_t)kchunk, (uint32_t)box_w, (uint32_t)box_h, (uint32_t)p.tn};
     uint32_t es[4] = {1, 1, 1, 1};
-    if (p.a_mode == 0) es[1] = es[2] = (uint32_t)d->stride;
+    if (per_tap) es[1] = es[2] = (uint32_t)d->stride;
     int rc = make_tmap(&tmA, d->in, 4, dims, str, box, es, row_bytes, p.is_bf16);
     if (rc) return rc;
   }
   {
-    uint64_t dims[3] = {(uint64_t)d->cin_p, (uint64_t)d->cout_p, (uint64_t)taps};
+    uint64_t dims[3] = {(uint64_t)d->cin_p, (uint64_t)d->cout_p, (uint64_t)(stem8 ? kStemSlots : taps)};
     uint64_t str[2] = {(uint64_t)d->cin_p * 2, (uint64_t)d->cout_p * d->cin_p * 2};
     uint32_t box[3] = {(uint32_t)kchunk, (uint32_t)(p.cg2 ? p.block_n / 2 : p.block_n), 1};
     uint32_t es[3] = {1, 1, 1};

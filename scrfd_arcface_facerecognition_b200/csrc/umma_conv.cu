@@ -1039,8 +1039,8 @@ using namespace b2f;
 extern "C" int b2f_conv2d(const b2f_conv_desc* d, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   B2F_REQUIRE(d != nullptr, "b2f_conv2d: null descriptor");
-  B2F_REQUIRE(d->cin_p % 16 == 0 && d->cout_p % 16 == 0, "b2f_conv2d: channels must be padded to 16 (got %d, %d)",
-              d->cin_p, d->cout_p);
+  B2F_REQUIRE((d->cin_p % 16 == 0 || d->cin_p == 8) && d->cout_p % 16 == 0,
+              "b2f_conv2d: channels must be padded to 16, or cin_p == 8 for the stem form (got %d, %d)", d->cin_p, d->cout_p);
   B2F_REQUIRE(d->stride == 1 || d->stride == 2, "b2f_conv2d: stride %d unsupported", d->stride);
   B2F_REQUIRE(d->bias != nullptr && d->in != nullptr && d->weight != nullptr && d->out != nullptr,
               "b2f_conv2d: null tensor");
@@ -1050,6 +1050,12 @@ extern "C" int b2f_conv2d(const b2f_conv_desc* d, void* stream_) {
   const int Wo = (d->w + 2 * d->pad - d->kw) / d->stride + 1;
   B2F_REQUIRE(Ho == d->ho && Wo == d->wo, "b2f_conv2d: output size mismatch (%dx%d vs %dx%d)", d->ho, d->wo, Ho, Wo);
 
+  if (d->cin_p == 8) {
+    // stem form: input [n][h][w][8] (16-byte pixels), weight [10][cout_p][8] with slot = filter tap and slot 9 zero;
+    // only conv_tile_kernel has this operand layout (A mode 3)
+    B2F_REQUIRE(d->stride == 1 || d->stride == 2, "b2f_conv2d: stride %d unsupported", d->stride);
+    return conv_tile_launch(d, 8, stream, 0);
+  }
   UmmaParams p;
   memset(&p, 0, sizeof(p));
   p.N = d->n, p.Ho = Ho, p.Wo = Wo, p.H = d->h, p.W = d->w;

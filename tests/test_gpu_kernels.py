@@ -808,3 +808,36 @@ def test_conv2d_in_place_block_output(lib, case):
     finally:
         _lib.check(lib.b2f_set_tuning(16, 1))
         _lib.check(lib.b2f_set_tuning(2, 2))
+
+
+@pytest.mark.parametrize("n,h,w,cout,stride,act", [(3, 112, 112, 64, 1, 2), (2, 64, 48, 32, 2, 1), (130, 16, 16, 64, 1, 0), (1, 33, 21, 128, 1, 2)],
+                         ids=lambda v: str(v))
+def test_stem8_conv_matches_fp32_reference(lib, n, h, w, cout, stride, act):
+    """the 8-channel stem form of b2f_conv2d (16-byte pixels, one TMA box per filter tap into no-swizzle slots, K = 16
+    steps spanning two taps): equals conv3x3(pad 1) of the three real channels; fp16 operands, fp32 accumulation,
+    tolerance 4e-3 * max|ref|"""
+    g = torch.Generator().manual_seed(n + h + cout)
+    x = _q(torch.randn((n, 3, h, w), generator=g))
+    wt = _q(torch.randn((cout, 3, 3, 3), generator=g) * 0.3)
+    b = torch.randn(cout, generator=g) * 0.1
+    slope = torch.rand(cout, generator=g) * 0.5
+    ref = F.conv2d(x, wt, b, stride, 1)
+    ref = torch.relu(ref) if act == 1 else (torch.where(ref >= 0, ref, ref * slope[None, :, None, None]) if act == 2 else ref)
+    ho, wo = ref.shape[2], ref.shape[3]
+    xin = torch.zeros((n, h, w, 8), dtype=torch.float16)
+    xin[..., :3] = x.permute(0, 2, 3, 1).half()
+    wk = torch.zeros((10, cout, 8), dtype=torch.float16)                    # [slot = tap][cout][8], slot 9 zero
+    wk[:9, :, :3] = wt.permute(2, 3, 0, 1).reshape(9, cout, 3).half()
+    d = _lib.ConvDesc()
+    d.n, d.h, d.w, d.cin_p, d.ho, d.wo, d.cout_p = n, h, w, 8, ho, wo, cout
+    d.kh, d.kw, d.stride, d.pad = 3, 3, stride, 1
+    d.dtype, d.out_dtype, d.act, d.bias_classes = 0, 0, act, 1
+    keep = [xin.cuda(), wk.cuda(), b.reshape(1, cout).float().cuda(), slope.float().cuda()]
+    d.in_, d.weight, d.bias, d.slope = (t.data_ptr() for t in keep)
+    out = torch.full((n, ho, wo, cout), float("nan"), dtype=torch.float16, device="cuda")
+    d.out = out.data_ptr()
+    _lib.check(lib.b2f_conv2d(C.byref(d), sp()), "b2f_conv2d")
+    torch.cuda.synchronize()
+    got = out.float().cpu().permute(0, 3, 1, 2)
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() <= 4e-3 * max(1.0, ref.abs().max().item())
