@@ -113,11 +113,17 @@ int b2f_norm_crop(const uint8_t* frames, int h, int w, const int* frame_idx, con
 int b2f_norm_crop_patches(const uint8_t* frames, int h, int w, const int* frame_idx, const float* landmarks, int faces,
                           int size, float mean, float scale, void* out_patches, int dtype, void* stream);
 
+/* the same crop as 16-byte pixels [faces][112][112][8] (R, G, B, then zeros), the input of b2f_conv2d's stem form
+ * (cin_p == 8); bit-identical to b2f_norm_crop with c_pad = 8 */
+int b2f_norm_crop_image8(const uint8_t* frames, int h, int w, const int* frame_idx, const float* landmarks, int faces,
+                         int size, float mean, float scale, void* out_image8, int dtype, void* stream);
+
 /* ---- a4 / a15: convolution layers of the detector / embedder ------------------------------------
  * replaces onnxruntime session.run at reference models/scrfd.py:83 and models/arcface.py:51.
  * NHWC activations, weights [kh*kw][cout_p][cin_p], fp32 bias table, fused residual + activation. */
 typedef struct b2f_conv_desc {
-  int n, h, w, cin_p;       /* input  [n][h][w][cin_p]  */
+  int n, h, w, cin_p;       /* input  [n][h][w][cin_p]; cin_p == 8 selects the stem form: 3x3 kernel, 16-byte pixels, weight
+                             * [10][cout_p][8] with slot = filter tap (ky * 3 + kx) and slot 9 zero, cout_p <= 256 */
   int ho, wo, cout_p;       /* output [n][ho][wo][cout_p] */
   int kh, kw, stride, pad;
   int dtype;                /* activations + weights: B2F_F16 or B2F_BF16 */

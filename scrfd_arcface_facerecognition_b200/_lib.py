@@ -93,6 +93,7 @@ SIGNATURES = {
     "b2f_warp_affine_u8": [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp],
     "b2f_norm_crop": [_vp, _i, _i, _vp, _vp, _i, _i, _f, _f, _vp, _i, _i, _vp, _vp, _vp],
     "b2f_norm_crop_patches": [_vp, _i, _i, _vp, _vp, _i, _i, _f, _f, _vp, _i, _vp],
+    "b2f_norm_crop_image8": [_vp, _i, _i, _vp, _vp, _i, _i, _f, _f, _vp, _i, _vp],
     "b2f_conv2d": [C.POINTER(ConvDesc), _vp],
     "b2f_stem_conv3x3": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "b2f_im2col3x3": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],

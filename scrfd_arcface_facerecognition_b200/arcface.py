@@ -7,6 +7,8 @@ that keeps crops and embeddings on the device.
 """
 from __future__ import annotations
 
+import os
+
 import threading
 from typing import List, Optional, Sequence
 
@@ -50,6 +52,7 @@ class ArcFace:
         self._engine = NetEngine(compile_graph(graph, (h, w)))
         self._scale = float(np.float32(1.0 / self.input_std))   # blobFromImages multiplies by float32(1/std)
         self.fuse_stem = True
+        self.stem8 = os.environ.get("B2F_STEM8", "1") != "0"      # first convolution in its 8-channel stem form
         if session is None:
             self.session = self                                  # keeps `recognizer.session` truthy for callers
 
@@ -101,6 +104,21 @@ class ArcFace:
         with self._lock:
             f = int(frame_idx.shape[0])
             w, h = self.input_size
+            stem8 = self._engine.stem8(f) if (self.fuse_stem and self.stem8 and crops_u8 is None) else None
+            if stem8 is not None:
+                # aligned crop kept as an 8-channel image (16 B per pixel); the first convolution reads it tap by tap
+                if w == h == 112:                       # one CTA per face, crop staged in shared memory
+                    _lib.check(self._lib.b2f_norm_crop_image8(
+                        frames.data_ptr(), frames.shape[1], frames.shape[2], frame_idx.data_ptr(),
+                        kps.reshape(f, 10).contiguous().data_ptr(), f, w, float(self.input_mean), self._scale,
+                        stem8[0].data_ptr(), self._engine.dtype, stream_ptr()), "b2f_norm_crop_image8")
+                else:
+                    _lib.check(self._lib.b2f_norm_crop(
+                        frames.data_ptr(), frames.shape[1], frames.shape[2], frame_idx.data_ptr(),
+                        kps.reshape(f, 10).contiguous().data_ptr(), f, w, float(self.input_mean), self._scale,
+                        stem8[0].data_ptr(), 8, self._engine.dtype, None, None, stream_ptr()), "b2f_norm_crop")
+                stem8[1]()
+                return self._engine.run(f, start=2)[self.output_names[0]].reshape(f, -1)
             patches = self._engine.patch_buffer(f) if (self.fuse_stem and crops_u8 is None and w == h == 112) else None
             if patches is not None and patches[1] == 1:
                 # norm_crop + blob + first-layer patch extraction in one kernel (one CTA per face)

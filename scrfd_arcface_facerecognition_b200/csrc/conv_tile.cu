@@ -659,6 +659,45 @@ __device__ __forceinline__ void mma_issuer_stem(const TileParams& p, const MmaCt
   }
 }
 
+// A mode 4, the stride-1 stem: ONE box per 8 x 16 tile -- (16 + 2) rows of (8 + 2) 16-byte pixels, 160 B per row, fetched
+// through a tensor map that merges the pixel and channel dimensions -- serves all nine taps: a tap's operand starts
+// (ky * 10 + kx) pixels into the box, its 8-row groups are one box row (160 B) apart, and the second K core matrix of a
+// step is simply the next tap's start (16 B, or 128 B across a row of taps).  The last step pairs tap 8 with zero weights.
+constexpr int kStemBoxRow = 10 * 16, kStemBoxBytes = 18 * kStemBoxRow, kStemBoxStage = 3072;
+__device__ __forceinline__ void mma_issuer_stem_halo(const TileParams& p, const MmaCtx& c) {
+  const uint32_t idesc = umma_idesc(128, (uint32_t)p.block_n, (uint32_t)p.is_bf16);
+  const uint32_t b_slot = (uint32_t)p.b_tile_bytes;
+  const int acc_mask = (1 << p.n_acc_log2) - 1, acc_log2 = p.n_acc_log2, stages_a = p.stages_a;
+  const bool do_mma = !(p.debug & 4);
+  mbar_wait(c.bres, 0);
+  tc_fence_after();
+  int sa = 0;
+  uint32_t pa = 0;
+  for (int seq = 0; seq < c.items_cta; ++seq) {
+    const int acc = seq & acc_mask;
+    mbar_wait(&c.tempty[acc], ((uint32_t)(seq >> acc_log2) & 1u) ^ 1u);
+    mbar_wait(&c.fullA[sa], pa);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t a0 = c.a_ring + (uint32_t)(sa * kStemBoxStage);
+      const uint32_t d = c.tmem_base + (uint32_t)acc * (uint32_t)p.acc_stride;
+      if (do_mma) {
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+          const int t0 = 2 * s, t1 = t0 + 1;
+          const uint32_t o0 = (uint32_t)((t0 / 3) * 10 + t0 % 3) * 16u;
+          const uint32_t o1 = s == 4 ? o0 + 16u : (uint32_t)((t1 / 3) * 10 + t1 % 3) * 16u;
+          umma_f16(d, umma_smem_desc_noswz(a0 + o0, o1 - o0, kStemBoxRow),
+                   umma_smem_desc_noswz(c.b_base + (uint32_t)s * 2u * b_slot, b_slot, 128), idesc, s ? 1u : 0u);
+        }
+      }
+      umma_commit(&c.emptyA[sa]);
+      umma_commit(&c.tfull[acc]);
+    }
+    if (++sa == stages_a) sa = 0, pa ^= 1;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
@@ -738,6 +777,12 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       *reinterpret_cast<uint4*>(a_ring + (size_t)(i >> 7) * p.a_stage_bytes + 9 * kStemSlotBytes + (i & 127) * 16) = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
   }
+  if (p.a_mode == 4) {                         // the slack after each box is read by the zero-weight half of the last K step
+    constexpr int kPad16 = (kStemBoxStage - kStemBoxBytes) / 16;
+    for (int i = threadIdx.x; i < p.stages_a * kPad16; i += blockDim.x)
+      *reinterpret_cast<uint4*>(a_ring + (size_t)(i / kPad16) * kStemBoxStage + kStemBoxBytes + (i % kPad16) * 16) = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+  }
   for (int i = threadIdx.x; i < p.bias_classes * p.cout_p; i += blockDim.x) s_bias[i] = p.bias[i];
   for (int i = threadIdx.x; i < p.cout_p; i += blockDim.x) s_slope[i] = p.act == 2 ? p.slope[i] : 0.f;
   tc_fence_before();
@@ -783,7 +828,21 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       auto load_a = [&](void* dst, uint64_t* bar, int c0, int x, int y, int n) { load_a_from(&tmA, dst, bar, c0, x, y, n); };
       auto load_b = [&](void* dst, uint64_t* bar, int c0, int row, int tap) { load_b_from(&tmB, dst, bar, c0, row, tap); };
       const int sc_cchunks = p.sc_cchunks;
-      if (mode == 3) {
+      if (mode == 4) {
+        if constexpr (!CG2) {
+          mbar_arrive_expect_tx(bres, (uint32_t)(kStemSlots * block_n * 16));
+          for (int j = 0; j < kStemSlots; ++j) tma_load_3d(b_base + (size_t)j * b_tile_bytes, &tmB, bres, 0, 0, j);
+          int sa = 0;
+          uint32_t pa = 0;
+          for (int i = first; i < p.items; i += stride_items) {
+            const int ax = (i % tiles_x) * p.tw - 1, ay = ((i / tiles_x) % tiles_y) * p.th - 1, an = i / tiles_xy;
+            mbar_wait(&emptyA[sa], pa ^ 1);
+            mbar_arrive_expect_tx(&fullA[sa], (uint32_t)kStemBoxBytes);
+            tma_load_3d(a_ring + (size_t)sa * kStemBoxStage, &tmA, &fullA[sa], ax * 8, ay, an);
+            if (++sa == stages_a) sa = 0, pa ^= 1;
+          }
+        }
+      } else if (mode == 3) {
         if constexpr (!CG2) {
           mbar_arrive_expect_tx(bres, (uint32_t)(kStemSlots * block_n * 16));      // the bytes that land; slots are b_tile_bytes apart
           for (int j = 0; j < kStemSlots; ++j) tma_load_3d(b_base + (size_t)j * b_tile_bytes, &tmB, bres, 0, 0, j);
@@ -917,6 +976,8 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     c.peerB = peerB, c.peer_tempty = peer_tempty, c.rank = cta_rank;
     if (p.a_mode == 3) {
       if constexpr (!CG2) mma_issuer_stem(p, c);
+    } else if (p.a_mode == 4) {
+      if constexpr (!CG2) mma_issuer_stem_halo(p, c);
     } else {
     const int variant = p.a_mode * 4 + (p.b_resident ? (p.mt == 2 ? 3 : 0) : p.mt);   // (mode, {res, stream mt1, stream mt2, res mt2})
 #define B2F_MMA_CASE(MODE, V, MT, RES)                                         \
@@ -1161,10 +1222,11 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
     // one plan: a stage = ten 2 KB tap slots, weights resident, as many stages and epilogue groups as fit
     for (int groups = 4; groups >= 2 && best.cost < 0; groups -= 2) {
       const int staging = p.epi_tma ? groups * p.stg_bufs * p.stg_bytes : 0;
-      int stages_a = (kSmemMax - fixed - staging - b_all) / (kStemSlots * kStemSlotBytes);
+      const bool halo = d->stride == 1 && d->pad == 1 && g_vhalo;        // one box per tile instead of nine
+      int stages_a = (kSmemMax - fixed - staging - b_all) / (halo ? kStemBoxStage : kStemSlots * kStemSlotBytes);
       if (stages_a > kTStages) stages_a = kTStages;
       if (stages_a < 2) continue;
-      best.cost = 1.0, best.mode = 3, best.mt = 1, best.groups = groups, best.resident = 1, best.stages_a = stages_a, best.stages_b = 0;
+      best.cost = 1.0, best.mode = halo ? 4 : 3, best.mt = 1, best.groups = groups, best.resident = 1, best.stages_a = stages_a, best.stages_b = 0;
     }
   }
   for (int relax = 0; relax < 2 && best.cost < 0 && !stem8; ++relax) {      // forced knobs that cannot fit are dropped
@@ -1254,6 +1316,7 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   }
   B2F_REQUIRE(best.cost >= 0, "conv: no tile plan fits in shared memory (cin_p %d cout_p %d k %d)", d->cin_p, d->cout_p, d->kh);
   if (best.mode == 0 || best.mode == 3) pick_m_tile(d->n, Ho, Wo, d->stride, &best.tw, &best.th, &best.tn);   // geometry for the real batch
+  if (best.mode == 4) best.tw = 8, best.th = 16, best.tn = 1;
   p.a_mode = best.mode, p.tw = best.tw, p.th = best.th, p.tn = best.tn, p.mt = best.mt, p.groups = best.groups;
   p.b_resident = best.resident, p.stages_a = best.stages_a, p.stages_b = best.stages_b;
   p.tiles_x = (Wo + p.tw - 1) / p.tw;
@@ -1277,6 +1340,7 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   p.a_box_bytes = round_up(p.a_mode == 0 && p.a_bytes < 128 * row_bytes ? 128 * row_bytes : p.a_bytes, 1024);
   p.a_stage_bytes = p.a_box_bytes * p.mt;
   if (p.a_mode == 3) p.a_box_bytes = kStemSlotBytes, p.a_stage_bytes = kStemSlots * kStemSlotBytes;
+  if (p.a_mode == 4) p.a_bytes = kStemBoxBytes, p.a_box_bytes = kStemBoxStage, p.a_stage_bytes = kStemBoxStage;
   p.stg_box_bytes = p.tw * p.th * p.tn * p.ochunk * 2;
   p.combined = (p.a_mode == 0 && !p.b_resident) ? 1 : 0;
   if (p.cg2) p.items = n_tiles * ((p.m_tiles + 2 * p.mt - 1) / (2 * p.mt));      // an item = 2 x mt M tiles, mt per CTA
@@ -1291,7 +1355,15 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   if (smem < 120 * 1024) smem = 120 * 1024;      // one CTA per SM: it owns all 512 TMEM columns
 
   CUtensorMap tmA, tmB, tmO, tmR, tmA2, tmB2;
-  {
+  if (p.a_mode == 4) {
+    // pixels and channels merged into one dimension: a box row is (8 + 2) whole 16-byte pixels
+    uint64_t dims[3] = {(uint64_t)d->w * 8, (uint64_t)d->h, (uint64_t)d->n};
+    uint64_t str[2] = {(uint64_t)d->w * 16, (uint64_t)d->h * d->w * 16};
+    uint32_t box[3] = {80, 18, 1};
+    uint32_t es[3] = {1, 1, 1};
+    int rc = make_tmap(&tmA, d->in, 3, dims, str, box, es, 0, p.is_bf16);
+    if (rc) return rc;
+  } else {
     uint64_t dims[4] = {(uint64_t)d->cin_p, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
     uint64_t str[3] = {(uint64_t)d->cin_p * 2, (uint64_t)d->w * d->cin_p * 2, (uint64_t)d->h * d->w * d->cin_p * 2};
     uint32_t box[4] = {(uint32_t)kchunk, (uint32_t)box_w, (uint32_t)box_h, (uint32_t)p.tn};

@@ -698,6 +698,7 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(WarpParams p) {
 // shared memory (uint8, exactly the cv2.warpAffine arithmetic of warp_affine_kernel), then every thread emits
 // 16-byte pieces of the [size][size][32] patch tensor the first ArcFace convolution consumes as a 1x1 conv.
 constexpr int kPatchCrop = 112;
+template <bool IMG8>   // IMG8: emit the crop itself as 16-byte pixels (R, G, B, 0 x 5) for the stem-form convolution
 __global__ void __launch_bounds__(512) warp_patches_kernel(WarpParams p, uint16_t* __restrict__ out) {
   __shared__ uint8_t crop[kPatchCrop * kPatchCrop * 3];
   __shared__ uint16_t lut[256];
@@ -729,6 +730,14 @@ __global__ void __launch_bounds__(512) warp_patches_kernel(WarpParams p, uint16_
     crop[idx * 3 + 0] = (uint8_t)bgr[0], crop[idx * 3 + 1] = (uint8_t)bgr[1], crop[idx * 3 + 2] = (uint8_t)bgr[2];
   }
   __syncthreads();
+  if (IMG8) {
+    uint4* o8 = reinterpret_cast<uint4*>(out) + (size_t)f * size * size;
+    for (int pix = threadIdx.x; pix < size * size; pix += blockDim.x) {
+      const uint8_t* c = crop + pix * 3;
+      o8[pix] = make_uint4(lut[c[2]] | ((uint32_t)lut[c[1]] << 16), lut[c[0]], 0u, 0u);
+    }
+    return;
+  }
   uint16_t* o = out + (size_t)f * size * size * 32;
   // emission: one thread per crop pixel, values through a 256-entry table (measured faster than recomputing them
   // and than piece-per-lane coalescing)
@@ -932,7 +941,22 @@ extern "C" int b2f_norm_crop_patches(const uint8_t* frames, int h, int w, const 
   memset(&p, 0, sizeof(p));
   p.frames = frames, p.h = h, p.w = w, p.frame_idx = frame_idx, p.landmarks = landmarks, p.faces = faces;
   p.size = size, p.mean = mean, p.scale = scale, p.is_bf16 = dtype == B2F_BF16;
-  warp_patches_kernel<<<faces, 512, 0, (cudaStream_t)stream>>>(p, reinterpret_cast<uint16_t*>(out_patches));
+  warp_patches_kernel<false><<<faces, 512, 0, (cudaStream_t)stream>>>(p, reinterpret_cast<uint16_t*>(out_patches));
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b2f_norm_crop_image8(const uint8_t* frames, int h, int w, const int* frame_idx, const float* landmarks,
+                                    int faces, int size, float mean, float scale, void* out_image8, int dtype, void* stream) {
+  B2F_REQUIRE(size == kPatchCrop, "b2f_norm_crop_image8: crop size must be %d (got %d)", kPatchCrop, size);
+  B2F_REQUIRE(dtype == B2F_F16 || dtype == B2F_BF16, "b2f_norm_crop_image8: dtype must be f16 or bf16");
+  if (faces <= 0) return 0;
+  WarpParams p;
+  memset(&p, 0, sizeof(p));
+  p.frames = frames, p.h = h, p.w = w, p.frame_idx = frame_idx, p.landmarks = landmarks, p.faces = faces;
+  p.size = size, p.mean = mean, p.scale = scale, p.is_bf16 = dtype == B2F_BF16;
+  warp_patches_kernel<true><<<faces, 512, 0, (cudaStream_t)stream>>>(p, reinterpret_cast<uint16_t*>(out_image8));
   g_launches.fetch_add(1);
   B2F_LAUNCH_CHECK();
   return 0;

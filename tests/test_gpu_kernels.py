@@ -407,6 +407,16 @@ def test_fused_norm_crop_patches_equal_norm_crop_plus_im2col(lib):
                                              got.data_ptr(), dtype, sp()))
         torch.cuda.synchronize()
         assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+        # the same crop as 16-byte pixels for the stem-form convolution: bit-identical to norm_crop with c_pad = 8
+        want8 = torch.full((n, 112, 112, 8), float("nan"), dtype=tdt, device="cuda")
+        _lib.check(lib.b2f_norm_crop(frames.data_ptr(), h, w, fidx.data_ptr(), kps.data_ptr(), n, 112, 127.5, scale,
+                                     want8.data_ptr(), 8, dtype, None, None, sp()))
+        got8 = torch.full((n, 112, 112, 8), float("nan"), dtype=tdt, device="cuda")
+        _lib.check(lib.b2f_norm_crop_image8(frames.data_ptr(), h, w, fidx.data_ptr(), kps.data_ptr(), n, 112, 127.5, scale,
+                                            got8.data_ptr(), dtype, sp()))
+        torch.cuda.synchronize()
+        assert torch.equal(got8.view(torch.int16), want8.view(torch.int16))
+        assert torch.equal(got8[..., :3].view(torch.int16), x[..., :3].view(torch.int16)) and (got8[..., 3:] == 0).all()
 
 
 def test_pool_and_eltwise(lib):

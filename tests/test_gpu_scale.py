@@ -69,6 +69,29 @@ def test_config3_embedding_is_batch_invariant():
     assert torch.isfinite(big).all() and big.norm(dim=1).min().item() > 0
 
 
+def test_stem8_path_equals_patch_path():
+    """the first ArcFace convolution in its 8-channel stem form (crop kept as 16-byte pixels, one TMA box per filter tap)
+    against the 32-channel patch tensor path: same embeddings up to the order of the fp32 accumulation of the first
+    layer (cosine >= 0.99999, max abs difference <= 2e-3 of the embedding scale), also for MobileFaceNet"""
+    from models import ArcFace
+    frames = torch.from_numpy(np.stack([inputs.frame(80 + i, 360, 480) for i in range(3)])).cuda()
+    n = 70
+    kps = torch.from_numpy(inputs.landmarks(81, 360, 480, n).reshape(n, 10)).cuda()
+    fidx = (torch.arange(n, device="cuda") % 3).to(torch.int32)
+    for path in ("weights/w600k_r50.onnx", "weights/w600k_mbf.onnx"):
+        rec = ArcFace(path)
+        if rec._engine.stem8(n) is None:                  # a plan that does not open with patches + 1x1
+            assert "r50" not in path
+            continue
+        rec.stem8 = True
+        a = rec.embed_batch(frames, fidx, kps).clone()
+        rec.stem8 = False
+        b = rec.embed_batch(frames, fidx, kps).clone()
+        cos = torch.nn.functional.cosine_similarity(a, b, dim=1)
+        assert cos.min().item() >= 0.99999, cos.min().item()
+        assert (a - b).abs().max().item() <= 2e-3 * b.abs().max().item()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # config 4: all-pairs cosine clustering of 200k embeddings, upper triangle block-partitioned over ranks
 # ---------------------------------------------------------------------------------------------------------
