@@ -493,7 +493,16 @@ def conv_roofline(a, det, rec, frames, pipe, B, F):
         t_det, t_rec = [], []
         eng_d = det._engine_for(det.input_size[1], det.input_size[0])
         eng_d.run(B, timings=t_det)
-        rec._engine.run(B * F, timings=t_rec)
+        st8 = rec._engine.stem8(B * F) if getattr(rec, "stem8", False) else None
+        if st8 is not None:                                  # the product path: first layer in its 8-channel stem form
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            st8[1]()
+            e1.record()
+            t_rec.append((1, "conv", e0, e1))
+            rec._engine.run(B * F, timings=t_rec, start=2)
+        else:
+            rec._engine.run(B * F, timings=t_rec)
         torch.cuda.synchronize()
         for eng, n, tl in ((eng_d, B, t_det), (rec._engine, B * F, t_rec)):
             for i, kind, e0, e1 in tl:
