@@ -44,6 +44,16 @@ class _Bound:
         self.fn, self.args, self.keep = fn, args, keep
 
 
+def stem8_weights(w: torch.Tensor) -> torch.Tensor:
+    """[1][cout_p][32] weights of the first convolution as a 1x1 over 3x3 patches (k = tap * 3 + channel, 27 used) ->
+    [10][cout_p][8] for `b2f_conv2d`'s stem form: slot = filter tap (ky * 3 + kx), 8 stored channels per pixel (3 used),
+    slot 9 zero (the second half of the last K = 16 step)."""
+    cout_p = w.shape[1]
+    w8 = torch.zeros((10, cout_p, 8), dtype=w.dtype, device=w.device)
+    w8[:9, :, :3] = w[0, :, :27].reshape(cout_p, 9, 3).permute(1, 0, 2)
+    return w8.contiguous()
+
+
 class NetEngine:
     def __init__(self, plan: Plan, device: Optional[torch.device] = None, dtype: Optional[int] = None):
         if not torch.cuda.is_available():
@@ -215,10 +225,7 @@ class NetEngine:
             a0, w1 = ops[0].attrs, self._weights[1]
             spec_out = self.plan.tensors[ops[1].dst]
             if self._stem8_w is None:
-                w = w1["weight"]                                   # [1][cout_p][32], k = tap * 3 + channel
-                w8 = torch.zeros((10, w.shape[1], 8), dtype=w.dtype, device=w.device)
-                w8[:9, :, :3] = w[0, :, :27].reshape(w.shape[1], 9, 3).permute(1, 0, 2)
-                self._stem8_w = w8.contiguous()
+                self._stem8_w = stem8_weights(w1["weight"])
             img = torch.zeros((n, a0["h"], a0["w"], 8), dtype=torch_dtype(self.dtype), device=self.device)
             d = _lib.ConvDesc()
             d.n, d.h, d.w, d.cin_p = n, a0["h"], a0["w"], 8

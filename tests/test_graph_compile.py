@@ -114,3 +114,28 @@ def test_known_weight_names_resolve_to_architectures():
     assert archs.arch_for_path("/x/w600k_r50.onnx") == "arcface_r50"
     assert archs.arch_for_path("other.onnx") is None
     assert abs(archs.count_macs(archs.build_arch("scrfd_10g"), (1, 3, 480, 640)) / 1e9 - 10.006) < 0.01
+
+
+def test_stem_form_weights_equal_patch_gemm():
+    """engine.stem8_weights: the first convolution's 1x1-over-patches weights regrouped as [10 taps][cout][8 channels]
+    compute the same 3x3 convolution (CPU, fp32): slot t = tap (ky*3+kx), 3 of 8 channels used, slot 9 zero"""
+    from scrfd_arcface_facerecognition_b200.engine import stem8_weights
+    plan = graph.compile_graph(archs.build_arch("arcface_mbf"), (112, 112))
+    assert plan.ops[0].kind == "im2col" and plan.ops[1].kind == "conv" and plan.ops[1].attrs["kh"] == 1
+    w = torch.from_numpy(np.ascontiguousarray(plan.ops[1].arrays["weight"])).float()      # [1][cout_p][32]
+    w8 = stem8_weights(w)
+    cout_p = w.shape[1]
+    assert w8.shape == (10, cout_p, 8) and (w8[9] == 0).all() and (w8[:, :, 3:] == 0).all()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((2, 3, 20, 24), generator=g)
+    stride = plan.ops[0].attrs["stride"]
+    # patches: k = tap * 3 + channel, then the 1x1 GEMM
+    cols = torch.nn.functional.unfold(x, 3, padding=1, stride=stride)                     # [n, c*9, L] with k = c*9 + tap
+    cols = cols.reshape(2, 3, 9, -1).permute(0, 2, 1, 3).reshape(2, 27, -1)               # k = tap*3 + c
+    want = torch.einsum("ok,nkl->nol", w[0, :, :27], cols)
+    # stem form: a 3x3 convolution over the 8-channel image with the regrouped weights
+    w33 = w8[:9].reshape(3, 3, cout_p, 8).permute(2, 3, 0, 1)                             # [cout][8][ky][kx]
+    x8 = torch.zeros((2, 8, 20, 24))
+    x8[:, :3] = x
+    got = torch.nn.functional.conv2d(x8, w33, None, stride, 1).reshape(2, cout_p, -1)
+    assert torch.allclose(got, want, atol=1e-5)
