@@ -316,21 +316,29 @@ def merge_duplicates(emb: np.ndarray, thr: float) -> np.ndarray:
     return leader
 
 
-def online_clusters(emb: np.ndarray, grouping_thr: float, search_thr: float = 0.0) -> np.ndarray:
+def online_clusters(emb: np.ndarray, grouping_thr: float, search_thr: float = 0.0,
+                    duplicate_thr: float = None) -> np.ndarray:
     """Online leader clustering in visit order: each embedding searches the persons created so far (one stored
     embedding per person = its first visit) and joins the BEST match when its similarity >= grouping_thr, else
     becomes a new person.  Semantics of the per-visit decision at reference duplicate.py:1853-1949 (JSON variant
     :2166-2262) over `search_person` (:1619-1643, cosine top-k with score >= search_thr, best first), made
     deterministic by processing visits in index order instead of thread-pool order.
-    Ties between equally similar persons go to the earliest person.  Returns the person (leader index) of every row."""
+    Ties between equally similar persons go to the earliest person.  Returns the person (leader index) of every row.
+    `duplicate_thr` (config `duplicate_similarity_threshold`, 0.95): `is_duplicate_image` (duplicate.py:2618-2652)
+    drops a visit whose best cosine to an existing person reaches it -- label -1, no visit stored.  That check only
+    runs when the database already owns the `low_similarity_images` table (otherwise its query raises and the
+    function returns False), hence None = off, the behaviour of a fresh database.
+    Pinned by tests/golden/cluster_outputs.npz (the reference's own loop, tests/golden/make_cluster_golden.py)."""
     g = normalize_rows(emb).astype(np.float64)
     n = len(g)
     label = np.full(n, -1, np.int64)
     leaders: list = []
     for i in range(n):
         if leaders:
-            s = g[leaders] @ g[i]
-            s = np.where(s >= search_thr, s, -np.inf)
+            full = g[leaders] @ g[i]
+            if duplicate_thr is not None and full.max() >= duplicate_thr:
+                continue                                # skipped as a duplicate image
+            s = np.where(full >= search_thr, full, -np.inf)
             j = int(np.argmax(s))                       # first maximum = earliest person among equals
             if np.isfinite(s[j]) and s[j] >= grouping_thr:
                 label[i] = leaders[j]
@@ -344,11 +352,14 @@ def online_similarities(emb: np.ndarray, label: np.ndarray, search_thr: float = 
     """The similarity the reference records with each visit of the online loop (duplicate.py:1854-1855:
     `search_results[0]['similarity'] if search_results else 0.0`): for a visit that joined a person its cosine to that
     person, for a visit that founded one the best cosine to the persons existing before it (0.0 when the search
-    returned nothing, i.e. no person yet or none >= search_thr).  `label` as returned by `online_clusters`."""
+    returned nothing, i.e. none >= search_thr); the very first person is stored with 1.0 (duplicate.py:1826), a
+    skipped visit (label -1) with nothing (0).  `label` as returned by `online_clusters`."""
     g = normalize_rows(emb).astype(np.float32)
     out = np.zeros(len(g), np.float32)
     leaders: list = []
     for i in range(len(g)):
+        if label[i] < 0:
+            continue
         if label[i] != i:
             out[i] = np.float32(g[i] @ g[label[i]])
             continue
@@ -356,5 +367,7 @@ def online_similarities(emb: np.ndarray, label: np.ndarray, search_thr: float = 
             s = g[leaders] @ g[i]
             s = s[s >= search_thr]
             out[i] = s.max() if len(s) else 0.0
+        else:
+            out[i] = 1.0
         leaders.append(i)
     return out

@@ -259,16 +259,23 @@ class Gallery:
             pairs = torch.sort(torch.cat([b[:int(c.item())] for b, c in zip(bufs, cnts)])).values
         return self.resolve_pairs(pairs)
 
-    def online_clusters(self, grouping_threshold: float) -> np.ndarray:
+    def online_clusters(self, grouping_threshold: float, duplicate_threshold: Optional[float] = None,
+                        search_threshold: float = 0.0) -> np.ndarray:
         """person (leader row) of every row under the reference's online decision (duplicate.py:1853-1949, processed in
         row order): a row joins the most similar earlier person when cos >= threshold, else founds a new person.
         The founders are exactly the survivors of the greedy leader merge (a row founds a person iff no earlier
         founder reaches the threshold), so: thresholded pairs (tcgen05 GEMM) -> founders (cluster_resolve) -> every
-        other row picks its most similar founder among its pairs (exact fp32 dot, earliest founder on ties)."""
+        other row picks its most similar founder among its pairs (exact fp32 dot, earliest founder on ties).
+        `duplicate_threshold` (config `duplicate_similarity_threshold`): a row whose best cosine to an earlier person
+        reaches it is dropped as a duplicate image (`is_duplicate_image`, duplicate.py:2618-2652) -- label -1.  The
+        reference only reaches that check when its database already has the `low_similarity_images` table; None (the
+        default) is the fresh-database behaviour.  `search_threshold` is `search_person`'s score floor
+        (duplicate.py:1619-1643); a grouping threshold below it cannot admit a row the search did not return."""
         n = len(self)
         if n == 0:
             return np.empty(0, np.int64)
-        pairs = self.duplicate_pairs(grouping_threshold)
+        thr = max(float(grouping_threshold), float(search_threshold))
+        pairs = self.duplicate_pairs(thr)
         lowest = torch.from_numpy(self.resolve_pairs(pairs).astype(np.int64)).to(self.device)
         rows = torch.arange(n, device=self.device)
         founder = lowest == rows
@@ -286,6 +293,8 @@ class Gallery:
             first = torch.ones_like(b_s, dtype=torch.bool)
             first[1:] = b_s[1:] != b_s[:-1]
             label[b_s[first]] = a_s[first]
+            if duplicate_threshold is not None:
+                label[b_s[first][sim[order][first] >= float(duplicate_threshold)]] = -1
         return label.cpu().numpy()
 
     def online_similarities(self, label: np.ndarray, search_threshold: float = 0.0) -> np.ndarray:
@@ -297,7 +306,8 @@ class Gallery:
         n = len(self)
         label_t = torch.as_tensor(np.asarray(label, np.int64), device=self.device)
         rows = torch.arange(n, device=self.device)
-        sim = (self.f32 * self.f32[label_t]).sum(dim=1)
+        sim = (self.f32 * self.f32[label_t.clamp(min=0)]).sum(dim=1)
+        sim[label_t < 0] = 0.0                                                      # skipped as duplicate images
         founders = rows[label_t == rows]
         fm = self.f32[founders]
         best = torch.zeros(len(founders), dtype=torch.float32, device=self.device)
@@ -311,6 +321,8 @@ class Gallery:
             s = torch.where(earlier & (s >= search_threshold), s, torch.full_like(s, -1.0e30))
             m = s.max(dim=1).values
             best[start:stop] = torch.where(m > -1.0e29, m, torch.zeros_like(m))
+        if len(founders):
+            best[0] = 1.0                                                           # first person: duplicate.py:1826
         sim[founders] = best
         return sim.cpu().numpy()
 

@@ -79,3 +79,32 @@ def clustered(seed: int, centres: int, members: int, dim: int = 512, noise: floa
     n /= np.linalg.norm(n, axis=1, keepdims=True)
     x = x + noise * n
     return x[rng.permutation(len(x))].astype(np.float32)
+
+
+def chains(seed: int, n_chains: int, length: int, step: float, dim: int = 512) -> np.ndarray:
+    """Random-walk chains, shuffled: neighbours k apart along a chain have cos ~ 1/sqrt(1 + k step^2), so a threshold
+    between the one-hop and two-hop value makes transitive closure and the reference's greedy one-hop merge differ."""
+    rng = np.random.default_rng(seed)
+    rows = []
+    for _ in range(n_chains):
+        x = rng.standard_normal(dim)
+        x /= np.linalg.norm(x)
+        for _ in range(length):
+            rows.append(x.copy())
+            n = rng.standard_normal(dim)
+            n /= np.linalg.norm(n)
+            x = x + step * n
+            x /= np.linalg.norm(x)
+    x = np.asarray(rows, np.float32)
+    return x[rng.permutation(len(x))]
+
+
+def cluster_cases():
+    """(name, rows) of the clustering golden set (tests/golden/make_cluster_golden.py); rows are raw (un-normalised)."""
+    a = clustered(41, 60, 5, noise=0.6)                       # clean clusters, cos ~ 0.73 inside
+    b = chains(42, 24, 12, 1.2)                               # online threshold 0.45 sits between hop 2 and hop 3
+    c = chains(43, 30, 10, 0.6)                               # merge threshold 0.8 sits between hop 1 and hop 2
+    d = np.concatenate([clustered(44, 40, 4, noise=0.35), clustered(45, 25, 6, noise=0.2)])   # tight: cos ~ 0.89 / 0.96
+    d = d[np.random.default_rng(46).permutation(len(d))]
+    scale = np.random.default_rng(47).uniform(3.0, 25.0, (len(d), 1)).astype(np.float32)
+    return [("clusters", a), ("chains_wide", b), ("chains_tight", c), ("mixed", d * scale)]

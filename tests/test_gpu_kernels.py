@@ -728,6 +728,34 @@ def test_online_clusters_match_oracle(lib, centres, members, noise):
     assert Gallery().online_clusters(0.8).shape == (0,)
 
 
+@pytest.mark.parametrize("case", inputs.cluster_cases(), ids=lambda c: c[0])
+def test_clustering_matches_reference_run(lib, case):
+    """rows a19-a21 against the REFERENCE's own code run verbatim (tests/golden/make_cluster_golden.py: duplicate.py's
+    online loop, find_and_merge_duplicates and QdrantManager.search_similar over a restated qdrant local mode).
+    Identities / labels / leaders bit-exact; similarities within fp32 summation-order noise (2e-6)."""
+    import os
+    from scrfd_arcface_facerecognition_b200.gallery import Gallery
+    name, rows = case
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "cluster_outputs.npz")))
+    grouping, search, duplicate, merge = (float(v) for v in g["thresholds"])
+    G = Gallery()
+    G.add(rows)
+    label = G.online_clusters(grouping, search_threshold=search)
+    np.testing.assert_array_equal(label, g[f"online_{name}_label"])
+    np.testing.assert_allclose(G.online_similarities(label, search), g[f"online_{name}_sim"], rtol=0, atol=2e-6)
+    label = G.online_clusters(grouping, duplicate_threshold=duplicate, search_threshold=search)
+    np.testing.assert_array_equal(label, g[f"online_dup_{name}_label"])
+    np.testing.assert_allclose(G.online_similarities(label, search), g[f"online_dup_{name}_sim"], rtol=0, atol=2e-6)
+    np.testing.assert_array_equal(G.merge_duplicates(merge), g[f"merge_{name}_leader"])
+    qs, _ = inputs.planted_queries(rows, 90, 12, noise=0.8)
+    for qi, q in enumerate(qs):
+        res = G.search_similar(q, k=5, threshold=search)
+        gi, gs = g[f"search_{name}_idx"][qi], g[f"search_{name}_score"][qi]
+        k = int((gi >= 0).sum())
+        assert [r["person_id"] for r in res] == list(gi[:k])
+        np.testing.assert_allclose([r["similarity"] for r in res], gs[:k], rtol=0, atol=2e-6)
+
+
 @pytest.mark.gpu
 def test_clustering_results_written_from_gpu_labels(lib, tmp_path):
     """GPU labels -> the reference's SQLite rows and clustering_results JSON; identical to the same

@@ -170,3 +170,61 @@ def test_online_clusters_semantics():
     founders = restate.merge_duplicates(emb, 0.8) == np.arange(len(emb))
     assert ((lab == np.arange(len(emb))) == founders).all()      # same founders as the greedy merge
     assert len(np.unique(lab)) == 40
+
+
+# ---------------------------------------------------------------------------------------------
+# a19-a21 pinned to the reference's own clustering code (tests/golden/make_cluster_golden.py ran duplicate.py and
+# qdrant_manager.py verbatim over oracle/fakes.py; outputs in tests/golden/cluster_outputs.npz)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def cluster_golden():
+    import os
+    return dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "cluster_outputs.npz")))
+
+
+@pytest.mark.parametrize("case", inputs.cluster_cases(), ids=lambda c: c[0])
+def test_clustering_restatement_matches_reference_run(cluster_golden, case):
+    name, rows = case
+    g = cluster_golden
+    grouping, search, duplicate, merge = g["thresholds"]
+    label = restate.online_clusters(rows, grouping, search)
+    np.testing.assert_array_equal(label, g[f"online_{name}_label"])                      # a20, fresh database
+    np.testing.assert_allclose(restate.online_similarities(rows, label, search), g[f"online_{name}_sim"], rtol=0, atol=1e-6)
+    label = restate.online_clusters(rows, grouping, search, duplicate)
+    np.testing.assert_array_equal(label, g[f"online_dup_{name}_label"])                  # a20 with the 0.95 duplicate gate
+    np.testing.assert_allclose(restate.online_similarities(rows, label, search), g[f"online_dup_{name}_sim"], rtol=0, atol=1e-6)
+    np.testing.assert_array_equal(restate.merge_duplicates(rows, merge), g[f"merge_{name}_leader"])   # a21
+    qs, _ = inputs.planted_queries(rows, 90, 12, noise=0.8)
+    for qi, q in enumerate(qs):                                                          # a19: k = 5, score >= 0.35
+        idx, sc = restate.search_similar(q, rows, 5, search)
+        gi, gs = g[f"search_{name}_idx"][qi], g[f"search_{name}_score"][qi]
+        np.testing.assert_array_equal(gi[:len(idx)], idx)
+        assert (gi[len(idx):] < 0).all()
+        np.testing.assert_allclose(gs[:len(idx)], sc, rtol=0, atol=1e-6)
+
+
+def test_cluster_golden_exercises_the_hard_cases(cluster_golden):
+    """The fixture is only worth its name if greedy one-hop != transitive closure somewhere and the duplicate gate fires."""
+    g = cluster_golden
+    n = len(g["merge_chains_tight_leader"])
+    survivors = int((g["merge_chains_tight_leader"] == np.arange(n)).sum())
+    assert 30 < survivors < n                                                            # 30 chains; closure would leave 30
+    assert int((g["online_dup_mixed_label"] < 0).sum()) > 50 and int((g["online_mixed_label"] < 0).sum()) == 0
+
+
+def test_fake_qdrant_semantics():
+    """The restated qdrant local mode: cosine normalises at upsert, `>=` threshold, descending order, upsert replaces."""
+    from oracle import fakes
+    c = fakes.QdrantClient(":memory:")
+    c.create_collection("x", fakes.VectorParams(4, fakes.Distance.COSINE))
+    c.upsert("x", [fakes.PointStruct(1, [2, 0, 0, 0], {"name": "a"}), fakes.PointStruct(2, [1, 1, 0, 0], {"name": "b"}),
+                   fakes.PointStruct(3, [0, 0, 3, 0], {"name": "c"})])
+    r = c.search("x", [5, 0, 0, 0], limit=10, score_threshold=float(np.float32(1 / np.sqrt(2))) - 1e-7)
+    assert [p.id for p in r] == [1, 2] and abs(r[0].score - 1.0) < 1e-7
+    assert np.allclose(c.retrieve("x", [2], with_vectors=True)[0].vector, [2 ** -0.5, 2 ** -0.5, 0, 0])
+    c.upsert("x", [fakes.PointStruct(2, [0, 0, 0, 1], {"name": "b2"})])
+    assert c.get_collection("x").points_count == 3 and [p.id for p in c.search("x", [5, 0, 0, 0], limit=1)] == [1]
+    c.delete("x", fakes.PointIdsList([1]))
+    assert c.get_collection("x").points_count == 2
+    c.delete("x", fakes.FilterSelector(fakes.Filter()))
+    assert c.get_collection("x").points_count == 0 and c.search("x", [1, 0, 0, 0], limit=3) == []
