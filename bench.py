@@ -23,6 +23,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# weights/*.onnx cannot be fetched offline: the benchmark opts in to seeded random weights of the same architectures
+# (the product raises FileNotFoundError on a missing model file otherwise) and says so in `config.weights`
+os.environ.setdefault("B2F_SYNTHETIC_WEIGHTS", "1")
 
 METRIC = "end-to-end faces/sec SCRFD-10G+ArcFace-R50 (detect->align->embed->match vs 1M gallery)"
 UNIT = "faces/s"

@@ -2,9 +2,11 @@
 
 Imports the reference's own `models/scrfd.py`, `models/arcface.py` and `utils/helpers.py`
 *verbatim* from the read-only reference tree (never copied into this repo), with the two missing
-third-party wheels replaced by oracle.shims.  The reference tree only exists in the build
-container (`/root/reference`, or $B2F_REFERENCE); on the GPU box `load()` returns None and tests
-fall back to the committed fixtures in tests/golden/.
+third-party wheels replaced by oracle.shims.  The reference tree exists in the build container
+(`/root/reference`, or $B2F_REFERENCE); `oracle/install_ref.py` (run by `__graft_entry__.build()`) places the four
+files of the path under the git-ignored `baseline/_ref/`, which travels to the GPU box, so `load()` finds the
+reference there too.  With neither, `load()` returns None and callers fall back to the restated port and the committed
+fixtures in tests/golden/.
 """
 from __future__ import annotations
 
@@ -18,7 +20,10 @@ _CACHE = {}
 
 
 def reference_root() -> Optional[str]:
-    for cand in (os.environ.get("B2F_REFERENCE"), "/root/reference"):
+    """$B2F_REFERENCE, the read-only tree of the build container, or the copy oracle/install_ref.py placed under
+    baseline/_ref/ (git-ignored; that one travels to the GPU box)."""
+    repo_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.environ.get("B2F_REFERENCE"), "/root/reference", os.path.join(repo_root, "baseline", "_ref")):
         if cand and os.path.isfile(os.path.join(cand, "models", "scrfd.py")):
             return cand
     return None

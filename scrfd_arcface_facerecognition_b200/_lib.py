@@ -39,17 +39,49 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu for sm_100a into csrc/libb2f.so (in-tree, travels with the repo snapshot)."""
+    """Compile csrc/*.cu for sm_100a into csrc/libb2f.so (in-tree, travels with the repo snapshot).
+    Ranks of one torchrun job may all find the library stale: an exclusive file lock serialises them (the ones that
+    waited see a fresh library and return), and each compile goes to its own temp file before the atomic rename."""
     if not force and not _stale():
         return SO_PATH
-    nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", SO_PATH + ".tmp"] + SOURCES
-    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise B2FError(f"nvcc failed ({' '.join(cmd)}):\n{res.stdout}\n{res.stderr}")
-    os.replace(SO_PATH + ".tmp", SO_PATH)
-    if verbose:
-        print(res.stdout, res.stderr)
+    import fcntl
+    with open(os.path.join(CSRC, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return SO_PATH
+            nvcc = os.environ.get("NVCC", "nvcc")
+            # one object per source, compiled in parallel and only when the source (or a header) is newer than it
+            from concurrent.futures import ThreadPoolExecutor
+            objdir = os.path.join(CSRC, "build")
+            os.makedirs(objdir, exist_ok=True)
+            hdr_m = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS if os.path.exists(os.path.join(CSRC, h)))
+
+            def compile_one(src):
+                obj = os.path.join(objdir, src.replace(".cu", ".o"))
+                src_m = max(os.path.getmtime(os.path.join(CSRC, src)), hdr_m)
+                if not force and os.path.exists(obj) and os.path.getmtime(obj) >= src_m:
+                    return obj, None
+                cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-c", "-o", obj, src]
+                res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+                return obj, (None if res.returncode == 0 else f"({' '.join(cmd)}):\n{res.stdout}\n{res.stderr}")
+            with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+                results = list(ex.map(compile_one, SOURCES))
+            errors = [e for _, e in results if e]
+            if errors:
+                raise B2FError("nvcc failed " + "\n".join(errors))
+            tmp = f"{SO_PATH}.{os.getpid()}.tmp"
+            cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + [o for o, _ in results]
+            res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise B2FError(f"nvcc link failed ({' '.join(cmd)}):\n{res.stdout}\n{res.stderr}")
+            os.replace(tmp, SO_PATH)
+            if verbose:
+                print(res.stdout, res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return SO_PATH
 
 
@@ -130,11 +162,18 @@ def lib() -> C.CDLL:
         if _lib is not None:
             return _lib
         if _stale():
-            try:
-                build()
-            except Exception as e:  # no nvcc on the box and no prebuilt .so: fail loudly
-                if not os.path.exists(SO_PATH):
-                    raise B2FError(f"libb2f.so is missing and could not be built: {e}") from e
+            # a library older than its sources is never loaded silently: rebuild, and if that fails, raise.  The one
+            # exception is a box without a compiler that received a prebuilt library next to freshly copied sources
+            # (file times are not preserved by the snapshot): B2F_PREBUILT=1, or no nvcc on PATH at all.
+            import shutil
+            have_nvcc = shutil.which(os.environ.get("NVCC", "nvcc")) is not None
+            if os.path.exists(SO_PATH) and (os.environ.get("B2F_PREBUILT") == "1" or not have_nvcc):
+                pass
+            else:
+                try:
+                    build()
+                except Exception as e:
+                    raise B2FError(f"libb2f.so is stale or missing and could not be rebuilt: {e}") from e
         try:
             handle = C.CDLL(SO_PATH)
         except OSError as e:

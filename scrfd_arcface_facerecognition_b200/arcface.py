@@ -92,45 +92,53 @@ class ArcFace:
             frame = torch.from_numpy(np.ascontiguousarray(image)).cuda(non_blocking=True)[None]
             lm = torch.from_numpy(kps.reshape(1, 10)).cuda(non_blocking=True)
             idx = torch.zeros(1, dtype=torch.int32, device=frame.device)
-            emb = self.embed_batch(frame, idx, lm)
+            emb = self.embed_batch(frame, idx, lm, copy=False)      # the D2H copy below happens under the lock
             return emb[0].cpu().numpy().flatten()
 
     get_embedding = __call__
 
     def embed_batch(self, frames: torch.Tensor, frame_idx: torch.Tensor, kps: torch.Tensor,
-                    crops_u8: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    crops_u8: Optional[torch.Tensor] = None, copy: bool = True) -> torch.Tensor:
         """frames [B,H,W,3] u8 cuda; frame_idx [F] int32; kps [F,10] (or [F,5,2]) f32 -> [F,512] f32 (device).
-        norm_crop (similarity estimate + warpAffine + normalise + layout) is one kernel; the net follows."""
+        norm_crop (similarity estimate + warpAffine + normalise + layout) is one kernel; the net follows.
+        The engine writes into persistent buffers shared by every call of the same capacity, so by default the result
+        is copied out (on the stream, still under the model lock) and belongs to the caller -- the reference's
+        callers run the shared model from a thread pool (duplicate.py:1954).  `copy=False` returns the aliased view;
+        it stays valid only until the next call on this model (the CUDA-graph pipeline, which owns the model, uses it)."""
         with self._lock:
-            f = int(frame_idx.shape[0])
-            w, h = self.input_size
-            stem8 = self._engine.stem8(f) if (self.fuse_stem and self.stem8 and crops_u8 is None) else None
-            if stem8 is not None:
-                # aligned crop kept as an 8-channel image (16 B per pixel); the first convolution reads it tap by tap
-                if w == h == 112:                       # one CTA per face, crop staged in shared memory
-                    _lib.check(self._lib.b2f_norm_crop_image8(
-                        frames.data_ptr(), frames.shape[1], frames.shape[2], frame_idx.data_ptr(),
-                        kps.reshape(f, 10).contiguous().data_ptr(), f, w, float(self.input_mean), self._scale,
-                        stem8[0].data_ptr(), self._engine.dtype, stream_ptr()), "b2f_norm_crop_image8")
-                else:
-                    _lib.check(self._lib.b2f_norm_crop(
-                        frames.data_ptr(), frames.shape[1], frames.shape[2], frame_idx.data_ptr(),
-                        kps.reshape(f, 10).contiguous().data_ptr(), f, w, float(self.input_mean), self._scale,
-                        stem8[0].data_ptr(), 8, self._engine.dtype, None, None, stream_ptr()), "b2f_norm_crop")
-                stem8[1]()
-                return self._engine.run(f, start=2)[self.output_names[0]].reshape(f, -1)
-            patches = self._engine.patch_buffer(f) if (self.fuse_stem and crops_u8 is None and w == h == 112) else None
-            if patches is not None and patches[1] == 1:
-                # norm_crop + blob + first-layer patch extraction in one kernel (one CTA per face)
-                _lib.check(self._lib.b2f_norm_crop_patches(
+            out = self._embed_batch_view(frames, frame_idx, kps, crops_u8)
+            return out.clone() if copy else out
+
+    def _embed_batch_view(self, frames, frame_idx, kps, crops_u8):
+        f = int(frame_idx.shape[0])
+        w, h = self.input_size
+        stem8 = self._engine.stem8(f) if (self.fuse_stem and self.stem8 and crops_u8 is None) else None
+        if stem8 is not None:
+            # aligned crop kept as an 8-channel image (16 B per pixel); the first convolution reads it tap by tap
+            if w == h == 112:                       # one CTA per face, crop staged in shared memory
+                _lib.check(self._lib.b2f_norm_crop_image8(
                     frames.data_ptr(), frames.shape[1], frames.shape[2], frame_idx.data_ptr(),
                     kps.reshape(f, 10).contiguous().data_ptr(), f, w, float(self.input_mean), self._scale,
-                    patches[0].data_ptr(), self._engine.dtype, stream_ptr()), "b2f_norm_crop_patches")
-                return self._engine.run(f, start=1)[self.output_names[0]].reshape(f, -1)
-            x = self._engine.input_buffer(f)
-            _lib.check(self._lib.b2f_norm_crop(
+                    stem8[0].data_ptr(), self._engine.dtype, stream_ptr()), "b2f_norm_crop_image8")
+            else:
+                _lib.check(self._lib.b2f_norm_crop(
+                    frames.data_ptr(), frames.shape[1], frames.shape[2], frame_idx.data_ptr(),
+                    kps.reshape(f, 10).contiguous().data_ptr(), f, w, float(self.input_mean), self._scale,
+                    stem8[0].data_ptr(), 8, self._engine.dtype, None, None, stream_ptr()), "b2f_norm_crop")
+            stem8[1]()
+            return self._engine.run(f, start=2)[self.output_names[0]].reshape(f, -1)
+        patches = self._engine.patch_buffer(f) if (self.fuse_stem and crops_u8 is None and w == h == 112) else None
+        if patches is not None and patches[1] == 1:
+            # norm_crop + blob + first-layer patch extraction in one kernel (one CTA per face)
+            _lib.check(self._lib.b2f_norm_crop_patches(
                 frames.data_ptr(), frames.shape[1], frames.shape[2], frame_idx.data_ptr(),
-                kps.reshape(f, 10).contiguous().data_ptr(), f, w, float(self.input_mean), self._scale, x.data_ptr(),
-                4, self._engine.dtype, None if crops_u8 is None else crops_u8.data_ptr(), None, stream_ptr()),
-                "b2f_norm_crop")
-            return self._embed_loaded(f)
+                kps.reshape(f, 10).contiguous().data_ptr(), f, w, float(self.input_mean), self._scale,
+                patches[0].data_ptr(), self._engine.dtype, stream_ptr()), "b2f_norm_crop_patches")
+            return self._engine.run(f, start=1)[self.output_names[0]].reshape(f, -1)
+        x = self._engine.input_buffer(f)
+        _lib.check(self._lib.b2f_norm_crop(
+            frames.data_ptr(), frames.shape[1], frames.shape[2], frame_idx.data_ptr(),
+            kps.reshape(f, 10).contiguous().data_ptr(), f, w, float(self.input_mean), self._scale, x.data_ptr(),
+            4, self._engine.dtype, None if crops_u8 is None else crops_u8.data_ptr(), None, stream_ptr()),
+            "b2f_norm_crop")
+        return self._embed_loaded(f)

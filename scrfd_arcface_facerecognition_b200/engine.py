@@ -44,6 +44,18 @@ class _Bound:
         self.fn, self.args, self.keep = fn, args, keep
 
 
+def capacity_for(n: int) -> int:
+    """Activation buffers are sized for the next power of two >= n, so a service that sees every face count 1..K binds
+    log2(K) buffer sets (at most 2x the largest) instead of K of them."""
+    cap = 1
+    while cap < n:
+        cap *= 2
+    return cap
+
+
+MAX_BOUND = 64      # per-batch-size launch lists kept (descriptors only, a few KB each); least recently used goes first
+
+
 def stem8_weights(w: torch.Tensor) -> torch.Tensor:
     """[1][cout_p][32] weights of the first convolution as a 1x1 over 3x3 patches (k = tap * 3 + channel, 27 used) ->
     [10][cout_p][8] for `b2f_conv2d`'s stem form: slot = filter tap (ky * 3 + kx), 8 stored channels per pixel (3 used),
@@ -72,7 +84,9 @@ class NetEngine:
                     t = t.to(tdt)
                 dev[k] = t.to(self.device).contiguous()
             self._weights.append(dev)
+        # launch lists per exact batch size n (descriptors + views) over buffer pools per capacity (capacity_for(n))
         self._bound: Dict[int, Tuple[List[_Bound], Dict[str, torch.Tensor], List[torch.Tensor]]] = {}
+        self._pools: Dict[int, List[torch.Tensor]] = {}
         # liveness: last op index that reads each tensor
         self._last_use: Dict[str, int] = {}
         for i, op in enumerate(plan.ops):
@@ -84,19 +98,45 @@ class NetEngine:
         self._out_tensors = {o[1] for o in plan.outputs}
         self.in_place = os.environ.get("B2F_IN_PLACE", "1") != "0"
         self._stem8: Dict[int, tuple] = {}
+        self._stem8_img: Dict[int, torch.Tensor] = {}
         self._stem8_w: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------------------------------
+    def _bound_for(self, n: int):
+        if n in self._bound:
+            self._bound[n] = self._bound.pop(n)              # most recently used last
+            return self._bound[n]
+        while len(self._bound) >= MAX_BOUND:
+            old = next(iter(self._bound))
+            self._bound.pop(old)
+            self._stem8.pop(old, None)
+        self._bound[n] = self._bind(n)
+        return self._bound[n]
+
     def _bind(self, n: int):
+        """Views and launch descriptors for exactly n images over the buffer pool of capacity_for(n).  Buffer sizes and
+        the order they are requested in depend on the capacity only, so every n of one capacity replays the same
+        allocation sequence and lands on the same buffers (NHWC with the image index outermost: n images are a prefix)."""
         plan = self.plan
         esz = 2
+        cap = capacity_for(n)
+        pool = self._pools.setdefault(cap, [])
+        cursor = [0]
         free: List[torch.Tensor] = []
-        all_bufs: List[torch.Tensor] = []
         tens: Dict[str, torch.Tensor] = {}
         bound: List[_Bound] = []
+
+        def new_buffer(nbytes: int) -> torch.Tensor:
+            j = cursor[0]
+            cursor[0] += 1
+            if j == len(pool):
+                pool.append(torch.empty(nbytes, dtype=torch.uint8, device=self.device))
+            assert pool[j].numel() >= nbytes
+            return pool[j]
+
         h0, w0 = plan.in_hw
-        in_buf = torch.empty((n, h0, w0, 4), dtype=torch_dtype(self.dtype), device=self.device)
-        tens[plan.input_name] = in_buf
+        in_raw = new_buffer(cap * h0 * w0 * 4 * esz)
+        tens[plan.input_name] = in_raw[:n * h0 * w0 * 4 * esz].view(torch_dtype(self.dtype)).view(n, h0, w0, 4)
 
         def alloc(nbytes: int) -> torch.Tensor:
             best = -1
@@ -105,26 +145,24 @@ class NetEngine:
                     best = j
             if best >= 0:
                 return free.pop(best)
-            b = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            all_bufs.append(b)
-            return b
+            return new_buffer(nbytes)
 
         backing: Dict[str, torch.Tensor] = {}
         for i, op in enumerate(plan.ops):
             spec = plan.tensors[op.dst]
-            nbytes = n * spec.h * spec.w * spec.cp * (4 if spec.f32 else esz)
+            per_image = spec.h * spec.w * spec.cp * (4 if spec.f32 else esz)
             if self._in_place(i, op, backing):
                 raw = backing.pop(op.residual)          # the block output overwrites its identity input
             else:
-                raw = alloc((nbytes + 255) // 256 * 256)
+                raw = alloc((cap * per_image + 255) // 256 * 256)
             backing[op.dst] = raw
-            view = raw[:nbytes].view(torch.float32 if spec.f32 else torch_dtype(self.dtype))
+            view = raw[:n * per_image].view(torch.float32 if spec.f32 else torch_dtype(self.dtype))
             tens[op.dst] = view.view(n, spec.h, spec.w, spec.cp)
             bound.append(self._bind_op(i, op, n, tens))
             for name in (op.src, op.residual, op.sc_src):
                 if name and name in backing and self._last_use.get(name) == i and name not in self._out_tensors:
                     free.append(backing.pop(name))
-        return bound, tens, all_bufs
+        return bound, tens, pool
 
     def _in_place(self, i: int, op: FusedOp, backing: Dict[str, torch.Tensor]) -> bool:
         """A residual convolution without an activation after the add (every IResNet block output) may write over its
@@ -194,9 +232,7 @@ class NetEngine:
     # ------------------------------------------------------------------------------------------
     def input_buffer(self, n: int) -> torch.Tensor:
         """[n, H, W, 4] 16-bit NHWC buffer the preprocess / norm_crop kernels write into."""
-        if n not in self._bound:
-            self._bound[n] = self._bind(n)
-        return self._bound[n][1][self.plan.input_name]
+        return self._bound_for(n)[1][self.plan.input_name]
 
     def patch_buffer(self, n: int) -> Optional[Tuple[torch.Tensor, int]]:
         """When the plan starts with the 3x3 patch extraction of the first convolution, the ([n,ho,wo,32] tensor it
@@ -204,9 +240,7 @@ class NetEngine:
         op = self.plan.ops[0]
         if op.kind != "im2col":
             return None
-        if n not in self._bound:
-            self._bound[n] = self._bind(n)
-        return self._bound[n][1][op.dst], int(op.attrs["stride"])
+        return self._bound_for(n)[1][op.dst], int(op.attrs["stride"])
 
     def stem8(self, n: int):
         """When the plan opens with the 3x3 / pad 1 patch extraction followed by the first convolution as a 1x1 over the
@@ -219,14 +253,15 @@ class NetEngine:
                 or ops[1].sc_src or ops[1].attrs["kh"] != 1 or self.plan.tensors[ops[1].dst].f32):
             return None
         if n not in self._stem8:
-            if n not in self._bound:
-                self._bound[n] = self._bind(n)
-            tens = self._bound[n][1]
+            tens = self._bound_for(n)[1]
             a0, w1 = ops[0].attrs, self._weights[1]
             spec_out = self.plan.tensors[ops[1].dst]
             if self._stem8_w is None:
                 self._stem8_w = stem8_weights(w1["weight"])
-            img = torch.zeros((n, a0["h"], a0["w"], 8), dtype=torch_dtype(self.dtype), device=self.device)
+            cap = capacity_for(n)
+            if cap not in self._stem8_img:
+                self._stem8_img[cap] = torch.zeros((cap, a0["h"], a0["w"], 8), dtype=torch_dtype(self.dtype), device=self.device)
+            img = self._stem8_img[cap][:n]
             d = _lib.ConvDesc()
             d.n, d.h, d.w, d.cin_p = n, a0["h"], a0["w"], 8
             d.ho, d.wo, d.cout_p = a0["ho"], a0["wo"], spec_out.cp
@@ -249,9 +284,7 @@ class NetEngine:
         """Run the net on whatever `input_buffer(n)` holds (or, with start=1, on a filled `patch_buffer(n)`);
         returns {graph output name: [n,H,W,C] fp32 view}.
         `timings`, when given, receives (op index, kind, start event, end event) per launch (bench roofline)."""
-        if n not in self._bound:
-            self._bound[n] = self._bind(n)
-        bound, tens, _ = self._bound[n]
+        bound, tens, _ = self._bound_for(n)
         sp = stream_ptr()
         for i, b in enumerate(bound):
             if i < start:
@@ -275,9 +308,21 @@ class NetEngine:
         return len(self.plan.ops)
 
     def release(self, n: Optional[int] = None) -> None:
+        """Drop the launch list of batch size n (all of them, with every buffer pool, when n is None)."""
         if n is None:
             self._bound.clear()
             self._stem8.clear()
+            self._pools.clear()
+            self._stem8_img.clear()
         else:
             self._bound.pop(n, None)
             self._stem8.pop(n, None)
+            cap = capacity_for(n)
+            if not any(capacity_for(m) == cap for m in self._bound):
+                self._pools.pop(cap, None)
+                self._stem8_img.pop(cap, None)
+
+    def buffer_bytes(self) -> int:
+        """Bytes of activation storage currently held (all capacities)."""
+        return sum(b.numel() for pool in self._pools.values() for b in pool) + \
+            sum(t.numel() * t.element_size() for t in self._stem8_img.values())

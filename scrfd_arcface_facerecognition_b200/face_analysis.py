@@ -87,7 +87,8 @@ class FaceAnalysis:
             frame = torch.from_numpy(np.ascontiguousarray(img)).cuda(non_blocking=True)[None]
             lm = torch.from_numpy(np.ascontiguousarray(kpss, dtype=np.float32).reshape(-1, 10)).cuda(non_blocking=True)
             idx = torch.zeros(lm.shape[0], dtype=torch.int32, device=frame.device)
-            embs = self.rec_model.embed_batch(frame, idx, lm).cpu().numpy()
+            with self.rec_model._lock:       # D2H inside the model lock: another thread's run cannot overwrite the buffer
+                embs = self.rec_model.embed_batch(frame, idx, lm, copy=False).cpu().numpy()
         faces = []
         for i in range(bboxes.shape[0]):
             face = Face(bbox=bboxes[i, 0:4], kps=kpss[i], det_score=float(bboxes[i, 4]))

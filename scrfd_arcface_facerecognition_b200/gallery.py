@@ -84,6 +84,9 @@ class Gallery:
         self.payloads: List[dict] = []
         self.idx_base = 0            # global index of this shard's first row
         self._scratch = {}
+        # bumped whenever the row count, the base index or the storage pointers change: a CUDA graph that captured a
+        # match against this gallery is valid for one version only (FacePipeline.capture keys its cache on it)
+        self.version = 0
 
     # ---- population ------------------------------------------------------------------------------
     def __len__(self) -> int:
@@ -117,6 +120,7 @@ class Gallery:
         self.f32, self.h16 = self._store32[:start + n], self._store16[:start + n]
         self.ids.extend(ids if ids is not None else range(start, start + n))
         self.payloads.extend(payloads if payloads is not None else [{} for _ in range(n)])
+        self.version += 1
 
     def set_shard(self, embeddings, idx_base: int) -> None:
         """Replace the contents with one shard of a larger gallery whose first row has global index idx_base."""
@@ -127,6 +131,7 @@ class Gallery:
         self._cap = 0
         self.add(embeddings)
         self.idx_base = int(idx_base)
+        self.version += 1
 
     def replace_rows(self, rows: torch.Tensor, embeddings: torch.Tensor) -> None:
         """Overwrite local rows (int64 indices into this shard) with new embeddings (upsert of existing ids)."""
@@ -135,13 +140,17 @@ class Gallery:
         self.h16[rows] = h16
 
     def remove(self, row: int) -> None:
-        """Delete one row; later rows keep their order (indices above `row` shift down by one)."""
+        """Delete one row; later rows keep their order (indices above `row` shift down by one).  The tail moves down in
+        bounded chunks (front to back, so a chunk never overwrites rows it has yet to read): no O(G) temporary."""
         n = len(self)
-        if row < n - 1:
-            self.f32[row:n - 1] = self.f32[row + 1:n].clone()
-            self.h16[row:n - 1] = self.h16[row + 1:n].clone()
+        chunk = 1 << 16
+        for lo in range(row, n - 1, chunk):
+            hi = min(lo + chunk, n - 1)
+            self.f32[lo:hi] = self.f32[lo + 1:hi + 1].clone()
+            self.h16[lo:hi] = self.h16[lo + 1:hi + 1].clone()
         self.f32, self.h16 = self.f32[:n - 1], self.h16[:n - 1]
         del self.ids[row], self.payloads[row]
+        self.version += 1
 
     def clear(self) -> None:
         self.set_shard(torch.empty((0, self.dim)), 0)

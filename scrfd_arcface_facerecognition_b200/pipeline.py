@@ -36,8 +36,9 @@ class FacePipeline:
     def process(self, frames: torch.Tensor) -> Dict[str, torch.Tensor]:
         """frames [B,H,W,3] uint8 on the device.  All results stay on the device."""
         b = frames.shape[0]
-        det, kps, counts = self.det.detect_batch(frames, self.max_num, self.metric, max_det=self.max_num)
-        emb = self.rec.embed_batch(frames, self._frame_idx(b, frames.device), kps.reshape(b * self.max_num, 10))
+        # the pipeline owns both models for the step: results stay in the models' persistent buffers (no copies)
+        det, kps, counts = self.det.detect_batch(frames, self.max_num, self.metric, max_det=self.max_num, copy=False)
+        emb = self.rec.embed_batch(frames, self._frame_idx(b, frames.device), kps.reshape(b * self.max_num, 10), copy=False)
         out = {"det": det, "kps": kps, "counts": counts, "emb": emb}
         out["valid"] = (torch.arange(self.max_num, device=frames.device)[None, :] < counts[:, 0:1])
         if self.gallery is not None:
@@ -49,9 +50,12 @@ class FacePipeline:
     # ---- CUDA-graph replay of the whole step -----------------------------------------------------
     def capture(self, b: int, h: int, w: int):
         """Warm up and capture `process` for a [b,h,w,3] batch.  Returns (static_frames, outputs, graph, kernels)."""
+        version = self.gallery.version if self.gallery is not None else -1
         key = (b, h, w)
         if key in self._graphs:
-            return self._graphs[key]
+            if self._graphs[key][4] == version:
+                return self._graphs[key][:4]
+            del self._graphs[key]       # the gallery changed since capture: its row count / pointers in the graph are stale
         dev = self.det._engine_for(self.det.input_size[1], self.det.input_size[0]).device
         static = torch.zeros((b, h, w, 3), dtype=torch.uint8, device=dev)
         side = torch.cuda.Stream(device=dev)
@@ -66,5 +70,7 @@ class FacePipeline:
         with torch.cuda.graph(graph):
             outs = self.process(static)
         kernels = _lib.launch_count() - before
-        self._graphs[key] = (static, outs, graph, kernels)
-        return self._graphs[key]
+        # the graph holds raw pointers: keep the detector's scratch tensors of this capture alive with it
+        keep = [dict(v) for v in self.det._scratch.values()]
+        self._graphs[key] = (static, outs, graph, kernels, version, keep)
+        return self._graphs[key][:4]

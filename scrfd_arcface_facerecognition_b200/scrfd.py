@@ -22,14 +22,25 @@ from .graph import compile_graph
 __all__ = ["SCRFD"]
 
 
+def synthetic_weights_allowed() -> bool:
+    return os.environ.get("B2F_SYNTHETIC_WEIGHTS", "0") == "1"
+
+
 def load_graph(model_path: str):
-    """ONNX initialisers from `model_path`; the same architecture with seeded random weights when the
-    file is absent offline and its name is one of the reference's five (download.sh:12-16)."""
+    """ONNX initialisers from `model_path`.  A missing file raises FileNotFoundError, as the reference's
+    `onnxruntime.InferenceSession` does (models/scrfd.py:59-68 prints and re-raises).  Only with the explicit opt-in
+    B2F_SYNTHETIC_WEIGHTS=1 (the offline tests and bench.py set it: the five files of download.sh:12-16 cannot be
+    fetched there) is a missing file of one of those five names replaced by the same architecture with seeded
+    random weights -- loudly, because such a model detects and embeds noise."""
     if model_path is not None and os.path.isfile(model_path):
         return onnx_wire.load_model(model_path)
     arch = archs.arch_for_path(str(model_path))
-    if arch is None:
-        raise FileNotFoundError(f"Load model from {model_path} failed: file not found and not a known weight name")
+    if arch is None or not synthetic_weights_allowed():
+        hint = "" if arch is None else " (set B2F_SYNTHETIC_WEIGHTS=1 to run the architecture with random weights)"
+        raise FileNotFoundError(f"Load model from {model_path} failed: file not found{hint}")
+    import warnings
+    warnings.warn(f"{model_path} is missing: running {arch} with SEEDED RANDOM weights (B2F_SYNTHETIC_WEIGHTS=1); "
+                  "detections and embeddings are meaningless outside tests and benchmarks", RuntimeWarning, stacklevel=3)
     return archs.build_arch(arch)
 
 
@@ -95,7 +106,11 @@ class SCRFD:
 
     def _bufs(self, batch: int, h: int, w: int, max_cand: int, max_det: int) -> Dict[str, torch.Tensor]:
         key = (batch, h, w, max_cand, max_det)
-        if key not in self._scratch:
+        if key in self._scratch:
+            self._scratch[key] = self._scratch.pop(key)         # most recently used last
+        else:
+            while len(self._scratch) >= 8:                      # a service sees few distinct (batch, shape) keys; cap the rest
+                self._scratch.pop(next(iter(self._scratch)))
             dev = self._engine_for(h, w).device
             ws = int(self._lib.b2f_decode_nms_workspace(batch, max_cand))
             self._scratch[key] = dict(
@@ -193,10 +208,14 @@ class SCRFD:
             kpss = bufs["kps"][0, :n].cpu().numpy().reshape(-1, 5, 2)
         return det, kpss
 
-    def detect_batch(self, frames, max_num=0, metric="max", max_cand: int = 4096, max_det: Optional[int] = None):
+    def detect_batch(self, frames, max_num=0, metric="max", max_cand: int = 4096, max_det: Optional[int] = None,
+                     copy: bool = True):
         """Batched detect over same-sized frames.  frames: [B,H,W,3] uint8 (numpy or cuda tensor).
         Returns device tensors (det [B,max_det,5], kps [B,max_det,5,2], counts [B,4]); row b holds
-        counts[b,0] valid detections.  counts[b,3] != 0 flags a candidate / detection overflow."""
+        counts[b,0] valid detections.  counts[b,3] != 0 flags a candidate / detection overflow.
+        The kernels write into scratch tensors kept per (batch, shape): by default the three results are copied out
+        under the model lock and belong to the caller (the reference's callers share one model between threads,
+        duplicate.py:1954); `copy=False` returns the scratch views, valid until the next call on this model."""
         with self._lock:
             if isinstance(frames, np.ndarray):
                 frames = torch.from_numpy(np.ascontiguousarray(frames)).cuda(non_blocking=True)
@@ -210,6 +229,8 @@ class SCRFD:
                 max_det = max_num if max_num > 0 else max_cand
             bufs = self._decode(outs, b, height, width, [np.float32(det_scale)] * b, [[h, w]] * b, self.conf_thres,
                                 np.float32(self.iou_thres), max_num, metric, max_cand, max_det)
+            if copy:
+                return bufs["det"].clone(), bufs["kps"].clone().view(b, max_det, 5, 2), bufs["counts"].clone()
             return bufs["det"], bufs["kps"].view(b, max_det, 5, 2), bufs["counts"]
 
     def nms(self, dets, iou_thres):

@@ -4,6 +4,9 @@ import sys
 import numpy as np
 import pytest
 
+# the five .onnx files cannot be downloaded offline: the tests opt in to seeded random weights of the same architectures
+os.environ.setdefault("B2F_SYNTHETIC_WEIGHTS", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:

@@ -139,3 +139,20 @@ def test_stem_form_weights_equal_patch_gemm():
     x8[:, :3] = x
     got = torch.nn.functional.conv2d(x8, w33, None, stride, 1).reshape(2, cout_p, -1)
     assert torch.allclose(got, want, atol=1e-5)
+
+
+def test_missing_model_file_raises_unless_synthetic_weights_are_opted_in(monkeypatch):
+    """reference models/scrfd.py:59-68: a wrong weights path fails at construction, it does not run on random weights"""
+    import pytest
+    from scrfd_arcface_facerecognition_b200.scrfd import load_graph
+    monkeypatch.delenv("B2F_SYNTHETIC_WEIGHTS", raising=False)
+    with pytest.raises(FileNotFoundError):
+        load_graph("weights/det_10g.onnx")
+    with pytest.raises(FileNotFoundError):
+        load_graph("weights/not_a_model.onnx")
+    monkeypatch.setenv("B2F_SYNTHETIC_WEIGHTS", "1")
+    with pytest.warns(RuntimeWarning, match="RANDOM weights"):
+        g = load_graph("weights/det_500m.onnx")
+    assert len(g.outputs) == 9
+    with pytest.raises(FileNotFoundError):
+        load_graph("weights/not_a_model.onnx")

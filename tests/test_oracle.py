@@ -228,3 +228,20 @@ def test_fake_qdrant_semantics():
     assert c.get_collection("x").points_count == 2
     c.delete("x", fakes.FilterSelector(fakes.Filter()))
     assert c.get_collection("x").points_count == 0 and c.search("x", [1, 0, 0, 0], limit=3) == []
+
+
+def test_port_equals_reference_run_on_headline_detector():
+    """bench.py's CPU arm on the GPU box is the restated port (no reference tree there): on SCRFD-10G it must return
+    exactly what the reference's own detect() returned here (tests/golden/headline_outputs.npz)."""
+    import os
+    from oracle.torch_exec import TorchGraph
+    from scrfd_arcface_facerecognition_b200 import archs
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "headline_outputs.npz")))
+    tg = TorchGraph(archs.build_arch("scrfd_10g"))
+    for tag, seed, hw, max_num, metric in (("10g_640_all", 72, (640, 640), 0, "max"), ("10g_1080p_max16", 70, (1080, 1920), 16, "max")):
+        img = inputs.frame(seed, *hw)
+        canvas, ds = restate.letterbox_u8(img, 640, 640)
+        out = tg.run(restate.blob_from_bgr(canvas, 1 / 128, 127.5))
+        det, kps = restate.scrfd_postprocess([out[n] for n in tg.output_names], 640, 640, ds, 0.5, 0.4, max_num, metric, hw)
+        np.testing.assert_array_equal(det, g[f"detect_{tag}_det"])
+        np.testing.assert_array_equal(kps, g[f"detect_{tag}_kps"])
