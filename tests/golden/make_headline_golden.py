@@ -37,6 +37,38 @@ def detect_cases():
     ]
 
 
+class _Tap:
+    """Records what the reference's own `session.run` returned during detect() (models/scrfd.py:83): the raw head tensors
+    are the ground truth for the network's numerical error, independent of which near-tied anchor wins the NMS."""
+
+    def __init__(self, session):
+        self.session, self.last = session, None
+
+    def run(self, names, feed):
+        self.last = self.session.run(names, feed)
+        return self.last
+
+    def __getattr__(self, name):
+        return getattr(self.session, name)
+
+
+CAND_FLOOR = 0.3        # anchors whose reference score reaches this are stored (a few hundred per frame)
+
+
+def candidates(heads):
+    """global anchor index (level base + pixel * 2 + anchor), score, bbox [4], kps [10] (stride units) of every anchor with
+    score >= CAND_FLOOR, from the nine reference outputs (three strides x score / bbox / kps)."""
+    idx, sc, bb, kp = [], [], [], []
+    base = 0
+    for lvl in range(3):
+        s, b, k = heads[lvl].reshape(-1), heads[lvl + 3].reshape(-1, 4), heads[lvl + 6].reshape(-1, 10)
+        sel = np.nonzero(s >= CAND_FLOOR)[0]
+        idx.append(sel + base), sc.append(s[sel]), bb.append(b[sel]), kp.append(k[sel])
+        base += len(s)
+    return (np.concatenate(idx).astype(np.int64), np.concatenate(sc).astype(np.float32),
+            np.concatenate(bb).astype(np.float32), np.concatenate(kp).astype(np.float32))
+
+
 def main():
     ref = ref_loader.load()
     if ref is None:
@@ -46,10 +78,15 @@ def main():
     for tag, weight, seed, (h, w), max_num, metric in detect_cases():
         if weight not in dets:
             dets[weight] = ref.SCRFD(os.path.join("weights", weight))
+            dets[weight].session = _Tap(dets[weight].session)
         img = inputs.frame(seed, h, w)
         d, k = dets[weight].detect(img, max_num=max_num, metric=metric)
         gold[f"detect_{tag}_det"], gold[f"detect_{tag}_kps"] = d, k
-        print(f"detect_{tag}: {len(d)} detections, score range {d[:, 4].min() if len(d) else 0:.3f}..{d[:, 4].max() if len(d) else 0:.3f}")
+        ci, cs, cb, ck = candidates(dets[weight].session.last)
+        gold[f"detect_{tag}_cand_anchor"], gold[f"detect_{tag}_cand_score"] = ci, cs
+        gold[f"detect_{tag}_cand_bbox"], gold[f"detect_{tag}_cand_kps"] = cb, ck
+        print(f"detect_{tag}: {len(d)} detections, score range {d[:, 4].min() if len(d) else 0:.3f}..{d[:, 4].max() if len(d) else 0:.3f}, "
+              f"{len(ci)} anchors >= {CAND_FLOOR}")
 
     rec = ref.ArcFace(os.path.join("weights", "w600k_r50.onnx"))
     # (a) the embeddings of the reference's own detections on a 1080p frame (main.py:130-134: detect, then one call per face)
