@@ -192,6 +192,12 @@ int b2f_match_merge(const float* part_score, const int* part_idx, int q, int n_c
                     const float* g_f32, int dim, int topk, float threshold, int strict_gt, long long idx_base,
                     float* out_score /*[Q][topk]*/, long long* out_idx /*[Q][topk], -1 = none*/, void* stream);
 
+/* sharded top-1 exchange (gallery rows split over GPUs, per-shard results merged by score desc, index asc):
+ * (score, global index >= 0 or -1) <-> one int64 key whose signed maximum over the shards IS that merge, so the
+ * exchange is a single MAX all-reduce of Q keys (an empty slot is INT64_MIN).  Global indices must be < 2^32 - 1. */
+int b2f_topk_pack_keys(const float* score, const long long* idx, long long n, long long* keys, void* stream);
+int b2f_topk_unpack_keys(const long long* keys, long long n, float* score, long long* idx, void* stream);
+
 /* ---- a21: duplicate merge (greedy one-hop leader clustering in ascending id order) ------------------
  * replaces the N Qdrant searches of reference duplicate.py:2726-2797. */
 int b2f_pairs_threshold(const void* emb16, int n, int dim, int dtype, int row_begin, int row_end, float threshold,

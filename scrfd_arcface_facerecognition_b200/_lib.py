@@ -137,6 +137,8 @@ SIGNATURES = {
     "b2f_match_partial": [_vp, _i, _vp, _ll, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "b2f_match_splits": [_ll, _i],
     "b2f_match_merge": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _f, _i, _ll, _vp, _vp, _vp],
+    "b2f_topk_pack_keys": [_vp, _vp, _ll, _vp, _vp],
+    "b2f_topk_unpack_keys": [_vp, _ll, _vp, _vp, _vp],
     "b2f_pairs_threshold": [_vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _ll, _vp, _vp],
     "b2f_cluster_resolve": [_vp, _ll, _i, _vp, _vp],
     "b2f_debug_tma_probe": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp],
@@ -204,6 +206,46 @@ def call(name: str, *args):
     if name not in _NO_STATUS:
         check(rc, name)
     return rc
+
+
+# ---- per-call timing of the memory-bound kernels (bench.py's HBM rooflines) ---------------------------------------
+_spans = None
+
+
+class span:
+    """`with _lib.span(name, algorithmic_bytes):` around one C-ABI call.  Does nothing unless `profile_begin()` armed it;
+    then it brackets the call with CUDA events on the current stream (never used under graph capture)."""
+
+    def __init__(self, name: str, nbytes: float):
+        self.name, self.nbytes = name, float(nbytes)
+
+    def __enter__(self):
+        if _spans is not None:
+            import torch
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _spans is not None:
+            self.e1.record()
+            _spans.append((self.name, self.nbytes, self.e0, self.e1))
+        return False
+
+
+def profile_begin() -> None:
+    global _spans
+    _spans = []
+
+
+def profile_end():
+    """[(name, algorithmic bytes, milliseconds)] of the spans recorded since profile_begin()."""
+    global _spans
+    import torch
+    torch.cuda.synchronize()
+    out = [(n, b, e0.elapsed_time(e1)) for n, b, e0, e1 in (_spans or [])]
+    _spans = None
+    return out
 
 
 def launch_count() -> int:

@@ -83,6 +83,31 @@ class ArcFace:
                                                         self._engine.dtype, stream_ptr()), "b2f_preprocess")
             return self._embed_loaded(n).cpu().numpy()
 
+    def embed_crops(self, crops_u8: torch.Tensor, copy: bool = True) -> torch.Tensor:
+        """[F,112,112,3] uint8 BGR aligned crops ON THE DEVICE -> [F,512] f32 (device): `get_feat` (reference
+        models/arcface.py:39-52) without the host round trip, for crops that are already aligned (BASELINE config 3).
+        blobFromImages' (x - 127.5) * float32(1/127.5), BGR->RGB and the layout change are one kernel writing the
+        16-byte-pixel image the first convolution reads; results alias the engine's buffers unless `copy`."""
+        with self._lock:
+            f = int(crops_u8.shape[0])
+            w, h = self.input_size
+            assert tuple(crops_u8.shape[1:]) == (h, w, 3) and crops_u8.dtype == torch.uint8 and crops_u8.is_cuda
+            stem8 = self._engine.stem8(f) if (self.fuse_stem and self.stem8) else None
+            if stem8 is not None:
+                with _lib.span("letterbox_kernel<crop8>", f * (w * h * 3 + w * h * 16)):
+                    _lib.check(self._lib.b2f_preprocess(crops_u8.data_ptr(), f, h, w, w, h, w, h, float(self.input_mean),
+                                                        self._scale, stem8[0].data_ptr(), 8, self._engine.dtype,
+                                                        stream_ptr()), "b2f_preprocess")
+                stem8[1]()
+                out = self._engine.run(f, start=2)[self.output_names[0]].reshape(f, -1)
+            else:
+                x = self._engine.input_buffer(f)
+                _lib.check(self._lib.b2f_preprocess(crops_u8.data_ptr(), f, h, w, w, h, w, h, float(self.input_mean),
+                                                    self._scale, x.data_ptr(), 4, self._engine.dtype, stream_ptr()),
+                           "b2f_preprocess")
+                out = self._embed_loaded(f)
+            return out.clone() if copy else out
+
     def __call__(self, image, kps):
         """Align by the five landmarks and embed: (512,) float32, not L2-normalised
         (reference models/arcface.py:54-57)."""
@@ -116,10 +141,12 @@ class ArcFace:
         if stem8 is not None:
             # aligned crop kept as an 8-channel image (16 B per pixel); the first convolution reads it tap by tap
             if w == h == 112:                       # one CTA per face, crop staged in shared memory
-                _lib.check(self._lib.b2f_norm_crop_image8(
-                    frames.data_ptr(), frames.shape[1], frames.shape[2], frame_idx.data_ptr(),
-                    kps.reshape(f, 10).contiguous().data_ptr(), f, w, float(self.input_mean), self._scale,
-                    stem8[0].data_ptr(), self._engine.dtype, stream_ptr()), "b2f_norm_crop_image8")
+                # algorithmic bytes: a source region the size of the crop (lower bound) + the 16-byte-pixel crop written
+                with _lib.span("warp_patches_kernel<image8>", f * (w * h * 3 + w * h * 16)):
+                    _lib.check(self._lib.b2f_norm_crop_image8(
+                        frames.data_ptr(), frames.shape[1], frames.shape[2], frame_idx.data_ptr(),
+                        kps.reshape(f, 10).contiguous().data_ptr(), f, w, float(self.input_mean), self._scale,
+                        stem8[0].data_ptr(), self._engine.dtype, stream_ptr()), "b2f_norm_crop_image8")
             else:
                 _lib.check(self._lib.b2f_norm_crop(
                     frames.data_ptr(), frames.shape[1], frames.shape[2], frame_idx.data_ptr(),

@@ -606,6 +606,49 @@ extern "C" int b2f_match_merge(const float* part_score, const int* part_idx, int
   return 0;
 }
 
+// ---- sharded top-1 exchange: (score, global index) <-> one 64-bit key whose SIGNED integer maximum is the winner by
+// (score descending, index ascending), so the cross-shard merge of reference-order top-1 lists is a single MAX reduction
+// (int64 is what both NCCL and gloo reduce; the top bit is flipped so signed order == the unsigned order of the fields)
+__device__ __forceinline__ uint32_t score_order_bits(float s) {
+  const uint32_t u = __float_as_uint(s);
+  return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__global__ void topk_pack_keys_kernel(const float* __restrict__ score, const long long* __restrict__ idx, long long n,
+                                      unsigned long long* __restrict__ keys) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long g = idx[i];
+  const unsigned long long k = g < 0 ? 0ull : (((unsigned long long)score_order_bits(score[i]) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)g));
+  keys[i] = k ^ 0x8000000000000000ull;
+}
+__global__ void topk_unpack_keys_kernel(const unsigned long long* __restrict__ keys, long long n, float* __restrict__ score,
+                                        long long* __restrict__ idx) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long k = keys[i] ^ 0x8000000000000000ull;
+  if (k == 0ull) {
+    score[i] = 0.f, idx[i] = -1;
+    return;
+  }
+  const uint32_t ob = (uint32_t)(k >> 32);
+  score[i] = __uint_as_float(ob ^ ((ob >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+  idx[i] = (long long)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+}
+extern "C" int b2f_topk_pack_keys(const float* score, const long long* idx, long long n, long long* keys, void* stream) {
+  if (n <= 0) return 0;
+  topk_pack_keys_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(score, idx, n, reinterpret_cast<unsigned long long*>(keys));
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int b2f_topk_unpack_keys(const long long* keys, long long n, float* score, long long* idx, void* stream) {
+  if (n <= 0) return 0;
+  topk_unpack_keys_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(keys), n, score, idx);
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
+
 // leader[] doubles as output; workspace (3 ints per node + 1) is carved from the tail of `leader`'s
 // caller-provided scratch: state = leader + n, blocked = leader + 2n, flag = leader + 3n.
 extern "C" int b2f_cluster_resolve(const long long* pairs, long long n_pairs, int n, int* leader, void* stream_) {

@@ -68,6 +68,49 @@ def exchange_shard_topk(s: torch.Tensor, i: torch.Tensor, k: int, world_size: in
     return merge_shard_topk(gs, gi, k)
 
 
+def pack_top1_keys(s: torch.Tensor, i: torch.Tensor) -> torch.Tensor:
+    """(score f32, global index i64 or -1) -> int64 keys whose signed maximum is the winner by (score desc, index asc):
+    high word = the score's IEEE bits made monotone, low word = 0xFFFFFFFF - index, top bit flipped; empty = INT64_MIN.
+    CUDA tensors go through `b2f_topk_pack_keys`; host tensors (gloo tests of the exchange logic) use the same
+    arithmetic in torch."""
+    s, i = s.reshape(-1).contiguous(), i.reshape(-1).contiguous()
+    if s.is_cuda:
+        keys = torch.empty(s.shape[0], dtype=torch.int64, device=s.device)
+        _lib.check(_lib.lib().b2f_topk_pack_keys(s.data_ptr(), i.data_ptr(), s.shape[0], keys.data_ptr(), stream_ptr()),
+                   "b2f_topk_pack_keys")
+        return keys
+    u = s.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    ob = torch.where(u >> 31 != 0, u ^ 0xFFFFFFFF, u ^ 0x80000000)
+    key = ((ob - 0x80000000) << 32) | (0xFFFFFFFF - i.clamp(min=0))          # subtracting 2^31 from the high word == flipping bit 63
+    return torch.where(i < 0, torch.full_like(key, torch.iinfo(torch.int64).min), key)
+
+
+def unpack_top1_keys(keys: torch.Tensor):
+    if keys.is_cuda:
+        s = torch.empty(keys.shape[0], dtype=torch.float32, device=keys.device)
+        i = torch.empty(keys.shape[0], dtype=torch.int64, device=keys.device)
+        _lib.check(_lib.lib().b2f_topk_unpack_keys(keys.data_ptr(), keys.shape[0], s.data_ptr(), i.data_ptr(), stream_ptr()),
+                   "b2f_topk_unpack_keys")
+        return s, i
+    none = keys == torch.iinfo(torch.int64).min
+    ob = ((keys >> 32) + 0x80000000) & 0xFFFFFFFF
+    u = torch.where(ob >> 31 != 0, ob ^ 0x80000000, ob ^ 0xFFFFFFFF)
+    u = torch.where(u >= 0x80000000, u - (1 << 32), u).to(torch.int32)
+    s = torch.where(none, torch.zeros_like(u, dtype=torch.float32), u.view(torch.float32))
+    i = torch.where(none, torch.full_like(keys, -1), 0xFFFFFFFF - (keys & 0xFFFFFFFF))
+    return s, i
+
+
+def exchange_shard_top1(s: torch.Tensor, i: torch.Tensor, group=None):
+    """k = 1 exchange as ONE collective: every rank packs its shard's (score [Q] f32, global index [Q] i64, -1 = none)
+    into int64 keys (`pack_top1_keys`), the ranks MAX all-reduce the keys, and everyone unpacks the same answer --
+    identical to `merge_shard_top1` of the gathered lists.  No host synchronisation: legal inside a CUDA graph capture."""
+    import torch.distributed as dist
+    keys = pack_top1_keys(s, i)
+    dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=group)
+    return unpack_top1_keys(keys)
+
+
 class Gallery:
     def __init__(self, dim: int = 512, device: Optional[torch.device] = None, dtype: Optional[int] = None,
                  rank: int = 0, world_size: int = 1, process_group=None):
@@ -196,7 +239,26 @@ class Gallery:
         s, i = self.match_local(queries, k, threshold, strict)
         if self.world_size == 1:
             return s, i
+        if k == 1:
+            ms, mi = exchange_shard_top1(s, i, self.group)
+            return ms[:, None], mi[:, None]
         return exchange_shard_topk(s, i, k, self.world_size, self.group)
+
+    def match_sharded_queries(self, local_queries: torch.Tensor, threshold: float = float("-inf"), strict: bool = False):
+        """Top-1 for THIS rank's queries against the whole row-sharded gallery: all ranks all-gather their
+        raw fp32 queries (every rank must see every query), match them against their shard, exchange the per-shard
+        winners with one MAX all-reduce of packed keys, and keep their own slice.  Two collectives, no host sync.
+        Returns (scores [q_local,1], global indices [q_local,1])."""
+        if self.world_size == 1:
+            return self.match_local(local_queries, 1, threshold, strict)
+        import torch.distributed as dist
+        n = local_queries.shape[0]
+        allq = torch.empty((self.world_size * n, local_queries.shape[1]), dtype=local_queries.dtype, device=self.device)
+        dist.all_gather_into_tensor(allq, local_queries.contiguous(), group=self.group)
+        s, i = self.match_local(allq, 1, threshold, strict)
+        ms, mi = exchange_shard_top1(s, i, self.group)
+        lo = self.rank * n
+        return ms[lo:lo + n, None], mi[lo:lo + n, None]
 
     # ---- reference-shaped conveniences ------------------------------------------------------------
     def best_match(self, embedding: np.ndarray, similarity_thresh: float) -> Tuple[int, float]:

@@ -142,10 +142,12 @@ class SCRFD:
         b, h, w, _ = frames.shape
         patches = eng.patch_buffer(b) if self.fuse_stem else None
         if patches is not None:           # letterbox + blob + first-layer patch extraction in one pass
-            _lib.check(self._lib.b2f_preprocess_patches(frames.data_ptr(), b, h, w, new_w, new_h, in_w, in_h, patches[1],
-                                                        float(self.mean), float(np.float32(1.0 / self.std)),
-                                                        patches[0].data_ptr(), eng.dtype, stream_ptr()),
-                       "b2f_preprocess_patches")
+            # algorithmic bytes: the source pixels the resize needs + the patch tensor written
+            with _lib.span("letterbox_patches_kernel", b * (new_w * new_h * 3 + patches[0][0].numel() * 2)):
+                _lib.check(self._lib.b2f_preprocess_patches(
+                    frames.data_ptr(), b, h, w, new_w, new_h, in_w, in_h, patches[1], float(self.mean),
+                    float(np.float32(1.0 / self.std)), patches[0].data_ptr(), eng.dtype, stream_ptr()),
+                    "b2f_preprocess_patches")
             return eng.run(b, start=1)
         x = eng.input_buffer(b)
         _lib.check(self._lib.b2f_preprocess(frames.data_ptr(), b, h, w, new_w, new_h, in_w, in_h,
@@ -161,11 +163,13 @@ class SCRFD:
             bufs["hw"].copy_(torch.as_tensor(image_hw, dtype=torch.int32).reshape(batch, 2))
             bufs["_geom"] = geom
         lv = self._levels(outs)
-        _lib.check(self._lib.b2f_decode_nms(
-            C.byref(lv), batch, in_h, in_w, bufs["scale"].data_ptr(), bufs["hw"].data_ptr(), float(conf), float(iou),
-            int(max_num), 0 if metric == "max" else 1, max_cand, max_det, bufs["det"].data_ptr(),
-            bufs["kps"].data_ptr(), bufs["keep"].data_ptr(), bufs["counts"].data_ptr(), bufs["ws"].data_ptr(),
-            bufs["ws"].numel(), stream_ptr()), "b2f_decode_nms")
+        # algorithmic bytes: every anchor's score is read (bbox / kps only for candidates), the result rows are written
+        with _lib.span("decode_nms_kernel", batch * (self._total_anchors(in_h, in_w) * 4 + max_det * 60)):
+            _lib.check(self._lib.b2f_decode_nms(
+                C.byref(lv), batch, in_h, in_w, bufs["scale"].data_ptr(), bufs["hw"].data_ptr(), float(conf), float(iou),
+                int(max_num), 0 if metric == "max" else 1, max_cand, max_det, bufs["det"].data_ptr(),
+                bufs["kps"].data_ptr(), bufs["keep"].data_ptr(), bufs["counts"].data_ptr(), bufs["ws"].data_ptr(),
+                bufs["ws"].numel(), stream_ptr()), "b2f_decode_nms")
         return bufs
 
     # ------------------------------------------------------------------------------------------

@@ -90,3 +90,35 @@ def test_row_blocks_partition():
             covered[b:e] += 1
         assert (covered == 1).all()
     assert shard_range(10, 0, 4) == (0, 3) and shard_range(10, 3, 4) == (9, 10) and shard_range(2, 3, 4) == (2, 2)
+
+
+def _worker_top1(rank, world, port, s_np, i_np, ret):
+    from scrfd_arcface_facerecognition_b200.gallery import exchange_shard_top1
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ms, mi = exchange_shard_top1(torch.from_numpy(s_np[rank]), torch.from_numpy(i_np[rank]))   # ONE MAX all-reduce of packed keys
+    ret[rank] = (ms.numpy(), mi.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_top1_exchange_is_one_max_allreduce_of_packed_keys():
+    """the k = 1 collective of the sharded match (what bench.py runs under NCCL): packed (score, index) keys, MAX
+    all-reduce, unpack == merge by (score desc, index asc) of the gathered lists, on every rank"""
+    from scrfd_arcface_facerecognition_b200.gallery import merge_shard_top1, pack_top1_keys, unpack_top1_keys
+    g = torch.Generator().manual_seed(6)
+    p, q = 2, 300
+    s = torch.rand((p, q), generator=g) * 2 - 1
+    i = torch.randint(0, 1_000_000, (p, q), generator=g)
+    s[1, 10:60] = s[0, 10:60]                           # equal scores across shards: lowest index wins
+    i[torch.rand((p, q), generator=g) < 0.2] = -1       # empty slots never win
+    i[:, 100:110] = -1
+    i[0, 0], i[1, 0] = 2 ** 32 - 2, 5                   # the largest representable global index
+    rs, ri = unpack_top1_keys(pack_top1_keys(s[0], i[0]))
+    assert torch.equal(ri, i[0]) and torch.equal(rs[i[0] >= 0], s[0][i[0] >= 0])
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_top1, args=(p, _free_port(), s.numpy(), i.numpy(), ret), nprocs=p, join=True)
+    want_s, want_i = merge_shard_top1(s, i)
+    for rank in range(p):
+        np.testing.assert_array_equal(ret[rank][1], want_i.numpy())
+        np.testing.assert_array_equal(ret[rank][0], want_s.numpy())

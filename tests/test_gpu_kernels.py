@@ -697,6 +697,26 @@ def test_best_match_and_search_similar_semantics(lib, golden):
     np.testing.assert_allclose([r["similarity"] for r in res], sc, atol=2e-6)
 
 
+def test_top1_key_kernels_match_host_arithmetic(lib):
+    """b2f_topk_pack_keys / b2f_topk_unpack_keys == the torch restatement used by the gloo tests, bit for bit"""
+    from scrfd_arcface_facerecognition_b200.gallery import pack_top1_keys, unpack_top1_keys
+    g = torch.Generator().manual_seed(9)
+    s = torch.rand(5000, generator=g) * 2 - 1
+    i = torch.randint(0, 2 ** 32 - 1, (5000,), generator=g)
+    i[torch.rand(5000, generator=g) < 0.1] = -1
+    s[:3] = torch.tensor([0.0, 1.0, -1.0])
+    host = pack_top1_keys(s, i)
+    devk = pack_top1_keys(s.cuda(), i.cuda())
+    assert torch.equal(devk.cpu(), host)
+    ds, di = unpack_top1_keys(devk)
+    hs, hi = unpack_top1_keys(host)
+    assert torch.equal(di.cpu(), hi) and torch.equal(ds.cpu().view(torch.int32), hs.view(torch.int32))
+    assert torch.equal(hi, i) and torch.equal(hs[i >= 0], s[i >= 0]) and (hs[i < 0] == 0).all()
+    order = torch.argsort(host)                        # key order == (score asc, index desc)
+    so, io = s[order][i[order] >= 0], i[order][i[order] >= 0]
+    assert ((so[1:] > so[:-1]) | ((so[1:] == so[:-1]) & (io[1:] < io[:-1]))).all()
+
+
 @pytest.mark.parametrize("centres,members", [(50, 4), (700, 3)])
 def test_duplicate_merge_matches_oracle(lib, centres, members):
     from scrfd_arcface_facerecognition_b200.gallery import Gallery
