@@ -185,7 +185,15 @@ int b2f_cosine_pairs(const float* a, const float* b, int pairs, int dim, float* 
 int b2f_match_partial(const void* queries, int q, const void* gallery, long long g, int dim, int dtype,
                       const float* row_scale, const float* col_scale, int topk, int n_splits,
                       float* part_score, int* part_idx, void* stream);
+/* same, with `keep` <= topk candidates actually tracked per list (the lists keep their topk stride, unused slots are empty):
+ * a top-1 query only needs a short list for the exact re-score, and the list length is what the epilogue costs */
+int b2f_match_partial_keep(const void* queries, int q, const void* gallery, long long g, int dim, int dtype,
+                           const float* row_scale, const float* col_scale, int topk, int keep, int n_splits,
+                           float* part_score, int* part_idx, void* stream);
 int b2f_match_splits(long long g, int want);
+/* the n_splits b2f_match_partial should be called with for q queries against g gallery rows: ranges per query tile that
+ * keep every SM (pair) evenly busy.  part_* must then hold [q][2*n_splits][topk] entries. */
+int b2f_match_plan(int q, long long g);
 /* merge pass: exact fp32 re-score of the coarse candidates, sort (score desc, index asc), threshold.
  * q_f32 / g_f32 are unit-norm fp32 rows; idx_base is added to indices (gallery shard offset). */
 int b2f_match_merge(const float* part_score, const int* part_idx, int q, int n_cand, const float* q_f32,

@@ -14,7 +14,7 @@ from typing import List
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libb2f.so")
-SOURCES = ["core.cu", "postproc.cu", "aux_ops.cu", "umma_conv.cu", "conv_tile.cu"]
+SOURCES = ["core.cu", "postproc.cu", "aux_ops.cu", "umma_conv.cu", "conv_tile.cu", "match_pair.cu"]
 HEADERS = ["b2f_common.cuh", "umma_shared.cuh", os.path.join("..", "..", "include", "b2f.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -135,7 +135,9 @@ SIGNATURES = {
     "b2f_l2norm_rows": [_vp, _ll, _i, _vp, _vp, _i, _vp, _vp],
     "b2f_cosine_pairs": [_vp, _vp, _i, _i, _vp, _vp],
     "b2f_match_partial": [_vp, _i, _vp, _ll, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp],
+    "b2f_match_partial_keep": [_vp, _i, _vp, _ll, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "b2f_match_splits": [_ll, _i],
+    "b2f_match_plan": [_i, _ll],
     "b2f_match_merge": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _f, _i, _ll, _vp, _vp, _vp],
     "b2f_topk_pack_keys": [_vp, _vp, _ll, _vp, _vp],
     "b2f_topk_unpack_keys": [_vp, _ll, _vp, _vp, _vp],
@@ -144,7 +146,8 @@ SIGNATURES = {
     "b2f_debug_tma_probe": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp],
 }
 _RESTYPES = {"b2f_last_error": C.c_char_p, "b2f_launch_count": _ll, "b2f_decode_nms_workspace": _ll}
-_NO_STATUS = {"b2f_version", "b2f_last_error", "b2f_launch_count", "b2f_decode_nms_workspace", "b2f_match_splits"}
+_NO_STATUS = {"b2f_version", "b2f_last_error", "b2f_launch_count", "b2f_decode_nms_workspace", "b2f_match_splits",
+              "b2f_match_plan"}
 
 
 def declared_symbols() -> List[str]:

@@ -13,6 +13,7 @@ extern int g_persistent;
 extern int g_vhalo;
 extern int g_debug;
 extern int g_a_res;
+extern int g_match_pair;
 extern int g_tile_groups, g_tile_mt, g_tile_amode, g_tile_epi, g_tile_max_n, g_tile_cg2, g_tile_cg2_min_n, g_tile_pdl, g_tile_wide_res, g_tile_big_res, g_tile_reduce;
 }  // namespace b2f
 
@@ -64,6 +65,7 @@ extern "C" int b2f_set_tuning(int key, int value) {
   if (key == 14) { b2f::g_tile_wide_res = value; return 0; }
   if (key == 15) { b2f::g_tile_big_res = value; return 0; }
   if (key == 16) { b2f::g_tile_reduce = value; return 0; }
+  if (key == 17) { b2f::g_match_pair = value; return 0; }
   b2f_set_error("unknown tuning key %d", key);
   return 2;
 }

@@ -1169,13 +1169,35 @@ extern "C" int b2f_conv2d(const b2f_conv_desc* d, void* stream_) {
 }
 
 // partial top-k of Q x G cosine scores: queries [Q][D], gallery [G][D] (both fp16 or bf16, K-major)
+namespace b2f {
+int match_pair_topk(const void* queries, int q, const void* gallery, long long g, int dim, int dtype, int topk, int keep,
+                    int n_splits, float* part_score, int* part_idx, cudaStream_t stream);
+int match_pair_pairs(const void* emb16, int n, int dim, int dtype, int row_begin, int row_end, float thr_coarse, float thr_exact,
+                     const float* emb_f32, long long* pairs, long long max_pairs, unsigned long long* pair_count,
+                     cudaStream_t stream);
+}  // namespace b2f
+using b2f::match_pair_pairs;
+using b2f::match_pair_topk;
+
 extern "C" int b2f_match_partial(const void* queries, int q, const void* gallery, long long g, int dim, int dtype,
                                  const float* row_scale, const float* col_scale, int topk, int n_splits,
                                  float* part_score, int* part_idx, void* stream_) {
+  return b2f_match_partial_keep(queries, q, gallery, g, dim, dtype, row_scale, col_scale, topk, topk, n_splits, part_score,
+                                part_idx, stream_);
+}
+
+extern "C" int b2f_match_partial_keep(const void* queries, int q, const void* gallery, long long g, int dim, int dtype,
+                                      const float* row_scale, const float* col_scale, int topk, int keep, int n_splits,
+                                      float* part_score, int* part_idx, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B2F_REQUIRE(keep >= 1 && keep <= topk, "b2f_match_partial_keep: keep must be in [1, topk]");
   B2F_REQUIRE(topk >= 1 && topk <= kTopKMax, "b2f_match_partial: topk must be in [1,%d]", kTopKMax);
   B2F_REQUIRE(dim % 64 == 0, "b2f_match_partial: dim must be a multiple of 64");
   B2F_REQUIRE(q > 0 && g > 0 && n_splits >= 1, "b2f_match_partial: empty problem");
+  if (row_scale == nullptr && col_scale == nullptr) {       // more than 128 queries: persistent CTA pairs (match_pair.cu)
+    const int rc = match_pair_topk(queries, q, gallery, g, dim, dtype, topk, keep, n_splits, part_score, part_idx, stream);
+    if (rc != -1000) return rc;
+  }
   UmmaParams p;
   memset(&p, 0, sizeof(p));
   p.N = q, p.Ho = 1, p.Wo = 1, p.H = 1, p.W = 1;
@@ -1226,6 +1248,12 @@ extern "C" int b2f_pairs_threshold(const void* emb16, int n, int dim, int dtype,
   B2F_REQUIRE(dim % 64 == 0, "b2f_pairs_threshold: dim must be a multiple of 64");
   B2F_REQUIRE(0 <= row_begin && row_begin < row_end && row_end <= n, "b2f_pairs_threshold: bad row range");
   const int rows = row_end - row_begin;
+  {                                                           // more than 128 rows: persistent CTA pairs (match_pair.cu)
+    // the 16-bit coarse score may sit a little under the exact one: widen the gate, re-check in fp32
+    const int rc = match_pair_pairs(emb16, n, dim, dtype, row_begin, row_end, emb_f32 ? threshold - 0.02f : threshold, threshold,
+                                    emb_f32, pairs, max_pairs, pair_count, stream);
+    if (rc != -1000) return rc;
+  }
   UmmaParams p;
   memset(&p, 0, sizeof(p));
   p.N = rows, p.Ho = 1, p.Wo = 1, p.H = 1, p.W = 1;

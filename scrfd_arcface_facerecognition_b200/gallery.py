@@ -220,13 +220,16 @@ class Gallery:
             return (torch.zeros((q, k), dtype=torch.float32, device=self.device),
                     torch.full((q, k), -1, dtype=torch.int64, device=self.device))
         qf, qh = self._normalise(queries)
-        m_tiles = (q + 127) // 128
-        want = splits if splits is not None else max(1, (2 * 148 + m_tiles - 1) // m_tiles)
-        splits = int(self.lib.b2f_match_splits(g, want))
+        # gallery ranges per query tile: the library's plan for this (q, g), or the caller's request rounded to one that
+        # tiles the gallery evenly
+        splits = int(self.lib.b2f_match_plan(q, g)) if splits is None else int(self.lib.b2f_match_splits(g, splits))
         sc = self._scratch_for(q, splits)
-        _lib.check(self.lib.b2f_match_partial(qh.data_ptr(), q, self.h16.data_ptr(), g, self.dim, self.dtype, None,
-                                              None, KMAX, splits, sc["ps"].data_ptr(), sc["pi"].data_ptr(),
-                                              stream_ptr()), "b2f_match_partial")
+        # coarse lists are KMAX wide; only k + 2 candidates per list are tracked (two spare ones for the exact re-score to
+        # re-order what 16-bit operands may have swapped): the running list length is what the GEMM's epilogue costs
+        keep = min(k + 2, KMAX)
+        _lib.check(self.lib.b2f_match_partial_keep(qh.data_ptr(), q, self.h16.data_ptr(), g, self.dim, self.dtype, None,
+                                                   None, KMAX, keep, splits, sc["ps"].data_ptr(), sc["pi"].data_ptr(),
+                                                   stream_ptr()), "b2f_match_partial_keep")
         thr = float(threshold) if np.isfinite(threshold) else -3.0e38
         _lib.check(self.lib.b2f_match_merge(sc["ps"].data_ptr(), sc["pi"].data_ptr(), q, 2 * splits * KMAX,
                                             qf.data_ptr(), self.f32.data_ptr(), self.dim, KMAX, thr,

@@ -697,6 +697,43 @@ def test_best_match_and_search_similar_semantics(lib, golden):
     np.testing.assert_allclose([r["similarity"] for r in res], sc, atol=2e-6)
 
 
+@pytest.mark.parametrize("q,g,k", [(129, 5000, 1), (700, 70001, 5), (2048, 300_000, 1)])
+def test_pair_kernel_matches_first_generation_kernel(lib, q, g, k):
+    """match_pair_kernel (persistent CTA pairs, cta_group::2) against umma_conv_kernel<EPI_TOPK> on the same inputs:
+    identical identities AND identical scores (the exact fp32 re-score makes them bit-equal), ragged last tiles included"""
+    from scrfd_arcface_facerecognition_b200.gallery import Gallery
+    gen = torch.Generator(device="cuda").manual_seed(q)
+    gal = torch.randn((g, 512), generator=gen, device="cuda")
+    ids = torch.randint(0, g, (q,), generator=gen, device="cuda")
+    qs = gal[ids] + 0.9 * torch.randn((q, 512), generator=gen, device="cuda")
+    G = Gallery()
+    G.add(gal)
+    try:
+        _lib.call("b2f_set_tuning", 17, 0)
+        s0, i0 = (t.clone() for t in G.match(qs, k))
+        _lib.call("b2f_set_tuning", 17, 1)
+        s1, i1 = (t.clone() for t in G.match(qs, k))
+    finally:
+        _lib.call("b2f_set_tuning", 17, 1)
+    assert torch.equal(i1[:, 0], ids) and torch.equal(i0, i1) and torch.equal(s0, s1)
+
+
+def test_pair_kernel_pairs_match_first_generation_kernel(lib):
+    """thresholded all-pairs: same sorted pair list from both kernels, whole matrix and an unaligned row block"""
+    from scrfd_arcface_facerecognition_b200.gallery import Gallery
+    emb = inputs.clustered(31, 900, 3, noise=0.45)
+    G = Gallery()
+    G.add(emb)
+    out = {}
+    try:
+        for gen in (0, 1):
+            _lib.call("b2f_set_tuning", 17, gen)
+            out[gen] = (G.duplicate_pairs(0.8).clone(), G.duplicate_pairs(0.8, 333, 1900).clone())
+    finally:
+        _lib.call("b2f_set_tuning", 17, 1)
+    assert out[0][0].numel() > 1000 and torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+
+
 def test_top1_key_kernels_match_host_arithmetic(lib):
     """b2f_topk_pack_keys / b2f_topk_unpack_keys == the torch restatement used by the gloo tests, bit for bit"""
     from scrfd_arcface_facerecognition_b200.gallery import pack_top1_keys, unpack_top1_keys
