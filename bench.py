@@ -69,8 +69,9 @@ def parse_args():
     ap.add_argument("--rec", default="weights/w600k_r50.onnx")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--tail", default="overlap", choices=["overlap", "inline"],
-                    help="N > 1, config 2: run step i's sharded match on a side stream under step i+1's nets, or in line")
+    ap.add_argument("--tail", default="inline", choices=["overlap", "inline"],
+                    help="N > 1, config 2: run step i's sharded match in line (default; measured faster: the persistent kernels of the "
+                         "nets and of the match each want every SM) or on a side stream under step i+1's nets")
     ap.add_argument("--layer-report", default=None, help="write a per-launch table of the conv nets to this path")
     a = ap.parse_args()
     for k, v in DEFAULTS[a.config].items():
@@ -509,7 +510,7 @@ def workload_config(a, n_gpus):
             "rows": a.rows, "pairs": a.rows * (a.rows - 1) // 2,
             "l2_policy": f"inputs larger than L2: {a.rows * 512 * 2 / 1e6:.0f} MB fp16 + {a.rows * 512 * 4 / 1e6:.0f} MB fp32 rows",
             "parallelism": ("single GPU" if n_gpus == 1 else
-                            f"4096-row blocks of the upper triangle dealt cyclically to {n_gpus} ranks (embeddings replicated); "
+                            f"upper triangle block-partitioned into {n_gpus} equal-area row ranges, one per rank (embeddings replicated); "
                             "NCCL all_gather of pair lists; resolve replicated"),
             "weights": "n/a"}
 
@@ -966,8 +967,8 @@ def run_cluster(a):
     value = pairs_total / (ms_step / 1e3)
 
     # the pair GEMM alone (this rank's row blocks), device events, max over ranks
-    from scrfd_arcface_facerecognition_b200.gallery import row_blocks
-    mine = [(b, e) for r, b, e in row_blocks(n, world) if r == rank] if world > 1 else [(0, n)]
+    from scrfd_arcface_facerecognition_b200.gallery import triangle_range
+    mine = [triangle_range(n, rank, world)] if world > 1 else [(0, n)]
 
     def pairs_only():
         for b, e in mine:

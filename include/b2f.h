@@ -148,6 +148,11 @@ typedef struct b2f_conv_desc {
   const void* sc_in;
   const void* sc_weight;
   int sc_cin_p, sc_stride, sc_h, sc_w;
+  /* pool == 1: a 3x3 / stride 2 / pad 1 max-pool of the (ReLU'd, hence non-negative) result is fused into the epilogue:
+   * `out` is the POOLED map [n][(ho-1)/2+1][(wo-1)/2+1][cout_p]; every 8x16 conv tile max-reduces its 5x9 partial
+   * window maxima into it through TMA (the entry zeroes `out` first).  Needs a 3x3 / stride 1 / pad 1 convolution with
+   * act == RELU, a 16-bit output, cout_p % 32 == 0 and no residual (reference graph: Conv-Relu-MaxPool of the SCRFD stem). */
+  int pool;
 } b2f_conv_desc;
 int b2f_conv2d(const b2f_conv_desc* desc, void* stream);
 

@@ -100,7 +100,7 @@ class ConvDesc(C.Structure):
                 ("in_", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p), ("slope", C.c_void_p),
                 ("residual", C.c_void_p), ("out", C.c_void_p),
                 ("sc_in", C.c_void_p), ("sc_weight", C.c_void_p),
-                ("sc_cin_p", C.c_int), ("sc_stride", C.c_int), ("sc_h", C.c_int), ("sc_w", C.c_int)]
+                ("sc_cin_p", C.c_int), ("sc_stride", C.c_int), ("sc_h", C.c_int), ("sc_w", C.c_int), ("pool", C.c_int)]
 
 
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong

@@ -66,6 +66,7 @@ struct TileParams {
   int cg2;                  // 1: CTA pair (cluster of 2, tcgen05 cta_group::2): M = 256 over two SMs, each loads half of B
   int n_acc_log2, acc_stride;
   int groups;
+  int pool, pool_h, pool_w, off_pool;   // fused 3x3 / s2 / p1 max-pool: pooled map size, per-group pooled staging
   int res_reduce;   // residual == out and no activation: the epilogue reduce-adds into the output instead of loading it
   int is_bf16, debug;
   int epi_tma, res_smem, res_global, ochunk, n_sub, stg_bytes, stg_box_bytes, stg_bufs;
@@ -360,6 +361,137 @@ __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& 
       if (c.leader && !skip_store) {
         if (RES == 3) tma_reduce_add_4d(c.tmO, bufp, t.cbase + j * och, t.x0, t.y0, t.n0);
         else tma_store_4d(c.tmO, bufp, t.cbase + j * och, t.x0, t.y0, t.n0);
+        bulk_commit();
+      }
+    }
+  }
+  if (c.leader) bulk_wait_all();
+}
+
+// Epilogue with a fused 3x3 / stride 2 / pad 1 max-pool (tiles of 8 x 16 pixels, ReLU, no residual): a 32-channel slice
+// goes TMEM -> registers -> bias + ReLU -> swizzled staging tile as usual; then the group's 128 threads reduce it to the
+// 5 x 9 window maxima this tile contributes to (windows that straddle a tile edge are partial) and one TMA reduce-store
+// max-merges them into the zero-initialised pooled map -- ReLU outputs are >= 0, so 0 is the identity of the max.
+// The conv result itself never reaches HBM.
+constexpr int kPoolW = 5, kPoolH = 9, kPoolBufBytes = 3072;
+template <bool BF16>
+__device__ __forceinline__ uint4 max8(const uint4& a, const uint4& b) {
+  uint4 r;
+  if (BF16) {
+    const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&b);
+    __nv_bfloat162* z = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) z[i] = __hmax2(x[i], y[i]);
+  } else {
+    const __half2* x = reinterpret_cast<const __half2*>(&a);
+    const __half2* y = reinterpret_cast<const __half2*>(&b);
+    __half2* z = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) z[i] = __hmax2(x[i], y[i]);
+  }
+  return r;
+}
+template <bool BF16>
+__device__ __forceinline__ void epilogue_pool(const TileParams& p, const EpiCtx& c, uint8_t* pbuf) {
+  const int G = p.groups, n_sub = p.n_sub, group = c.group;
+  const int n_acc_mask = (1 << p.n_acc_log2) - 1;
+  const int m = c.q * 32 + c.lane;                     // pixel of the 8 x 16 tile: lx = m & 7, ly = m >> 3
+  const int NB = p.stg_bufs;
+  const int my_tiles = c.tiles_cta > group ? (c.tiles_cta - group + G - 1) / G : 0;
+  const uint32_t row_off = (uint32_t)m * 64u;
+  uint32_t off[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t o = row_off + (uint32_t)i * 16;
+    off[i] = o ^ (((o >> 7) & 3u) << 4);
+  }
+  const int stg_bytes = p.stg_bytes, cout_p = p.cout_p;
+  // pooling work of this thread: 45 windows x four 16-byte pieces = 180 items over 128 threads (item m, and m + 128 for
+  // the first 52).  An item is the maximum over the 3 x 3 window clipped to the tile: out-of-tile taps are replaced by
+  // a clipped neighbour (a duplicate does not change a maximum), so the nine loads are unconditional and independent.
+  // The byte offsets into the swizzled staging tile are fixed for full tiles and computed once.
+  auto window = [](int it, int rows_in, int cols_in, uint32_t (&po)[9]) -> bool {
+    const int pp = it >> 2, piece = it & 3;
+    const int pyl = pp / kPoolW, pxl = pp - pyl * kPoolW;
+    const int ylo = max(2 * pyl - 1, 0), yhi = min(2 * pyl + 1, rows_in - 1);
+    const int xlo = max(2 * pxl - 1, 0), xhi = min(2 * pxl + 1, cols_in - 1);
+    if (ylo > yhi || xlo > xhi) return false;                 // the window lies outside the image part of this tile
+    const int ys[3] = {ylo, min(ylo + 1, yhi), yhi}, xs[3] = {xlo, min(xlo + 1, xhi), xhi};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+        po[a * 3 + b] = (uint32_t)((ys[a] * 8 + xs[b]) * 64 + ((piece ^ ((xs[b] >> 1) & 3)) << 4));   // 64-byte swizzle
+    return true;
+  };
+  auto reduce9 = [](const uint8_t* bufp, const uint32_t (&po)[9]) -> uint4 {
+    uint4 v[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) v[i] = *reinterpret_cast<const uint4*>(bufp + po[i]);
+    const uint4 a = max8<BF16>(max8<BF16>(v[0], v[1]), max8<BF16>(v[2], v[3]));
+    const uint4 b = max8<BF16>(max8<BF16>(v[4], v[5]), max8<BF16>(v[6], v[7]));
+    return max8<BF16>(max8<BF16>(a, b), v[8]);
+  };
+  const bool second = m + 128 < kPoolW * kPoolH * 4;
+  uint32_t po0[9], po1[9];
+  window(m, 16, 8, po0);
+  if (second) window(m + 128, 16, 8, po1);
+  const uint32_t dst0 = (uint32_t)((m >> 2) * 64 + (m & 3) * 16), dst1 = (uint32_t)(((m + 128) >> 2) * 64 + (m & 3) * 16);
+  int k = 0;
+  for (int tl = 0; tl < my_tiles; ++tl) {
+    const int seq = group + tl * G;
+    const TileCoord t = tile_of(p, c.first, c.stride, c.rank, seq);
+    int cls = 0;
+    if (p.bias_classes == 9) {
+      const int ox = t.x0 + (m & 7), oy = t.y0 + (m >> 3);
+      const int iy = oy - 1, ix = ox - 1;
+      const int cy = iy < 0 ? 0 : (iy + 2 >= p.H ? 2 : 1);
+      const int cx = ix < 0 ? 0 : (ix + 2 >= p.W ? 2 : 1);
+      cls = cy * 3 + cx;
+    }
+    const float* bias_row = c.s_bias + cls * cout_p + t.cbase;
+    const int acc = seq & n_acc_mask;
+    const uint32_t ph = (uint32_t)(seq >> p.n_acc_log2) & 1u;
+    mbar_wait(&c.tfull[acc], ph);
+    tc_fence_after();
+    const uint32_t t_addr = c.tmem_base + ((uint32_t)(c.q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+    // rows / columns of the tile that exist in the image (a tile may overhang the right / bottom edge)
+    const int rows_in = min(16, p.Ho - t.y0), cols_in = min(8, p.Wo - t.x0);
+    const bool full = rows_in == 16 && cols_in == 8;
+    for (int j = 0; j < n_sub; ++j, ++k) {
+      uint8_t* bufp = c.stg + (size_t)(k % NB) * stg_bytes;
+      uint32_t r[32];
+      tmem_ld32(t_addr + (uint32_t)(j * 32), r);
+      tmem_ld_wait();
+      if (j == n_sub - 1) {                              // accumulator fully read: hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (c.lane == 0) mbar_arrive(&c.tempty[acc]);
+      }
+      const int cl = j * 32;
+      epi_slice16<1, BF16, 0>(r, bias_row + cl, nullptr, reinterpret_cast<uint4*>(bufp + off[0]),
+                              reinterpret_cast<uint4*>(bufp + off[1]), t.cbase + cl, 0, nullptr);
+      epi_slice16<1, BF16, 0>(r + 16, bias_row + cl + 16, nullptr, reinterpret_cast<uint4*>(bufp + off[2]),
+                              reinterpret_cast<uint4*>(bufp + off[3]), t.cbase + cl + 16, 0, nullptr);
+      if (c.leader) bulk_wait_read0();                   // the previous reduce-store has left the pooled buffer
+      bar_sync_named(1 + group, 128);                    // the slice is complete in shared memory
+      if (full) {
+        *reinterpret_cast<uint4*>(pbuf + dst0) = reduce9(bufp, po0);
+        if (second) *reinterpret_cast<uint4*>(pbuf + dst1) = reduce9(bufp, po1);
+      } else {                                           // edge tiles: clip the windows to the rows / columns that exist
+        uint32_t pe[9];
+        const bool ok0 = window(m, rows_in, cols_in, pe);
+        *reinterpret_cast<uint4*>(pbuf + dst0) = ok0 ? reduce9(bufp, pe) : make_uint4(0u, 0u, 0u, 0u);
+        if (second) {
+          const bool ok1 = window(m + 128, rows_in, cols_in, pe);
+          *reinterpret_cast<uint4*>(pbuf + dst1) = ok1 ? reduce9(bufp, pe) : make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      fence_proxy_async();
+      bar_sync_named(1 + group, 128);
+      if (c.leader && !(p.debug & 1)) {
+        tma_reduce_max_4d(c.tmO, pbuf, t.cbase + cl, t.x0 >> 1, t.y0 >> 1, t.n0);
         bulk_commit();
       }
     }
@@ -909,8 +1041,9 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       c.s_bias = s_bias, c.s_slope = s_slope, c.tmO = &tmO, c.tmR = &tmR;
       c.tiles_cta = tiles_cta, c.group = group, c.q = q, c.lane = lane, c.leader = leader;
       c.first = first, c.stride = stride_items, c.rank = cta_rank, c.peer_tempty = peer_tempty;
-      const int variant = p.res_reduce ? 24 + (p.is_bf16 ? 1 : 0)
-                                       : p.act * 6 + (p.is_bf16 ? 3 : 0) + (p.res_smem ? 1 : (p.res_global ? 2 : 0));
+      const int variant = p.pool ? 26 + (p.is_bf16 ? 1 : 0)
+                          : p.res_reduce ? 24 + (p.is_bf16 ? 1 : 0)
+                                         : p.act * 6 + (p.is_bf16 ? 3 : 0) + (p.res_smem ? 1 : (p.res_global ? 2 : 0));
 #define B2F_EPI_CASE(ACT)                                                   \
       case ACT * 6 + 0: epilogue_tma<ACT, false, 0, CG2>(p, c); break;             \
       case ACT * 6 + 1: epilogue_tma<ACT, false, 1, CG2>(p, c); break;             \
@@ -925,6 +1058,8 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         B2F_EPI_CASE(3)
         case 24: epilogue_tma<0, false, 3, CG2>(p, c); break;
         case 25: epilogue_tma<0, true, 3, CG2>(p, c); break;
+        case 26: if constexpr (!CG2) epilogue_pool<false>(p, c, smem + p.off_pool + group * kPoolBufBytes); break;
+        case 27: if constexpr (!CG2) epilogue_pool<true>(p, c, smem + p.off_pool + group * kPoolBufBytes); break;
         default: break;
       }
 #undef B2F_EPI_CASE
@@ -1047,7 +1182,15 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   if (stem8)
     B2F_REQUIRE(d->cin_p == 8 && d->kh == 3 && d->kw == 3 && n_tiles == 1 && d->sc_in == nullptr && d->residual == nullptr,
                 "b2f_conv2d: the 8-channel stem form needs a 3x3 kernel, cout_p <= %d and no residual / shortcut", g_max_block_n);
-  const bool pair_legal = g_tile_cg2 != 0 && p.block_n % 32 == 0 && !stem8;
+  p.pool = d->pool ? 1 : 0;
+  if (p.pool) {
+    B2F_REQUIRE(d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && d->act == 1 && d->residual == nullptr &&
+                    d->sc_in == nullptr && d->out_dtype == d->dtype && p.block_n % 32 == 0 && p.block_n <= 128 && !stem8,
+                "b2f_conv2d: the fused max-pool needs a 3x3 / stride 1 / pad 1 convolution with ReLU, a 16-bit output, "
+                "at most 128 channels per tile in multiples of 32, and no residual / shortcut");
+    p.pool_h = (Ho - 1) / 2 + 1, p.pool_w = (Wo - 1) / 2 + 1;
+  }
+  const bool pair_legal = g_tile_cg2 != 0 && p.block_n % 32 == 0 && !stem8 && !p.pool;
   p.cg2 = (pair_legal && (pair == 1 || (pair < 0 && g_tile_cg2 == 2))) ? 1 : 0;
   p.b_tile_bytes = round_up(p.block_n / (p.cg2 ? 2 : 1) * row_bytes, 1024);
   p.acc_stride = round_up(p.block_n, 32);
@@ -1091,7 +1234,8 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
     p.res_global = (res_eff == 1 && wide) ? 1 : 0;
   }
   const int tab_bytes = round_up((p.bias_classes + 1) * p.cout_p * 4, 256);
-  const int fixed = 1024 /*align*/ + 1024 /*barriers*/ + tab_bytes;
+  const int pool_bytes = p.pool ? kTGroups * kPoolBufBytes : 0;
+  const int fixed = 1024 /*align*/ + 1024 /*barriers*/ + tab_bytes + pool_bytes;
 
   // ---- choose A mode, tile geometry, weight sharing and epilogue groups with a per-tile cycle model -----------
   const double kFabric = 64.0;                               // L2 -> SM bytes per clock per SM the rings can pull (measured 50-65)
@@ -1120,7 +1264,8 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   for (int relax = 0; relax < 2 && best.cost < 0 && !stem8; ++relax) {      // forced knobs that cannot fit are dropped
   const int f_groups = relax ? 0 : g_tile_groups, f_mt = relax ? 0 : g_tile_mt;
   for (int mode = 0; mode <= (halo_ok ? 2 : 0); ++mode) {
-    if (g_tile_amode >= 0 && halo_ok && mode != g_tile_amode) continue;
+    if (g_tile_amode >= 0 && halo_ok && mode != g_tile_amode && !p.pool) continue;
+    if (p.pool && mode != 2) continue;                         // the pooling epilogue is written for 8 x 16 tiles
     for (int tw = (mode == 0 ? 0 : 8); tw <= (mode == 1 ? 128 : (mode == 2 ? 8 : 0)); tw = tw ? tw * 2 : 1) {
       int gw, gh, gn;
       if (mode == 0) pick_m_tile(n_plan, Ho, Wo, d->stride, &gw, &gh, &gn);
@@ -1238,7 +1383,8 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   p.off_stg = p.off_b + (p.b_resident ? b_all : p.stages_b * p.b_stride);
   p.off_bar = p.off_stg + (p.epi_tma ? p.groups * p.stg_bufs * p.stg_bytes : 0);
   p.off_tab = p.off_bar + 1024;
-  size_t smem = (size_t)p.off_tab + tab_bytes + 1024;
+  p.off_pool = p.off_tab + tab_bytes;
+  size_t smem = (size_t)p.off_pool + pool_bytes + 1024;
   B2F_REQUIRE(smem <= (size_t)kSmemMax, "conv tile kernel: %zu bytes of shared memory requested", smem);
   if (smem < 120 * 1024) smem = 120 * 1024;      // one CTA per SM: it owns all 512 TMEM columns
 
@@ -1289,7 +1435,19 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
     uint64_t str[3] = {(uint64_t)d->cout_p * 2, (uint64_t)Wo * d->cout_p * 2, (uint64_t)Ho * Wo * d->cout_p * 2};
     uint32_t box[4] = {(uint32_t)p.ochunk, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
     uint32_t es[4] = {1, 1, 1, 1};
-    int rc = make_tmap(&tmO, d->out, 4, dims, str, box, es, p.ochunk * 2, d->out_dtype == 1);
+    int rc = 0;
+    if (p.pool) {
+      B2F_REQUIRE(p.tw == 8 && p.th == 16 && p.tn == 1 && p.ochunk == 32, "conv tile kernel: fused max-pool needs 8 x 16 tiles");
+      uint64_t pdims[4] = {(uint64_t)d->cout_p, (uint64_t)p.pool_w, (uint64_t)p.pool_h, (uint64_t)d->n};
+      uint64_t pstr[3] = {(uint64_t)d->cout_p * 2, (uint64_t)p.pool_w * d->cout_p * 2, (uint64_t)p.pool_h * p.pool_w * d->cout_p * 2};
+      uint32_t pbox[4] = {32, (uint32_t)kPoolW, (uint32_t)kPoolH, 1};
+      rc = make_tmap(&tmO, d->out, 4, pdims, pstr, pbox, es, 0, d->out_dtype == 1);
+      if (rc) return rc;
+      // 0 is the identity of the max over ReLU outputs: the tiles' partial window maxima are max-reduced into the map
+      B2F_CHECK_CUDA(cudaMemsetAsync(d->out, 0, (size_t)d->n * p.pool_h * p.pool_w * d->cout_p * 2, stream));
+    } else {
+      rc = make_tmap(&tmO, d->out, 4, dims, str, box, es, p.ochunk * 2, d->out_dtype == 1);
+    }
     if (rc) return rc;
     if (p.res_smem) {
       rc = make_tmap(&tmR, d->residual, 4, dims, str, box, es, p.ochunk * 2, p.is_bf16);

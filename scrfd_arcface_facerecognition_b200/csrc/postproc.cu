@@ -310,20 +310,44 @@ __global__ void __launch_bounds__(1024, 1) decode_nms_kernel(DecodeParams p) {
   if (tid == 0) s_count = 0;
   __syncthreads();
 
-  // ---- A. threshold + compaction (order restored by the sort) ----------------------------------
-  // keys live in shared memory when they fit, else in the global workspace
+  // ---- A. threshold + ordered stream compaction (warp ballots + a block-level prefix per 1024-anchor sweep) ------
+  // Candidates take slots in ANCHOR ORDER, so when a frame has more than max_cand of them the ones kept are always the
+  // first max_cand by anchor index (deterministic; counts[b][3] flags the overflow).  The sort below restores the
+  // reference's visiting order.  Keys live in shared memory when they fit, else in the global workspace.
   uint64_t* keys = (p.cap2 <= kSmemKeys) ? smem_keys : keys_g;
-  for (int a = tid; a < total; a += nthreads) {
-    const int l = a < lvl_base[1] ? 0 : (a < lvl_base[2] ? 1 : 2);
-    const int local = a - lvl_base[l];
-    const size_t npix = (size_t)(lvl_cnt[l] >> 1);
-    const float sc = p.lv.score[l][((size_t)b * npix + (local >> 1)) * p.lv.score_ps[l] + (local & 1)];
-    if (sc >= p.conf) {
-      const int slot = atomicAdd(&s_count, 1);
-      if (slot < p.max_cand)
-        keys[slot] = (p.forward_mode ? 0ull : ((uint64_t)float_order_bits(sc) << 32)) |
-                     (uint64_t)(0xFFFFFFFFu - (uint32_t)a) | (p.forward_mode ? (1ull << 63) : 0ull);
+  {
+    const int lane_a = tid & 31, warp_a = tid >> 5, nwarps_a = nthreads >> 5;
+    int base = 0;
+    for (int a0 = 0; a0 < total; a0 += nthreads) {
+      const int a = a0 + tid;
+      bool cand = false;
+      float sc = 0.f;
+      if (a < total) {
+        const int l = a < lvl_base[1] ? 0 : (a < lvl_base[2] ? 1 : 2);
+        const int local = a - lvl_base[l];
+        const size_t npix = (size_t)(lvl_cnt[l] >> 1);
+        sc = p.lv.score[l][((size_t)b * npix + (local >> 1)) * p.lv.score_ps[l] + (local & 1)];
+        cand = sc >= p.conf;
+      }
+      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, cand);
+      if (lane_a == 0) word_prefix[warp_a] = __popc(bal);          // (word_prefix is free until stage E)
+      __syncthreads();
+      int before = 0, sweep = 0;
+      for (int w = 0; w < nwarps_a; ++w) {
+        const int c = word_prefix[w];
+        before += w < warp_a ? c : 0;
+        sweep += c;
+      }
+      if (cand) {
+        const int slot = base + before + __popc(bal & ((1u << lane_a) - 1u));
+        if (slot < p.max_cand)
+          keys[slot] = (p.forward_mode ? 0ull : ((uint64_t)float_order_bits(sc) << 32)) |
+                       (uint64_t)(0xFFFFFFFFu - (uint32_t)a) | (p.forward_mode ? (1ull << 63) : 0ull);
+      }
+      base += sweep;
+      __syncthreads();
     }
+    if (tid == 0) s_count = base;
   }
   __syncthreads();
   const int n_found = s_count;
@@ -369,8 +393,10 @@ __global__ void __launch_bounds__(1024, 1) decode_nms_kernel(DecodeParams p) {
       if (j > i && j < n) {
         const float4 bj = boxes[j];
         const float aj = __fmul_rn(__fadd_rn(__fsub_rn(bj.z, bj.x), 1.f), __fadd_rn(__fsub_rn(bj.w, bj.y), 1.f));
-        const float ww = fmaxf(0.f, __fadd_rn(__fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), 1.f));
-        const float hh = fmaxf(0.f, __fadd_rn(__fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)), 1.f));
+        // np.maximum(0.0, x) propagates a NaN x (fmaxf would drop it): keep it, so a NaN overlap suppresses as in numpy
+        const float w0 = __fadd_rn(__fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), 1.f);
+        const float h0 = __fadd_rn(__fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)), 1.f);
+        const float ww = w0 < 0.f ? 0.f : w0, hh = h0 < 0.f ? 0.f : h0;
         const float inter = __fmul_rn(ww, hh);
         const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter));
         suppress = !(ovr <= p.iou);  // NaN (0/0 on degenerate boxes) suppresses, as np.where(ovr <= thr) does
@@ -507,8 +533,9 @@ nms_kernel(const float* __restrict__ dets, int n, float iou, uint64_t* __restric
       if (j > i && j < n) {
         const float* dj = dets + 5 * (size_t)(keys[j] & 0xFFFFFFFFull);
         const float aj = __fmul_rn(__fadd_rn(__fsub_rn(dj[2], dj[0]), 1.f), __fadd_rn(__fsub_rn(dj[3], dj[1]), 1.f));
-        const float ww = fmaxf(0.f, __fadd_rn(__fsub_rn(fminf(bx2, dj[2]), fmaxf(bx1, dj[0])), 1.f));
-        const float hh = fmaxf(0.f, __fadd_rn(__fsub_rn(fminf(by2, dj[3]), fmaxf(by1, dj[1])), 1.f));
+        const float w0 = __fadd_rn(__fsub_rn(fminf(bx2, dj[2]), fmaxf(bx1, dj[0])), 1.f);
+        const float h0 = __fadd_rn(__fsub_rn(fminf(by2, dj[3]), fmaxf(by1, dj[1])), 1.f);
+        const float ww = w0 < 0.f ? 0.f : w0, hh = h0 < 0.f ? 0.f : h0;   // np.maximum(0.0, x) keeps a NaN x
         const float inter = __fmul_rn(ww, hh);
         const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter));
         suppress = !(ovr <= iou);

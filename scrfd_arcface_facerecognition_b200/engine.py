@@ -195,6 +195,7 @@ class NetEngine:
                 rs = self.plan.tensors[op.residual]
                 d.res_h, d.res_w = rs.h, rs.w
             d.force_kchunk = 0
+            d.pool = int(a.get("pool", 0))              # dst is then the 3x3 / s2 max-pooled map (b2f.h, `pool`)
             d.in_, d.weight, d.bias = src.data_ptr(), w["weight"].data_ptr(), w["bias"].data_ptr()
             d.slope = _ptr(w.get("slope"))
             d.residual = _ptr(res)

@@ -312,16 +312,18 @@ class Gallery:
 
     def merge_duplicates(self, threshold: float) -> np.ndarray:
         """leader[i] for every row (leader[i] == i for survivors), reference duplicate.py:2726-2797 semantics.
-        With world_size > 1 the upper-triangle row blocks are dealt cyclically to ranks and the pair
-        lists are exchanged with all_gather before the (cheap, order-dependent) resolve."""
+        With world_size > 1 the upper triangle is block-partitioned by rows -- equal-area row ranges, one per rank
+        (`triangle_range`) -- and the pair lists are exchanged with all_gather before the (cheap, order-dependent)
+        resolve, which every rank runs on the same sorted list."""
         n = len(self)
         if self.world_size == 1:
             pairs = self.duplicate_pairs(threshold)
         else:
             import torch.distributed as dist
-            blocks = row_blocks(n, self.world_size)
-            mine = [self.duplicate_pairs(threshold, b, e) for r, b, e in blocks if r == self.rank]
-            local = torch.cat(mine) if mine else torch.empty(0, dtype=torch.int64, device=self.device)
+            # one contiguous row range per rank, cut so that every rank owns the same AREA of the upper triangle
+            # (row i meets n - 1 - i columns): one launch per rank instead of one per 4096-row block
+            b, e = triangle_range(n, self.rank, self.world_size)
+            local = self.duplicate_pairs(threshold, b, e) if e > b else torch.empty(0, dtype=torch.int64, device=self.device)
             cnt = torch.tensor([local.numel()], dtype=torch.int64, device=self.device)
             cnts = [torch.zeros_like(cnt) for _ in range(self.world_size)]
             dist.all_gather(cnts, cnt, group=self.group)
@@ -416,6 +418,20 @@ def row_blocks(n: int, world_size: int, block: int = 4096) -> List[Tuple[int, in
     for bi, start in enumerate(range(0, n, block)):
         out.append((bi % world_size, start, min(start + block, n)))
     return out
+
+
+def triangle_range(n: int, rank: int, world_size: int, align: int = 256) -> Tuple[int, int]:
+    """[begin, end) rows of the all-pairs upper triangle owned by `rank`: row i is compared with the n - 1 - i rows
+    after it, so equal work means equal area, begin_r = n (1 - sqrt(1 - r / P)), rounded to the 256-row tiles of the
+    pair kernel.  The ranges of all ranks cover [0, n) exactly once."""
+    def cut(r: int) -> int:
+        if r <= 0:
+            return 0
+        if r >= world_size:
+            return n
+        x = n * (1.0 - (1.0 - r / world_size) ** 0.5)
+        return min(n, int(round(x / align)) * align)
+    return cut(rank), cut(rank + 1)
 
 
 def shard_range(total: int, rank: int, world_size: int) -> Tuple[int, int]:

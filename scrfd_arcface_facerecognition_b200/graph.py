@@ -16,6 +16,8 @@ folding arithmetic is unit-tested on the CPU box (tests/test_graph_compile.py).
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -504,6 +506,34 @@ def compile_graph(g: Graph, in_hw: Tuple[int, int], stem_im2col: bool = True, me
             main.residual, main.res_mode = None, 0
             ops.remove(proj)
 
+    # ---- fuse a 3x3 / stride 2 / pad 1 MaxPool into the ReLU convolution that feeds it -----------------------------
+    # (the SCRFD stem: Conv-Relu-MaxPool).  `b2f_conv2d` then max-reduces the tiles' window maxima straight into the
+    # pooled map (include/b2f.h, `pool`), so the full-resolution conv output -- the largest tensor of the detector --
+    # never reaches HBM and the separate pooling pass disappears.  B2F_FUSE_POOL=0 keeps the two ops.
+    if os.environ.get("B2F_FUSE_POOL", "1") != "0":
+        readers = {}
+        for op in ops:
+            for t in (op.src, op.residual, op.sc_src):
+                if t:
+                    readers[t] = readers.get(t, 0) + 1
+        by_dst = {op.dst: op for op in ops}
+        for pool in [o for o in ops if o.kind == "pool"]:
+            pa = pool.attrs
+            conv = by_dst.get(pool.src)
+            if (pa["mode"] != 0 or pa["k"] != 3 or pa["stride"] != 2 or pa["pad"] != 1 or conv is None or conv.kind != "conv"
+                    or conv.act != ACT_RELU or conv.residual or conv.sc_src or readers.get(conv.dst, 0) != 1
+                    or conv.dst in out_names or pool.dst in out_names):
+                continue
+            ca = conv.attrs
+            cout_p = conv.arrays["weight"].shape[1]
+            if (ca["kh"], ca["kw"], ca["stride"], ca["pad"]) != (3, 3, 1, 1) or cout_p % 32 != 0 or cout_p > 128:
+                continue
+            if (pa["ho"], pa["wo"]) != ((ca["ho"] - 1) // 2 + 1, (ca["wo"] - 1) // 2 + 1):
+                continue
+            conv.attrs.update(pool=1, pool_ho=pa["ho"], pool_wo=pa["wo"])
+            conv.dst, conv.order = pool.dst, max(conv.order, pool.order)
+            ops.remove(pool)
+
     # ---- topological order over fused ops ------------------------------------------------------------
     inp = g.real_inputs()[0].name
     produced_by = {op.dst: op for op in ops}
@@ -533,6 +563,8 @@ def compile_graph(g: Graph, in_hw: Tuple[int, int], stem_im2col: bool = True, me
         a = op.attrs
         if op.kind in ("conv", "dwconv", "stem"):
             c, h, w = a["cout"], a["ho"], a["wo"]
+            if a.get("pool"):
+                h, w = a["pool_ho"], a["pool_wo"]
         elif op.kind == "pool":
             c, h, w = a["c"], a["ho"], a["wo"]
         else:

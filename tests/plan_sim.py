@@ -78,6 +78,8 @@ def run_plan(plan: Plan, x_nchw: np.ndarray, quantize=None):
                 y = torch.cat([torch.sigmoid(y[:, :a["sig_hi"]]), y[:, a["sig_hi"]:]], dim=1)
             else:
                 y = _act(y, op.act, slope[:cout] if slope is not None else None)
+            if a.get("pool"):                                              # fused 3x3 / s2 / p1 max-pool (b2f.h, `pool`)
+                y = F.max_pool2d(qz(y), 3, 2, 1)
         elif op.kind == "pool":
             if a["mode"] == 0:
                 y = F.max_pool2d(x, a["k"], a["stride"], a["pad"])

@@ -89,6 +89,13 @@ def test_row_blocks_partition():
             assert 0 <= r < world
             covered[b:e] += 1
         assert (covered == 1).all()
+    from scrfd_arcface_facerecognition_b200.gallery import triangle_range
+    for n, world in ((200_000, 8), (12_000, 2), (300, 4), (5, 8)):
+        cuts = [triangle_range(n, r, world) for r in range(world)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == n and all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+        if n >= 100_000:                                   # equal areas of the upper triangle within the 256-row rounding (a few %)
+            area = [sum(n - 1 - i for i in range(b, e, 64)) for b, e in cuts]
+            assert max(area) <= 1.06 * min(area)
     assert shard_range(10, 0, 4) == (0, 3) and shard_range(10, 3, 4) == (9, 10) and shard_range(2, 3, 4) == (2, 2)
 
 

@@ -266,6 +266,41 @@ def test_conv2d_fused_projection_shortcut(lib, case):
         _lib.check(lib.b2f_set_tuning(11, 1))
 
 
+@pytest.mark.parametrize("case", [(2, 64, 64, 32, 64), (3, 320, 320, 32, 64), (2, 33, 47, 32, 32), (2, 50, 24, 64, 96), (1, 16, 8, 32, 128)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_conv2d_fused_maxpool(lib, case):
+    """3x3 ReLU convolution with the 3x3 / s2 / p1 max-pool fused into its epilogue (SCRFD stem, b2f.h `pool`): BIT-EXACT
+    against the same convolution followed by b2f_pool -- max is order-independent, so the TMA max-reduce of the tiles'
+    partial window maxima equals the separate pass, also for maps that tiles overhang (odd sizes) and for bf16"""
+    n, h, w, cin, cout = case
+    g = torch.Generator().manual_seed(sum(case))
+    for dtype, tdt in ((0, torch.float16), (1, torch.bfloat16)):
+        x = (torch.randn((n, h, w, cin), generator=g)).to(tdt).cuda()
+        wt = (torch.randn((9, cout, cin), generator=g) * (2.0 / (cin * 9)) ** 0.5).to(tdt).cuda()
+        bias = (torch.randn((1, cout), generator=g) * 0.1).cuda()
+        hp, wp = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        full = torch.empty((n, h, w, cout), dtype=tdt, device="cuda")
+        pooled = torch.full((n, hp, wp, cout), float("nan"), dtype=tdt, device="cuda")      # the entry must zero it itself
+        want = torch.empty((n, hp, wp, cout), dtype=tdt, device="cuda")
+
+        def desc(out, pool):
+            d = _lib.ConvDesc()
+            d.n, d.h, d.w, d.cin_p, d.ho, d.wo, d.cout_p = n, h, w, cin, h, w, cout
+            d.kh, d.kw, d.stride, d.pad = 3, 3, 1, 1
+            d.dtype, d.out_dtype, d.act, d.bias_classes = dtype, dtype, 1, 1
+            d.in_, d.weight, d.bias, d.out, d.pool = x.data_ptr(), wt.data_ptr(), bias.data_ptr(), out.data_ptr(), pool
+            return d
+        _lib.check(lib.b2f_conv2d(C.byref(desc(full, 0)), sp()), "b2f_conv2d")
+        _lib.check(lib.b2f_pool(full.data_ptr(), n, h, w, cout, 3, 2, 1, 0, hp, wp, dtype, want.data_ptr(), sp()), "b2f_pool")
+        for _ in range(2):                                       # twice: the second launch finds stale maxima in `out`
+            _lib.check(lib.b2f_conv2d(C.byref(desc(pooled, 1)), sp()), "b2f_conv2d")
+        torch.cuda.synchronize()
+        assert torch.equal(pooled.view(torch.int16), want.view(torch.int16)), f"dtype {dtype}"
+        ref = F.max_pool2d(torch.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(1, 2, 0).reshape(cout, cin, 3, 3),
+                                               bias[0], 1, 1)), 3, 2, 1).permute(0, 2, 3, 1)
+        assert (pooled.float() - ref).abs().max().item() <= (6e-3 if dtype == 0 else 4e-2) * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("case", [(2, 64, 64, 64, 64), (2, 48, 80, 96, 96), (1, 32, 32, 128, 128), (3, 24, 40, 32, 32),
                                   (2, 56, 56, 64, 128), (2, 20, 20, 224, 224), (1, 33, 47, 64, 32), (2, 40, 24, 80, 80)],
                          ids=lambda c: "x".join(map(str, c)))
@@ -589,6 +624,21 @@ def test_decode_nms_edge_cases(lib):
     heads = inputs.head_tensors(1, 320, 320, score_mu=0.0)
     det, kps, kidx, cnt = run_decode(lib, heads, 320, 320, np.float32(1.0), (320, 320), 0.5, 0.4, 0, "max", max_cand=64)
     assert cnt[1] > 64 and (cnt[3] & 1)
+    # ... and deterministic: the candidates kept are the first 64 in anchor order (ordered ballot compaction), i.e. the
+    # result equals the oracle run on the head tensors with every later candidate pushed under the threshold
+    clipped = [h.copy() for h in heads]
+    seen = 0
+    for lvl in range(3):
+        over = np.nonzero(clipped[lvl][:, 0] >= 0.5)[0]
+        drop = over[max(0, 64 - seen):]
+        clipped[lvl][drop, 0] = 0.0
+        seen += len(over)
+    want_d, want_k = restate.scrfd_postprocess(clipped, 320, 320, 1.0, 0.5, 0.4)
+    np.testing.assert_array_equal(det, want_d)
+    np.testing.assert_array_equal(kps, want_k)
+    for _ in range(3):
+        det2, kps2, _, _ = run_decode(lib, heads, 320, 320, np.float32(1.0), (320, 320), 0.5, 0.4, 0, "max", max_cand=64)
+        np.testing.assert_array_equal(det2, det)
     # degenerate boxes: 0/0 overlap is NaN and must suppress, as np.where(ovr <= thr) does
     heads = inputs.head_tensors(2, 320, 320, score_mu=-2.0)
     for i in (3, 4, 5):

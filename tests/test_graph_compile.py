@@ -37,7 +37,8 @@ def test_scrfd_500m_plan_matches_oracle():
 def test_scrfd_2p5g_plan_matches_oracle():
     plan = _check("scrfd_2.5g", (160, 192))
     assert sum(o.res_mode == 2 for o in plan.ops) == 2            # both top-down upsample-adds are fused
-    assert sum(o.kind == "pool" for o in plan.ops) == 4            # stem max-pool + three avg_down shortcuts
+    assert sum(o.kind == "pool" for o in plan.ops) == 3            # the three avg_down shortcuts
+    assert sum(o.attrs.get("pool", 0) for o in plan.ops) == 1      # the stem max-pool rides in its convolution's epilogue
 
 
 def test_arcface_mbf_plan_matches_oracle():

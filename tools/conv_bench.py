@@ -26,12 +26,14 @@ def main():
     bias = torch.randn((9 if bias9 else 1, cout_p), device="cuda")
     slope = torch.rand(cout_p, device="cuda")
     r = torch.randn((n, ho, wo, cout_p), device="cuda").half()
-    out = torch.empty((n, ho, wo, cout_p), device="cuda", dtype=torch.float16)
+    pool = int(os.environ.get("B2F_POOL", "0"))          # fused 3x3 / s2 / p1 max-pool: `out` is the pooled map
+    out = torch.empty((n, (ho - 1) // 2 + 1, (wo - 1) // 2 + 1, cout_p) if pool else (n, ho, wo, cout_p), device="cuda", dtype=torch.float16)
     d = _lib.ConvDesc()
     d.n, d.h, d.w, d.cin_p, d.ho, d.wo, d.cout_p = n, h, w, cin_p, ho, wo, cout_p
     d.kh, d.kw, d.stride, d.pad = k, k, stride, pad
     d.dtype, d.out_dtype, d.act, d.bias_classes = 0, 0, act, 9 if bias9 else 1
     d.in_, d.weight, d.bias, d.slope, d.out = x.data_ptr(), wt.data_ptr(), bias.data_ptr(), slope.data_ptr(), out.data_ptr()
+    d.pool = pool
     if res:
         d.residual, d.res_mode = r.data_ptr(), 1
     sp = torch.cuda.current_stream().cuda_stream
