@@ -84,57 +84,66 @@ def _bn_affine(g: Graph, node: Node) -> Tuple[np.ndarray, np.ndarray]:
     return s, beta - mean * s
 
 
+def _infer_one(init: Dict[str, np.ndarray], n: Node, shapes: Dict[str, Tuple[int, ...]]) -> None:
+    """(C, H, W) of node n's output from its inputs' shapes (batch dimension implicit)."""
+    a = n.attrs
+    t = n.op_type
+    if t == "Conv":
+        c, h, w = shapes[n.inputs[0]]
+        wt = init[n.inputs[1]]
+        p, s = a.get("pads", [0, 0, 0, 0]), a.get("strides", [1, 1])
+        shapes[n.outputs[0]] = (wt.shape[0], (h + p[0] + p[2] - wt.shape[2]) // s[0] + 1,
+                                (w + p[1] + p[3] - wt.shape[3]) // s[1] + 1)
+    elif t in ("MaxPool", "AveragePool"):
+        c, h, w = shapes[n.inputs[0]]
+        k, s, p = a["kernel_shape"], a.get("strides", [1, 1]), a.get("pads", [0, 0, 0, 0])
+        if a.get("ceil_mode", 0):
+            ho = -(-(h + p[0] + p[2] - k[0]) // s[0]) + 1
+            wo = -(-(w + p[1] + p[3] - k[1]) // s[1]) + 1
+        else:
+            ho = (h + p[0] + p[2] - k[0]) // s[0] + 1
+            wo = (w + p[1] + p[3] - k[1]) // s[1] + 1
+        shapes[n.outputs[0]] = (c, ho, wo)
+    elif t in ("Resize", "Upsample"):
+        c, h, w = shapes[n.inputs[0]]
+        sc = None
+        for nm in n.inputs[1:]:
+            if nm and nm in init and init[nm].size == 4:
+                sc = init[nm]
+        if sc is None:
+            raise NotImplementedError("Resize whose scales / sizes do not fold to constants is not supported")
+        if sc.dtype.kind == "f":
+            shapes[n.outputs[0]] = (c, int(h * float(sc.reshape(-1)[2])), int(w * float(sc.reshape(-1)[3])))
+        else:
+            shapes[n.outputs[0]] = (c, int(sc.reshape(-1)[2]), int(sc.reshape(-1)[3]))
+    elif t == "Flatten":
+        shapes[n.outputs[0]] = (int(np.prod(shapes[n.inputs[0]])),)
+    elif t == "Gemm":
+        wt = init[n.inputs[1]]
+        shapes[n.outputs[0]] = (wt.shape[0] if a.get("transB", 0) else wt.shape[1],)
+    elif t in ("Transpose", "Reshape"):
+        shapes[n.outputs[0]] = shapes[n.inputs[0]]
+    else:
+        src = [i for i in n.inputs if i in shapes]
+        if not src:
+            raise NotImplementedError(f"cannot infer shape for {t}")
+        shapes[n.outputs[0]] = shapes[src[0]]
+
+
 def _infer_shapes(g: Graph, in_hw: Tuple[int, int]) -> Dict[str, Tuple[int, ...]]:
     inp = g.real_inputs()[0]
     shapes: Dict[str, Tuple[int, ...]] = {inp.name: (3, in_hw[0], in_hw[1])}
     for n in g.nodes:
-        a = n.attrs
-        t = n.op_type
-        if t == "Conv":
-            c, h, w = shapes[n.inputs[0]]
-            wt = g.initializers[n.inputs[1]]
-            p, s = a.get("pads", [0, 0, 0, 0]), a.get("strides", [1, 1])
-            shapes[n.outputs[0]] = (wt.shape[0], (h + p[0] + p[2] - wt.shape[2]) // s[0] + 1,
-                                    (w + p[1] + p[3] - wt.shape[3]) // s[1] + 1)
-        elif t in ("MaxPool", "AveragePool"):
-            c, h, w = shapes[n.inputs[0]]
-            k, s, p = a["kernel_shape"], a.get("strides", [1, 1]), a.get("pads", [0, 0, 0, 0])
-            if a.get("ceil_mode", 0):
-                ho = -(-(h + p[0] + p[2] - k[0]) // s[0]) + 1
-                wo = -(-(w + p[1] + p[3] - k[1]) // s[1]) + 1
-            else:
-                ho = (h + p[0] + p[2] - k[0]) // s[0] + 1
-                wo = (w + p[1] + p[3] - k[1]) // s[1] + 1
-            shapes[n.outputs[0]] = (c, ho, wo)
-        elif t in ("Resize", "Upsample"):
-            c, h, w = shapes[n.inputs[0]]
-            sc = None
-            for nm in n.inputs[1:]:
-                if nm and nm in g.initializers and g.initializers[nm].size == 4:
-                    sc = g.initializers[nm]
-            if sc is None:
-                raise NotImplementedError("Resize without constant scales/sizes is not supported")
-            if sc.dtype.kind == "f":
-                shapes[n.outputs[0]] = (c, int(h * float(sc[2])), int(w * float(sc[3])))
-            else:
-                shapes[n.outputs[0]] = (c, int(sc[2]), int(sc[3]))
-        elif t == "Flatten":
-            shapes[n.outputs[0]] = (int(np.prod(shapes[n.inputs[0]])),)
-        elif t == "Gemm":
-            wt = g.initializers[n.inputs[1]]
-            shapes[n.outputs[0]] = (wt.shape[0] if a.get("transB", 0) else wt.shape[1],)
-        elif t in ("Transpose", "Reshape"):
-            shapes[n.outputs[0]] = shapes[n.inputs[0]]
-        else:
-            src = [i for i in n.inputs if i in shapes]
-            if not src:
-                raise NotImplementedError(f"cannot infer shape for {t}")
-            shapes[n.outputs[0]] = shapes[src[0]]
+        _infer_one(g.initializers, n, shapes)
     return shapes
 
 
 def compile_graph(g: Graph, in_hw: Tuple[int, int], stem_im2col: bool = True, merge_heads: bool = True,
                   fuse_shortcuts: bool = True) -> Plan:
+    # exporter glue first: Constant nodes and the Shape / Gather / Concat arithmetic around Resize and Reshape fold to
+    # initializers for the static input size (onnx_fold.py); what is left is the network
+    from .onnx_fold import fold_shape_glue
+    g = fold_shape_glue(g, in_hw)
     nodes = g.nodes
     init = g.initializers
     shapes = _infer_shapes(g, in_hw)

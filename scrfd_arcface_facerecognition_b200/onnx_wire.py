@@ -303,7 +303,7 @@ def load_model(path: str) -> Graph:
 # ---------------------------------------------------------------------------------------------
 
 def _ser_tensor(name: str, arr: np.ndarray) -> bytes:
-    arr = np.ascontiguousarray(arr)
+    arr = np.asarray(arr)                       # (np.ascontiguousarray would turn a 0-d scalar into shape (1,))
     out = bytearray()
     for d in arr.shape:
         out += _w_int(1, int(d))

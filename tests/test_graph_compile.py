@@ -157,3 +157,103 @@ def test_missing_model_file_raises_unless_synthetic_weights_are_opted_in(monkeyp
     assert len(g.outputs) == 9
     with pytest.raises(FileNotFoundError):
         load_graph("weights/not_a_model.onnx")
+
+
+def _with_export_glue(g):
+    """The same network written the way exporters write it for dynamic input sizes: every Resize computes its `sizes`
+    from Shape / Slice / Gather / Cast / Mul / Floor / Unsqueeze / Concat arithmetic, every head Reshape gets its shape
+    from a Concat of Constant nodes, and small initializers become Constant nodes."""
+    from scrfd_arcface_facerecognition_b200.onnx_wire import Graph, Node
+    nodes, init = [], dict(g.initializers)
+    k = [0]
+
+    def name(p):
+        k[0] += 1
+        return f"glue_{p}_{k[0]}"
+
+    def const(arr):
+        out = name("const")
+        nodes.append(Node("Constant", [], [out], {"value": np.asarray(arr)}))
+        return out
+    for ri, n in enumerate(g.nodes):
+        if n.op_type == "Resize":
+            x = n.inputs[0]
+            shp = name("shape")
+            nodes.append(Node("Shape", [x], [shp]))
+            if ri % 2 == 0:                                  # Slice + integer Mul form
+                hw, nc, hw2, sizes = name("hw"), name("nc"), name("hw2"), name("sizes")
+                nodes.append(Node("Slice", [shp, const(np.asarray([2], np.int64)), const(np.asarray([4], np.int64)),
+                                            const(np.asarray([0], np.int64))], [hw]))
+                nodes.append(Node("Slice", [shp, const(np.asarray([0], np.int64)), const(np.asarray([2], np.int64)),
+                                            const(np.asarray([0], np.int64))], [nc]))
+                nodes.append(Node("Mul", [hw, const(np.asarray([2, 2], np.int64))], [hw2]))
+                nodes.append(Node("Concat", [nc, hw2], [sizes], {"axis": 0}))
+            else:                                            # Gather + Cast + float Mul + Floor + Unsqueeze form
+                parts = []
+                for axis, mul in ((0, 1.0), (1, 1.0), (2, 2.0), (3, 2.0)):
+                    d, f, m, fl, i64, u = (name(s) for s in ("dim", "f", "mul", "floor", "i64", "unsq"))
+                    nodes.append(Node("Gather", [shp, const(np.asarray(axis, np.int64))], [d], {"axis": 0}))
+                    nodes.append(Node("Cast", [d], [f], {"to": 1}))
+                    nodes.append(Node("Mul", [f, const(np.asarray(mul, np.float32))], [m]))
+                    nodes.append(Node("Floor", [m], [fl]))
+                    nodes.append(Node("Cast", [fl], [i64], {"to": 7}))
+                    nodes.append(Node("Unsqueeze", [i64], [u], {"axes": [0]}))
+                    parts.append(u)
+                sizes = name("sizes")
+                nodes.append(Node("Concat", parts, [sizes], {"axis": 0}))
+            nodes.append(Node("Resize", [x, "", "", sizes], n.outputs, dict(n.attrs)))
+            for i in n.inputs[1:]:
+                init.pop(i, None)
+        elif n.op_type == "Reshape":
+            tgt = init.pop(n.inputs[1])
+            shape = name("shape")
+            nodes.append(Node("Concat", [const(tgt[:1]), const(tgt[1:])], [shape], {"axis": 0}))
+            nodes.append(Node("Reshape", [n.inputs[0], shape], n.outputs, dict(n.attrs)))
+        else:
+            nodes.append(n)
+    return Graph(nodes, init, g.inputs, g.outputs, g.name)
+
+
+def test_exporter_shape_glue_is_constant_folded(tmp_path):
+    """reference models/scrfd.py:52-68 loads whatever the exporter wrote; onnxruntime folds the shape arithmetic at
+    session creation.  Here: a detector with Shape/Slice/Gather/Cast/Mul/Floor/Unsqueeze/Concat glue in front of every
+    Resize, Concat-of-Constant shapes on the head Reshapes and unfused BatchNormalization, through the protobuf
+    writer / reader, the folding pass and the compiler -- against the node-by-node oracle on the ORIGINAL graph."""
+    from scrfd_arcface_facerecognition_b200.onnx_fold import fold_shape_glue
+    hw = (160, 192)
+    g = archs.build_arch("scrfd_2.5g")
+    glued = _with_export_glue(g)
+    assert sum(n.op_type == "Shape" for n in glued.nodes) == 2 and sum(n.op_type == "Constant" for n in glued.nodes) > 20
+    path = tmp_path / "det_glue.onnx"
+    onnx_wire.save_model(glued, str(path))
+    loaded = onnx_wire.load_model(str(path))
+    assert [n.op_type for n in loaded.nodes] == [n.op_type for n in glued.nodes]
+    folded = fold_shape_glue(loaded, hw)
+    left = {n.op_type for n in folded.nodes}
+    assert not left & {"Shape", "Gather", "Slice", "Concat", "Cast", "Floor", "Unsqueeze", "Constant"}, left
+    for n in folded.nodes:
+        if n.op_type == "Resize":
+            sizes = folded.initializers[n.inputs[3]]
+            assert sizes.dtype == np.int64 and sizes.shape == (4,) and sizes[0] == 1
+    x = restate.blob_from_bgr(inputs.frame(50, hw[0], hw[1])[None], 1 / 128, 127.5)
+    ref = TorchGraph(g).run(x)
+    plan = graph.compile_graph(loaded, hw)
+    assert sum(o.res_mode == 2 for o in plan.ops) == 2                 # both upsample-adds still fuse into their convolutions
+    out = plan_sim.run_plan(plan, x)
+    glue_ref = TorchGraph(loaded).run(x)                               # the oracle executes the glue node by node
+    for name, r in ref.items():
+        np.testing.assert_allclose(out[name].reshape(r.shape), r, rtol=0, atol=2e-5 * max(1.0, np.abs(r).max()))
+        np.testing.assert_array_equal(glue_ref[name], r)
+
+
+def test_data_dependent_shape_ops_are_rejected():
+    """a Gather over activations is not glue: it must not be folded away silently"""
+    from scrfd_arcface_facerecognition_b200.onnx_wire import Node
+    g = archs.build_arch("scrfd_500m")
+    first = g.nodes[0].outputs[0]
+    g.nodes.insert(1, Node("Gather", [first, "idx"], ["gathered"], {"axis": 1}))
+    g.initializers["idx"] = np.asarray([0], np.int64)
+    for n in g.nodes[2:]:
+        n.inputs[:] = ["gathered" if i == first else i for i in n.inputs]
+    with pytest.raises((NotImplementedError, KeyError, RuntimeError)):
+        graph.compile_graph(g, (160, 160))
