@@ -195,6 +195,13 @@ int b2f_match_partial(const void* queries, int q, const void* gallery, long long
 int b2f_match_partial_keep(const void* queries, int q, const void* gallery, long long g, int dim, int dtype,
                            const float* row_scale, const float* col_scale, int topk, int keep, int n_splits,
                            float* part_score, int* part_idx, void* stream);
+/* prefix ("causal") variant: query row i, whose global index is causal_base + i, is matched only against the gallery rows
+ * before it -- the online clustering loop's "best earlier person" (reference duplicate.py:1853-1855) for all rows at once */
+int b2f_match_partial_causal(const void* queries, int q, const void* gallery, long long g, int dim, int dtype, int topk,
+                             int keep, int n_splits, long long causal_base, float* part_score, int* part_idx, void* stream);
+/* exact fp32 scores of one unit query against all stored unit rows (a Qdrant search with k = every row, reference
+ * duplicate.py:2757-2766): out[r] = <rows[r], query> */
+int b2f_rows_dot(const float* rows, long long n, int dim, const float* query, float* out, void* stream);
 int b2f_match_splits(long long g, int want);
 /* the n_splits b2f_match_partial should be called with for q queries against g gallery rows: ranges per query tile that
  * keep every SM (pair) evenly busy.  part_* must then hold [q][2*n_splits][topk] entries. */

@@ -136,6 +136,8 @@ SIGNATURES = {
     "b2f_cosine_pairs": [_vp, _vp, _i, _i, _vp, _vp],
     "b2f_match_partial": [_vp, _i, _vp, _ll, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "b2f_match_partial_keep": [_vp, _i, _vp, _ll, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "b2f_match_partial_causal": [_vp, _i, _vp, _ll, _i, _i, _i, _i, _i, _ll, _vp, _vp, _vp],
+    "b2f_rows_dot": [_vp, _ll, _i, _vp, _vp, _vp],
     "b2f_match_splits": [_ll, _i],
     "b2f_match_plan": [_i, _ll],
     "b2f_match_merge": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _f, _i, _ll, _vp, _vp, _vp],

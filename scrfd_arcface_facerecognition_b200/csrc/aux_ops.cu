@@ -586,6 +586,26 @@ extern "C" int b2f_l2norm_rows(const float* x, long long rows, int dim, float* o
   return 0;
 }
 
+// one unit query against every stored unit row: out[r] = <rows[r], query>, a warp per row (HBM-bound: rows * dim * 4 bytes)
+__global__ void __launch_bounds__(256)
+rows_dot_kernel(const float* __restrict__ rows, long long n, int dim, const float* __restrict__ query, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  const float* pr = rows + (size_t)row * dim;
+  float acc = 0.f;
+  for (int i = lane; i < dim; i += 32) acc = fmaf(pr[i], __ldg(query + i), acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc;
+}
+extern "C" int b2f_rows_dot(const float* rows, long long n, int dim, const float* query, float* out, void* stream) {
+  if (n <= 0) return 0;
+  rows_dot_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, n, dim, query, out);
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int b2f_cosine_pairs(const float* a, const float* b, int pairs, int dim, float* out, void* stream) {
   if (pairs <= 0) return 0;
   cosine_pairs_kernel<<<(pairs * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a, b, pairs, dim, out);

@@ -43,6 +43,8 @@ struct MatchPairParams {
   int m_pairs, n_tiles, splits, items;
   int is_bf16;
   // MP_TOPK
+  int causal;               // 1: query row i only sees gallery rows with index < causal_base + i (a prefix search)
+  long long causal_base;
   int topk;
   float* part_score;        // [q][splits][2 column halves][topk]
   int* part_idx;
@@ -78,12 +80,16 @@ __device__ __forceinline__ void item_range(const MatchPairParams& p, int it, int
     m_pair = it / p.splits;
     split = it - m_pair * p.splits;
   }
-  int first = 0;
+  int first = 0, last = p.n_tiles;
   if (EPI == MP_PAIRS) first = min((p.row_begin + m_pair * 256) / 256, p.n_tiles);
-  const int span = p.n_tiles - first;
+  if (EPI == MP_TOPK && p.causal) {      // tiles past the last column any row of this pair tile may see are skipped
+    const long long hi = p.causal_base + (long long)m_pair * 256 + 255;          // largest limit among the tile's rows
+    last = (int)min((long long)p.n_tiles, hi <= 0 ? 0ll : (hi - 1) / 256 + 1);
+  }
+  const int span = max(last - first, 0);
   const int per = (span + p.splits - 1) / p.splits;
-  nt_begin = min(first + split * per, p.n_tiles);
-  nt_end = min(nt_begin + per, p.n_tiles);
+  nt_begin = min(first + split * per, last);
+  nt_end = min(nt_begin + per, last);
 }
 
 // running top-K of one query row (one thread) over the gallery tiles of an item, K a compile-time list length.
@@ -99,13 +105,15 @@ __device__ __forceinline__ void topk_item(const MatchPairParams& p, uint32_t tme
 #pragma unroll
   for (int k = 0; k < K; ++k) best_s[k] = -INFINITY, best_i[k] = -1;
   float worst = -INFINITY;
+  // columns this row may see: the whole gallery, or (causal) only the rows before its own global index
+  const long long lim = p.causal ? max(0ll, min(p.g, p.causal_base + (long long)on)) : p.g;
   for (int nt = nt_begin; nt < nt_end; ++nt, ++t) {
     const int acc = t & 1;
     mbar_wait(&tfull[acc], (uint32_t)(t >> 1) & 1u);
     tc_fence_after();
     const uint32_t t_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * 256);
     const long long cbase = (long long)nt * 256;
-    const bool full_tile = cbase + 256 <= p.g;
+    const bool full_tile = cbase + 256 <= lim;
 #pragma unroll 1
     for (int c0 = c_begin; c0 < c_begin + 128; c0 += 32) {
       uint32_t r[32];
@@ -113,10 +121,10 @@ __device__ __forceinline__ void topk_item(const MatchPairParams& p, uint32_t tme
       tmem_ld32(t_addr + (uint32_t)c0, r);
       tmem_ld_wait();
       const int g0 = (int)cbase + c0;
-      if (!full_tile) {                           // ragged last tile: columns past the gallery can never win
+      if (!full_tile) {                           // ragged last tile / the causal limit: columns past it can never win
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (g0 + i >= p.g) r[i] = 0xff800000u;  // -inf
+          if (g0 + i >= lim) r[i] = 0xff800000u;  // -inf
       }
       float gm[4];
 #pragma unroll
@@ -464,8 +472,8 @@ constexpr int kPairDeclined = -1000;
 // registers is that long, which is what the epilogue costs -- a top-1 query with a re-score margin of two extra
 // candidates keeps 3, a top-5 search keeps all 8
 int match_pair_topk(const void* queries, int q, const void* gallery, long long g, int dim, int dtype, int topk, int keep,
-                    int n_splits, float* part_score, int* part_idx, cudaStream_t stream) {
-  if (!g_match_pair || q <= 128 || dim % 64 != 0 || (dim / 64 + kMpStages) * kMpTile + 1280 > 227 * 1024) return kPairDeclined;
+                    int n_splits, float* part_score, int* part_idx, cudaStream_t stream, int causal, long long causal_base) {
+  if (((!g_match_pair || q <= 128) && !causal) || dim % 64 != 0 || (dim / 64 + kMpStages) * kMpTile + 1280 > 227 * 1024) return kPairDeclined;
   MatchPairParams p;
   memset(&p, 0, sizeof(p));
   p.q = q, p.g = g, p.kchunks = dim / 64, p.is_bf16 = dtype == 1;
@@ -474,6 +482,7 @@ int match_pair_topk(const void* queries, int q, const void* gallery, long long g
   if ((p.n_tiles + per - 1) / per != n_splits) return kPairDeclined;     // the caller's partial buffers assume n_splits ranges
   p.splits = n_splits, p.items = p.m_pairs * n_splits;
   p.topk = topk, p.part_score = part_score, p.part_idx = part_idx;
+  p.causal = causal ? 1 : 0, p.causal_base = causal_base;
   CUtensorMap tmA, tmB;
   int rc = make_maps(&tmA, &tmB, queries, q, gallery, g, dim, p.is_bf16);
   if (rc) return rc;

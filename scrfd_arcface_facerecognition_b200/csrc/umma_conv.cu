@@ -1171,7 +1171,7 @@ extern "C" int b2f_conv2d(const b2f_conv_desc* d, void* stream_) {
 // partial top-k of Q x G cosine scores: queries [Q][D], gallery [G][D] (both fp16 or bf16, K-major)
 namespace b2f {
 int match_pair_topk(const void* queries, int q, const void* gallery, long long g, int dim, int dtype, int topk, int keep,
-                    int n_splits, float* part_score, int* part_idx, cudaStream_t stream);
+                    int n_splits, float* part_score, int* part_idx, cudaStream_t stream, int causal, long long causal_base);
 int match_pair_pairs(const void* emb16, int n, int dim, int dtype, int row_begin, int row_end, float thr_coarse, float thr_exact,
                      const float* emb_f32, long long* pairs, long long max_pairs, unsigned long long* pair_count,
                      cudaStream_t stream);
@@ -1195,7 +1195,7 @@ extern "C" int b2f_match_partial_keep(const void* queries, int q, const void* ga
   B2F_REQUIRE(dim % 64 == 0, "b2f_match_partial: dim must be a multiple of 64");
   B2F_REQUIRE(q > 0 && g > 0 && n_splits >= 1, "b2f_match_partial: empty problem");
   if (row_scale == nullptr && col_scale == nullptr) {       // more than 128 queries: persistent CTA pairs (match_pair.cu)
-    const int rc = match_pair_topk(queries, q, gallery, g, dim, dtype, topk, keep, n_splits, part_score, part_idx, stream);
+    const int rc = match_pair_topk(queries, q, gallery, g, dim, dtype, topk, keep, n_splits, part_score, part_idx, stream, 0, 0);
     if (rc != -1000) return rc;
   }
   UmmaParams p;
@@ -1239,6 +1239,19 @@ extern "C" int b2f_match_partial_keep(const void* queries, int q, const void* ga
   return launch_umma<EPI_TOPK>(tmA, tmB, p, m_tiles, grid_y, stream);
 }
 
+
+// prefix search: query row i (global index causal_base + i) against the gallery rows BEFORE it only -- the online loop's
+// "best earlier person" (reference duplicate.py:1853-1855) for a whole batch of rows in one tensor-core pass
+extern "C" int b2f_match_partial_causal(const void* queries, int q, const void* gallery, long long g, int dim, int dtype,
+                                        int topk, int keep, int n_splits, long long causal_base, float* part_score,
+                                        int* part_idx, void* stream_) {
+  B2F_REQUIRE(keep >= 1 && keep <= topk && topk <= kTopKMax, "b2f_match_partial_causal: need 1 <= keep <= topk <= %d", kTopKMax);
+  B2F_REQUIRE(q > 0 && g > 0 && n_splits >= 1 && dim % 64 == 0, "b2f_match_partial_causal: bad problem size");
+  const int rc = match_pair_topk(queries, q, gallery, g, dim, dtype, topk, keep, n_splits, part_score, part_idx,
+                                 reinterpret_cast<cudaStream_t>(stream_), 1, causal_base);
+  B2F_REQUIRE(rc != -1000, "b2f_match_partial_causal: n_splits %d does not tile the gallery evenly (use b2f_match_plan)", n_splits);
+  return rc;
+}
 
 // all-pairs cosine >= threshold among unit rows: rows [row_begin,row_end) against every row j > i
 extern "C" int b2f_pairs_threshold(const void* emb16, int n, int dim, int dtype, int row_begin, int row_end,

@@ -210,9 +210,11 @@ class Gallery:
         return self._scratch[key]
 
     def match_local(self, queries: torch.Tensor, k: int = 1, threshold: float = float("-inf"),
-                    strict: bool = False, splits: Optional[int] = None):
+                    strict: bool = False, splits: Optional[int] = None, causal_base: Optional[int] = None):
         """Top-k of this shard for raw (un-normalised) fp32 queries [Q,dim] on the device.
-        Returns (scores [Q,k] f32, global indices [Q,k] int64 with -1 for empty slots)."""
+        Returns (scores [Q,k] f32, global indices [Q,k] int64 with -1 for empty slots).
+        `causal_base`: query i is matched only against the rows before local row causal_base + i (a prefix search: the
+        "best earlier person" of the online loop, reference duplicate.py:1853-1855, for all rows in one pass)."""
         assert 1 <= k <= KMAX
         q = int(queries.shape[0])
         g = len(self)
@@ -222,14 +224,22 @@ class Gallery:
         qf, qh = self._normalise(queries)
         # gallery ranges per query tile: the library's plan for this (q, g), or the caller's request rounded to one that
         # tiles the gallery evenly
-        splits = int(self.lib.b2f_match_plan(q, g)) if splits is None else int(self.lib.b2f_match_splits(g, splits))
+        if causal_base is not None:
+            splits = 1                                   # (the causal limit already shortens every item's gallery range)
+        else:
+            splits = int(self.lib.b2f_match_plan(q, g)) if splits is None else int(self.lib.b2f_match_splits(g, splits))
         sc = self._scratch_for(q, splits)
         # coarse lists are KMAX wide; only k + 2 candidates per list are tracked (two spare ones for the exact re-score to
         # re-order what 16-bit operands may have swapped): the running list length is what the GEMM's epilogue costs
         keep = min(k + 2, KMAX)
-        _lib.check(self.lib.b2f_match_partial_keep(qh.data_ptr(), q, self.h16.data_ptr(), g, self.dim, self.dtype, None,
-                                                   None, KMAX, keep, splits, sc["ps"].data_ptr(), sc["pi"].data_ptr(),
-                                                   stream_ptr()), "b2f_match_partial_keep")
+        if causal_base is None:
+            _lib.check(self.lib.b2f_match_partial_keep(qh.data_ptr(), q, self.h16.data_ptr(), g, self.dim, self.dtype, None,
+                                                       None, KMAX, keep, splits, sc["ps"].data_ptr(), sc["pi"].data_ptr(),
+                                                       stream_ptr()), "b2f_match_partial_keep")
+        else:
+            _lib.check(self.lib.b2f_match_partial_causal(qh.data_ptr(), q, self.h16.data_ptr(), g, self.dim, self.dtype,
+                                                         KMAX, keep, splits, int(causal_base), sc["ps"].data_ptr(),
+                                                         sc["pi"].data_ptr(), stream_ptr()), "b2f_match_partial_causal")
         thr = float(threshold) if np.isfinite(threshold) else -3.0e38
         _lib.check(self.lib.b2f_match_merge(sc["ps"].data_ptr(), sc["pi"].data_ptr(), q, 2 * splits * KMAX,
                                             qf.data_ptr(), self.f32.data_ptr(), self.dim, KMAX, thr,
@@ -377,26 +387,22 @@ class Gallery:
         """The cosine each online decision was taken on, as the reference records it per visit
         (duplicate.py:1854-1855 `search_results[0]['similarity'] if search_results else 0.0`): a joining row's similarity
         to its person, a founding row's best similarity to the persons founded before it (0 when none reaches
-        `search_threshold`, 0 for the first).  Exact fp32 dots of the stored unit rows; the founder-vs-founder maxima
-        are a bookkeeping statistic for the result files, computed block-wise with a plain matmul."""
+        `search_threshold`, 1.0 for the very first person).  Exact fp32 dots of the stored unit rows; the
+        founder-vs-earlier-founder maxima come from one causal pass of the match kernel (`match_local(causal_base=0)`)."""
         n = len(self)
         label_t = torch.as_tensor(np.asarray(label, np.int64), device=self.device)
         rows = torch.arange(n, device=self.device)
         sim = (self.f32 * self.f32[label_t.clamp(min=0)]).sum(dim=1)
         sim[label_t < 0] = 0.0                                                      # skipped as duplicate images
         founders = rows[label_t == rows]
-        fm = self.f32[founders]
         best = torch.zeros(len(founders), dtype=torch.float32, device=self.device)
-        block = 4096
-        for start in range(0, len(founders), block):
-            stop = min(start + block, len(founders))
-            if stop <= 1:
-                continue
-            s = fm[start:stop] @ fm[:stop].T                                       # [rows of this block, earlier founders]
-            earlier = torch.arange(stop, device=self.device)[None, :] < torch.arange(start, stop, device=self.device)[:, None]
-            s = torch.where(earlier & (s >= search_threshold), s, torch.full_like(s, -1.0e30))
-            m = s.max(dim=1).values
-            best[start:stop] = torch.where(m > -1.0e29, m, torch.zeros_like(m))
+        if len(founders) > 1:
+            # founder i against the founders before it: one causal (prefix) top-1 pass of the tcgen05 match kernel over a
+            # scratch gallery of the founders' unit rows, exact fp32 re-score of the winner included
+            scratch = Gallery(self.dim, self.device, self.dtype)
+            scratch.add(self.f32[founders])
+            s, i = scratch.match_local(scratch.f32, 1, float(search_threshold), causal_base=0)
+            best = torch.where(i[:, 0] >= 0, s[:, 0], torch.zeros_like(s[:, 0])).clone()
         if len(founders):
             best[0] = 1.0                                                           # first person: duplicate.py:1826
         sim[founders] = best

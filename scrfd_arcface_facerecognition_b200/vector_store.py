@@ -16,6 +16,8 @@ from typing import Any, Dict, List, Optional
 import numpy as np
 import torch
 
+from . import _lib
+from .engine import stream_ptr
 from .gallery import KMAX, Gallery
 
 __all__ = ["QdrantManager", "GalleryManager"]
@@ -100,8 +102,10 @@ class GalleryManager:
         if len(g) == 0:
             return []
         qn = torch.from_numpy(q).to(g.device)
-        qn = qn / qn.norm().clamp_min(1e-30)
-        scores = g.f32 @ qn
+        qn = (qn / qn.norm().clamp_min(1e-30)).contiguous()
+        scores = torch.empty(len(g), dtype=torch.float32, device=g.device)
+        _lib.check(g.lib.b2f_rows_dot(g.f32.data_ptr(), len(g), g.dim, qn.data_ptr(), scores.data_ptr(), stream_ptr()),
+                   "b2f_rows_dot")
         order = torch.argsort(scores, descending=True, stable=True)[:k]
         out = []
         for row, sc in zip(order.tolist(), scores[order].tolist()):

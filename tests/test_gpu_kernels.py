@@ -784,6 +784,46 @@ def test_pair_kernel_pairs_match_first_generation_kernel(lib):
     assert out[0][0].numel() > 1000 and torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
 
 
+@pytest.mark.parametrize("n", [2, 130, 700, 5000])
+def test_causal_match_is_a_prefix_search(lib, n):
+    """b2f_match_partial_causal: row i against the rows BEFORE it only (the online loop's best earlier person,
+    reference duplicate.py:1853-1855, for all rows in one pass) == the sequential numpy prefix scan"""
+    from scrfd_arcface_facerecognition_b200.gallery import Gallery
+    emb = inputs.clustered(40 + n, n // 3 + 1, 3, noise=0.5)[:n]
+    assert len(emb) == n
+    G = Gallery()
+    G.add(emb)
+    s, i = G.match_local(G.f32, 1, 0.3, causal_base=0)
+    s, i = s[:, 0].cpu().numpy(), i[:, 0].cpu().numpy()
+    u = restate.normalize_rows(emb).astype(np.float64)
+    sims = np.tril(u @ u.T, -1) + np.triu(np.full((n, n), -2.0))             # only j < i
+    want_i = sims.argmax(1)
+    want_s = sims[np.arange(n), want_i]
+    ok = want_s >= 0.3
+    ok[0] = False
+    np.testing.assert_array_equal(i >= 0, ok)
+    gap = np.sort(sims, axis=1)[:, -1] - np.sort(sims, axis=1)[:, -2] if n > 2 else np.ones(n)
+    sure = ok & (gap >= 1e-3)
+    np.testing.assert_array_equal(i[sure], want_i[sure])
+    np.testing.assert_allclose(s[ok], want_s[ok], rtol=0, atol=2e-6)
+
+
+def test_exhaustive_search_uses_the_rows_dot_kernel(lib):
+    """QdrantManager-shaped search with k beyond the running top-8 (duplicate.py:2757-2766 asks for every row): exact
+    fp32 scores from b2f_rows_dot, ordered like the reference (score desc), thresholded with >="""
+    from scrfd_arcface_facerecognition_b200.vector_store import GalleryManager
+    emb = inputs.clustered(61, 30, 4, noise=0.4)
+    mgr = GalleryManager({"vector_database": {}})
+    for j in range(len(emb)):
+        assert mgr.add_embedding(j, emb[j], {"name": f"p{j}"})
+    before = _lib.launch_count()
+    res = mgr.search_similar(emb[7], k=len(emb), threshold=0.5)
+    assert _lib.launch_count() > before
+    idx, sc = restate.search_similar(emb[7], emb, len(emb), 0.5)
+    assert [r["person_id"] for r in res] == list(idx) and res[0]["person_id"] == 7
+    np.testing.assert_allclose([r["similarity"] for r in res], sc, rtol=0, atol=2e-6)
+
+
 def test_top1_key_kernels_match_host_arithmetic(lib):
     """b2f_topk_pack_keys / b2f_topk_unpack_keys == the torch restatement used by the gloo tests, bit for bit"""
     from scrfd_arcface_facerecognition_b200.gallery import pack_top1_keys, unpack_top1_keys
