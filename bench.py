@@ -715,7 +715,9 @@ def run_pipeline(a):
     if rank == 0:
         eng_d = det._engine_for(det.input_size[1], det.input_size[0])
         st8 = rec._engine.stem8(B * F) if getattr(rec, "stem8", False) else None
-        nets = [("SCRFD-10G" if a.config == 2 else "SCRFD-2.5G", eng_d, B, None, 1 if eng_d.patch_buffer(B) is not None else 0),
+        det_start = 2 if (det.fuse_stem and det.fuse_conv1 and eng_d.stem_fused(B) is not None) else \
+            (1 if eng_d.patch_buffer(B) is not None else 0)        # the first layer may live in the preprocess kernel
+        nets = [("SCRFD-10G" if a.config == 2 else "SCRFD-2.5G", eng_d, B, None, det_start),
                 ("R50", rec._engine, B * F, st8[1] if st8 is not None else None, 2 if st8 is not None else 0)]
         roofline, pool_spans = conv_roofline(a, nets, pk)
         roofline["share_of_step"] = roofline.pop("conv_ms_per_step") / ms_step if ms_step else None

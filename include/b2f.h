@@ -58,6 +58,15 @@ int b2f_preprocess(const uint8_t* frames, int batch, int h, int w, int new_w, in
 int b2f_preprocess_patches(const uint8_t* frames, int batch, int h, int w, int new_w, int new_h, int in_w, int in_h,
                            int stride, float mean, float scale, void* out_patches, int dtype, void* stream);
 
+/* a2 + a3 + the detector's FIRST convolution (3x3 / stride 2 / pad 1, 3 -> cout_p in {16, 32}, bias, optional ReLU) in one
+ * kernel: letterboxed, normalised pixels are produced in shared memory and consumed there, so neither the blob nor a
+ * patch tensor reaches HBM (reference models/scrfd.py:76-83, 135-138: resize + blobFromImage + the first Conv node of
+ * session.run).  weight [cout_p][32] 16-bit with k = tap * 3 + rgb (27 used), bias [cout_p] f32,
+ * out [batch][in_h/2][in_w/2][cout_p] 16-bit. */
+int b2f_preprocess_conv1(const uint8_t* frames, int batch, int h, int w, int new_w, int new_h, int in_w, int in_h,
+                         float mean, float scale, const void* weight, const float* bias, int cout_p, int act,
+                         void* out, int dtype, void* stream);
+
 /* ---- a3 exact: u8 BGR HWC -> fp32 NCHW RGB blob, (float(x)-mean)*scale, bit-exact vs
  * cv2.dnn.blobFromImage(s) (reference models/scrfd.py:76-82, models/arcface.py:44-50). */
 int b2f_blob_nchw_f32(const uint8_t* images, int batch, int h, int w, float mean, float scale, float* out,

@@ -114,6 +114,7 @@ SIGNATURES = {
     "b2f_letterbox_u8": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "b2f_preprocess": [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _i, _i, _vp],
     "b2f_preprocess_patches": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _i, _vp],
+    "b2f_preprocess_conv1": [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _i, _i, _vp, _i, _vp],
     "b2f_blob_nchw_f32": [_vp, _i, _i, _i, _f, _f, _vp, _vp],
     "b2f_decode_nms": [C.POINTER(DetLevels), _i, _i, _i, _vp, _vp, _f, _f, _i, _i, _i, _i, _vp, _vp, _vp, _vp,
                        _vp, _ll, _vp],

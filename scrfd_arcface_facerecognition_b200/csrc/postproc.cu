@@ -175,6 +175,126 @@ letterbox_patches_kernel(const uint8_t* __restrict__ frames, ResizeGeom g, int s
                       v[8 * j + 4] | ((uint32_t)v[8 * j + 5] << 16), v[8 * j + 6] | ((uint32_t)v[8 * j + 7] << 16));
 }
 
+// ---- letterbox + normalise + the detector's FIRST CONVOLUTION (3x3 / stride 2 / pad 1, 3 -> cout_p <= 32) in one pass ----
+// The stem layer has K = 27: its arithmetic is 0.6 % of the detector's and it is bound by writing its 320 x 320 x 32
+// output, so it is computed where the pixels are produced instead of materialising a 419 MB patch tensor for the tcgen05
+// kernel (one HBM round trip and one launch less).  A CTA owns a 32 x 8 tile of output pixels: the letterboxed,
+// normalised source pixels it touches are evaluated once into shared memory as [y][x][R,G,B,0] 16-bit values (taps
+// outside the canvas are the convolution's zero padding, the letterbox pad inside it a real normalised zero pixel);
+// warp w computes output row w as two m16 tiles with mma.sync.m16n8k16 (fp16 / bf16 operands, fp32 accumulation; K
+// order k = tap * 3 + rgb, 27 used, the same weight layout [cout_p][32] the patch GEMM reads), adds the bias, applies
+// ReLU and stores whole 64-byte pixels through a per-warp staging row.
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, bool bf16) {
+  if (bf16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <bool BF16, int NT>     // NT = cout_p / 8 n-tiles
+__global__ void __launch_bounds__(kLpW * kLpH)
+letterbox_conv1_kernel(const uint8_t* __restrict__ frames, ResizeGeom g, int ho, int wo, float mean, float scale,
+                       const uint16_t* __restrict__ weight, const float* __restrict__ bias, int act,
+                       uint16_t* __restrict__ out) {
+  constexpr int IW = kLpW * 2 + 1, IH = kLpH * 2 + 1, COUT = NT * 8;
+  __shared__ __align__(16) uint16_t tile[IH * IW * 4];
+  __shared__ __align__(16) uint16_t stage[kLpH][kLpW * COUT];
+  const int b = blockIdx.z, ox0 = blockIdx.x * kLpW, oy0 = blockIdx.y * kLpH;
+  const int ix0 = ox0 * 2 - 1, iy0 = oy0 * 2 - 1;
+  const uint8_t* img = frames + (size_t)b * g.H * g.W * 3;
+  for (int t = threadIdx.x; t < IW * IH; t += blockDim.x) {
+    const int ty = t / IW, tx = t - ty * IW;
+    const int iy = iy0 + ty, ix = ix0 + tx;
+    uint2 v = make_uint2(0u, 0u);
+    if (iy >= 0 && iy < g.in_h && ix >= 0 && ix < g.in_w) {
+      int bgr[3];
+      letterbox_pixel(img, g, ix, iy, bgr);
+      v.x = norm16(bgr[2], mean, scale, BF16) | ((uint32_t)norm16(bgr[1], mean, scale, BF16) << 16);   // R, G
+      v.y = norm16(bgr[0], mean, scale, BF16);                                                          // B, 0
+    }
+    *reinterpret_cast<uint2*>(tile + t * 4) = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g4 = lane >> 2, t4 = lane & 3;
+  // offsets (in 16-bit elements, relative to the tap-0 pixel of an output pixel) of the K entries this thread feeds:
+  // k = ks * 16 + {2t, 2t+1, 2t+8, 2t+9}; k = tap * 3 + rgb; K entries 27..31 read the always-zero fourth channel
+  int koff[2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = ks * 16 + 2 * t4 + (j & 1) + (j >> 1) * 8;
+      const int tap = k / 3, c = k - tap * 3;
+      koff[ks][j] = k < 27 ? ((tap / 3) * IW + tap % 3) * 4 + c : 3;
+    }
+  uint32_t bw[2][NT][2];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const uint16_t* wr = weight + (size_t)(nt * 8 + g4) * 32 + ks * 16 + 2 * t4;
+      bw[ks][nt][0] = *reinterpret_cast<const uint32_t*>(wr);
+      bw[ks][nt][1] = *reinterpret_cast<const uint32_t*>(wr + 8);
+    }
+  const int ly = warp;
+  float acc[2][NT][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const uint16_t* p0 = tile + ((ly * 2) * IW + (mt * 16 + g4) * 2) * 4;      // output pixel lx = mt*16 + g4 (rows g)
+    const uint16_t* p1 = p0 + 8 * 2 * 4;                                        // lx + 8 (rows g + 8)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t a[4];
+      a[0] = p0[koff[ks][0]] | ((uint32_t)p0[koff[ks][1]] << 16);
+      a[1] = p1[koff[ks][0]] | ((uint32_t)p1[koff[ks][1]] << 16);
+      a[2] = p0[koff[ks][2]] | ((uint32_t)p0[koff[ks][3]] << 16);
+      a[3] = p1[koff[ks][2]] | ((uint32_t)p1[koff[ks][3]] << 16);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) mma16816(acc[mt][nt], a, bw[ks][nt][0], bw[ks][nt][1], BF16);
+    }
+  }
+  // bias + activation -> 16-bit -> the warp's staging row [pixel][COUT]
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int col = nt * 8 + 2 * t4;
+    const float b0 = __ldg(bias + col), b1 = __ldg(bias + col + 1);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        float v0 = acc[mt][nt][2 * hrow] + b0, v1 = acc[mt][nt][2 * hrow + 1] + b1;
+        if (act == 1) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f);
+        uint32_t packed;
+        if (BF16) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+          packed = *reinterpret_cast<uint32_t*>(&h2);
+        } else {
+          __half2 h2 = __floats2half2_rn(v0, v1);
+          packed = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        *reinterpret_cast<uint32_t*>(&stage[warp][(mt * 16 + g4 + 8 * hrow) * COUT + col]) = packed;
+      }
+  }
+  __syncwarp();
+  const int oy = oy0 + ly;
+  if (oy >= ho) return;
+  uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)b * ho + oy) * wo + ox0) * COUT);
+  const uint4* src = reinterpret_cast<const uint4*>(stage[warp]);
+  constexpr int PIECES = kLpW * COUT / 8;                  // 16-byte pieces of the row segment
+  const int valid = min(kLpW, wo - ox0) * COUT / 8;
+  for (int i = lane; i < PIECES && i < valid; i += 32) dst[i] = src[i];
+}
+
 static int make_geom(ResizeGeom* g, int h, int w, int new_w, int new_h, int in_w, int in_h) {
   B2F_REQUIRE(h > 0 && w > 0 && new_w > 0 && new_h > 0 && new_w <= in_w && new_h <= in_h,
               "letterbox: bad geometry %dx%d -> %dx%d in %dx%d", w, h, new_w, new_h, in_w, in_h);
@@ -836,6 +956,35 @@ extern "C" int b2f_preprocess_patches(const uint8_t* frames, int batch, int h, i
   letterbox_patches_kernel<<<dim3((wo + kLpW - 1) / kLpW, (ho + kLpH - 1) / kLpH, batch), kLpW * kLpH, 0,
                              (cudaStream_t)stream>>>(frames, g, stride, ho, wo, mean, scale,
                                                      reinterpret_cast<uint16_t*>(out_patches), dtype == B2F_BF16);
+  g_launches.fetch_add(1);
+  B2F_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b2f_preprocess_conv1(const uint8_t* frames, int batch, int h, int w, int new_w, int new_h, int in_w, int in_h,
+                                    float mean, float scale, const void* weight, const float* bias, int cout_p, int act,
+                                    void* out, int dtype, void* stream) {
+  B2F_REQUIRE(dtype == B2F_F16 || dtype == B2F_BF16, "b2f_preprocess_conv1: dtype must be f16 or bf16");
+  B2F_REQUIRE(cout_p == 16 || cout_p == 32, "b2f_preprocess_conv1: cout_p must be 16 or 32 (got %d)", cout_p);
+  B2F_REQUIRE(act == B2F_ACT_NONE || act == B2F_ACT_RELU, "b2f_preprocess_conv1: activation must be none or ReLU");
+  B2F_REQUIRE(weight && bias && out, "b2f_preprocess_conv1: null argument");
+  ResizeGeom g;
+  int rc = make_geom(&g, h, w, new_w, new_h, in_w, in_h);
+  if (rc) return rc;
+  const int ho = (in_h + 2 - 3) / 2 + 1, wo = (in_w + 2 - 3) / 2 + 1;
+  if (batch <= 0) return 0;
+  B2F_REQUIRE(batch <= 65535, "b2f_preprocess_conv1: batch too large");
+  const dim3 grid((wo + kLpW - 1) / kLpW, (ho + kLpH - 1) / kLpH, batch);
+  const uint16_t* wt = reinterpret_cast<const uint16_t*>(weight);
+  uint16_t* o = reinterpret_cast<uint16_t*>(out);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B2F_BF16) {
+    if (cout_p == 32) letterbox_conv1_kernel<true, 4><<<grid, kLpW * kLpH, 0, st>>>(frames, g, ho, wo, mean, scale, wt, bias, act, o);
+    else letterbox_conv1_kernel<true, 2><<<grid, kLpW * kLpH, 0, st>>>(frames, g, ho, wo, mean, scale, wt, bias, act, o);
+  } else {
+    if (cout_p == 32) letterbox_conv1_kernel<false, 4><<<grid, kLpW * kLpH, 0, st>>>(frames, g, ho, wo, mean, scale, wt, bias, act, o);
+    else letterbox_conv1_kernel<false, 2><<<grid, kLpW * kLpH, 0, st>>>(frames, g, ho, wo, mean, scale, wt, bias, act, o);
+  }
   g_launches.fetch_add(1);
   B2F_LAUNCH_CHECK();
   return 0;

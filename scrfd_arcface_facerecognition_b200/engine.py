@@ -243,6 +243,21 @@ class NetEngine:
             return None
         return self._bound_for(n)[1][op.dst], int(op.attrs["stride"])
 
+    def stem_fused(self, n: int):
+        """When the plan opens with the stride-2 3x3 patch extraction followed by the first convolution as a 1x1 over the
+        27-channel patches (the SCRFD stem) and that convolution is small enough for `b2f_preprocess_conv1` (cout_p 16 or
+        32, bias + optional ReLU, 16-bit output): (weight [cout_p][32], bias [cout_p], act, output tensor, cout_p) -- the
+        caller runs letterbox + normalise + this convolution as ONE kernel and continues with run(start=2).  Else None."""
+        ops = self.plan.ops
+        if (len(ops) < 2 or ops[0].kind != "im2col" or ops[0].attrs["stride"] != 2 or ops[1].kind != "conv"
+                or ops[1].src != ops[0].dst or ops[1].residual or ops[1].sc_src or ops[1].attrs["kh"] != 1
+                or ops[1].act not in (0, 1) or ops[1].attrs["bias_classes"] != 1 or ops[1].attrs.get("pool")
+                or self.plan.tensors[ops[1].dst].f32 or self.plan.tensors[ops[1].dst].cp not in (16, 32)):
+            return None
+        tens = self._bound_for(n)[1]
+        w1 = self._weights[1]
+        return w1["weight"][0], w1["bias"][0], int(ops[1].act), tens[ops[1].dst], int(self.plan.tensors[ops[1].dst].cp)
+
     def stem8(self, n: int):
         """When the plan opens with the 3x3 / pad 1 patch extraction followed by the first convolution as a 1x1 over the
         27-channel patches: (image buffer [n,H,W,8], launch) for the 8-channel stem form of `b2f_conv2d` instead -- the

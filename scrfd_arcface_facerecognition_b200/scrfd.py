@@ -75,6 +75,7 @@ class SCRFD:
         self.std = 128.0
         self.center_cache = {}
         self.fuse_stem = True               # letterbox + blob + first-layer patches in one kernel when the plan allows
+        self.fuse_conv1 = os.environ.get("B2F_FUSE_CONV1", "1") != "0"   # ... and the first convolution itself with them
 
         self._lock = threading.RLock()      # duplicate.py calls the shared model from a 4-thread pool
         self._engines: Dict[Tuple[int, int], NetEngine] = {}
@@ -140,6 +141,16 @@ class SCRFD:
         """frames: [B,H,W,3] uint8 cuda.  Letterbox + normalise into the engine input, run the net."""
         eng = self._engine_for(in_h, in_w)
         b, h, w, _ = frames.shape
+        fused = eng.stem_fused(b) if (self.fuse_stem and self.fuse_conv1) else None
+        if fused is not None:             # letterbox + blob + the first convolution in one kernel: no patch tensor at all
+            wt, bias, act, out, cout_p = fused
+            # algorithmic bytes (SURVEY 8d): the source pixels the resize needs + the first layer's output
+            with _lib.span("letterbox_conv1_kernel", b * (new_w * new_h * 3 + out[0].numel() * 2)):
+                _lib.check(self._lib.b2f_preprocess_conv1(
+                    frames.data_ptr(), b, h, w, new_w, new_h, in_w, in_h, float(self.mean),
+                    float(np.float32(1.0 / self.std)), wt.data_ptr(), bias.data_ptr(), cout_p, act, out.data_ptr(),
+                    eng.dtype, stream_ptr()), "b2f_preprocess_conv1")
+            return eng.run(b, start=2)
         patches = eng.patch_buffer(b) if self.fuse_stem else None
         if patches is not None:           # letterbox + blob + first-layer patch extraction in one pass
             # algorithmic bytes (SURVEY 8d): the source pixels the resize needs + the patch tensor written

@@ -423,6 +423,48 @@ def test_fused_preprocess_patches_equal_preprocess_plus_im2col(lib, geom):
     assert torch.equal(got.view(torch.int16), want.view(torch.int16))
 
 
+@pytest.mark.parametrize("geom", [(1080, 1920, 640, 360), (720, 1280, 640, 360), (480, 640, 640, 480), (333, 517, 640, 412)],
+                         ids=lambda g: "x".join(map(str, g)))
+@pytest.mark.parametrize("cout", [28, 16])
+def test_fused_preprocess_conv1_matches_patches_plus_conv(lib, geom, cout):
+    """letterbox + blob + FIRST CONVOLUTION in one kernel (b2f_preprocess_conv1) against the two-kernel path it
+    replaces (b2f_preprocess_patches, bit-exact vs cv2, then the tcgen05 1x1 GEMM over the patches): same exact fp16
+    products, fp32 accumulation in a different order -> equal after the 16-bit rounding except for isolated 1-ulp
+    flips; and both within 2e-3 of the fp32 convolution of the exact blob"""
+    h, w, new_w, new_h = geom
+    n = 2
+    frames = torch.from_numpy(np.stack([inputs.frame(40 + i, h, w) for i in range(n)])).cuda()
+    gen = torch.Generator().manual_seed(cout)
+    cout_p = 32 if cout > 16 else 16
+    for dtype, tdt in ((0, torch.float16), (1, torch.bfloat16)):
+        wt = torch.zeros((1, cout_p, 32), dtype=tdt)
+        wt[0, :cout, :27] = (torch.randn((cout, 27), generator=gen) * (2.0 / 27) ** 0.5).to(tdt)
+        bias = torch.zeros((1, cout_p))
+        bias[0, :cout] = torch.randn(cout, generator=gen) * 0.1
+        wt_d, bias_d = wt.cuda(), bias.cuda()
+        patches = torch.empty((n, 320, 320, 32), dtype=tdt, device="cuda")
+        _lib.check(lib.b2f_preprocess_patches(frames.data_ptr(), n, h, w, new_w, new_h, 640, 640, 2, 127.5, 1 / 128.0,
+                                              patches.data_ptr(), dtype, sp()))
+        want = torch.empty((n, 320, 320, cout_p), dtype=tdt, device="cuda")
+        d = _lib.ConvDesc()
+        d.n, d.h, d.w, d.cin_p, d.ho, d.wo, d.cout_p = n, 320, 320, 32, 320, 320, cout_p
+        d.kh, d.kw, d.stride, d.pad = 1, 1, 1, 0
+        d.dtype, d.out_dtype, d.act, d.bias_classes = dtype, dtype, 1, 1
+        d.in_, d.weight, d.bias, d.out = patches.data_ptr(), wt_d.data_ptr(), bias_d.data_ptr(), want.data_ptr()
+        _lib.check(lib.b2f_conv2d(C.byref(d), sp()), "b2f_conv2d")
+        got = torch.full((n, 320, 320, cout_p), float("nan"), dtype=tdt, device="cuda")
+        _lib.check(lib.b2f_preprocess_conv1(frames.data_ptr(), n, h, w, new_w, new_h, 640, 640, 127.5, 1 / 128.0,
+                                            wt_d.data_ptr(), bias_d.data_ptr(), cout_p, 1, got.data_ptr(), dtype, sp()))
+        torch.cuda.synchronize()
+        differ = (got.view(torch.int16) != want.view(torch.int16))
+        assert differ.float().mean().item() <= 2e-3, f"{differ.float().mean().item():.2e} of the outputs differ"
+        ulp = 2.0 ** -10 if dtype == 0 else 2.0 ** -7
+        assert ((got.float() - want.float()).abs() <= ulp * want.float().abs().clamp_min(2.0 ** -14) * 1.01).all()
+        ref = torch.relu(patches.float().reshape(-1, 32) @ wt_d[0].float().T + bias_d[0]).reshape(n, 320, 320, cout_p)
+        assert (got.float() - ref).abs().max().item() <= (2e-3 if dtype == 0 else 1.6e-2) * max(1.0, ref.abs().max().item())
+        assert (got[..., cout:] == 0).all()
+
+
 def test_fused_norm_crop_patches_equal_norm_crop_plus_im2col(lib):
     h, w, n = 360, 480, 40
     frames = torch.from_numpy(np.stack([inputs.smooth_frame(50 + i, h, w) for i in range(2)])).cuda()
