@@ -70,9 +70,12 @@ def test_detector_heads_match_oracle(key, hw):
         worst[name] = float(np.abs(got - want).max())
     print(key, {k: f"{v:.2e}" for k, v in worst.items()})
     names = [o[0] for o in eng.plan.outputs]
-    # scores are probabilities; bbox / kps are in stride units (x8..32 px): fp16 activations vs fp32 oracle
-    assert max(worst[n] for n in names[:3]) <= 2e-2
-    assert max(worst[n] for n in names[3:]) <= 6e-2
+    # scores are probabilities; bbox / kps are in stride units (x8..32 px): fp16 operands / activations vs the fp32 oracle.
+    # Measured on B200: scores <= 2.2e-3, bbox / kps <= 6.0e-3 stride units (0.05-0.19 px at 640 x 640) -- asserted with 2x
+    # headroom.  The error is spread over all ~57 layers: keeping only the last head convolutions (or even every
+    # activation) in fp32 removes at most half of it, the weights' own 16-bit rounding is the rest.
+    assert max(worst[n] for n in names[:3]) <= 5e-3
+    assert max(worst[n] for n in names[3:]) <= 1.2e-2
 
 
 def test_scrfd_api_matches_reference_detect(golden):

@@ -178,6 +178,65 @@ def test_face_analysis_facade_matches_detect_plus_arcface():
     assert FaceAnalysis(name="buffalo_l")._det_path.endswith("det_10g.onnx")
 
 
+def test_shared_models_are_safe_across_threads():
+    """reference duplicate.py:1954 runs the shared FaceAnalysis object from a 4-thread pool: results handed to one
+    thread must not be overwritten by another thread's run on the same engine buffers (they are copied out under the
+    model lock).  Four threads, different images with the same face count, many rounds == the sequential answers."""
+    from concurrent.futures import ThreadPoolExecutor
+    from scrfd_arcface_facerecognition_b200.face_analysis import FaceAnalysis
+    app = FaceAnalysis(name="buffalo_s")
+    app.prepare(ctx_id=0, det_size=(640, 640))
+    imgs = [inputs.frame(120 + i, 480, 640) for i in range(4)]
+    want = [[(f.bbox.copy(), f.embedding.copy()) for f in app.get(im, max_num=3)] for im in imgs]
+    assert all(len(w) == 3 for w in want)
+
+    def work(i):
+        out = []
+        for _ in range(12):
+            out.append([(f.bbox, f.embedding) for f in app.get(imgs[i], max_num=3)])
+        return out
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        results = list(ex.map(work, range(4)))
+    for i, rounds in enumerate(results):
+        for faces in rounds:
+            assert len(faces) == 3
+            for (b, e), (wb, we) in zip(faces, want[i]):
+                np.testing.assert_array_equal(b, wb)
+                np.testing.assert_array_equal(e, we)
+    # the batched entries hand out copies by default: a second call must not change the first call's tensors
+    rec, det = app.rec_model, app.det_model
+    frames = torch.from_numpy(np.stack(imgs[:2])).cuda()
+    d1, k1, c1 = det.detect_batch(frames, max_num=3)
+    keep = (d1.clone(), k1.clone())
+    det.detect_batch(torch.from_numpy(np.stack(imgs[2:])).cuda(), max_num=3)
+    torch.cuda.synchronize()
+    assert torch.equal(d1, keep[0]) and torch.equal(k1, keep[1])
+    fidx = torch.zeros(3, dtype=torch.int32, device="cuda")
+    e1 = rec.embed_batch(frames, fidx, k1[0].reshape(3, 10))
+    e1_keep = e1.clone()
+    rec.embed_batch(frames, fidx + 1, k1[1].reshape(3, 10))
+    torch.cuda.synchronize()
+    assert torch.equal(e1, e1_keep)
+
+
+def test_engine_buffers_are_bucketed_by_capacity():
+    """a service that sees every face count 1..K must not keep one activation set per count: buffers are shared by
+    all batch sizes of one power-of-two capacity, and results do not depend on the capacity they ran in"""
+    from models import ArcFace
+    rec = ArcFace("weights/w600k_mbf.onnx")
+    frames = torch.from_numpy(np.stack([inputs.frame(130, 360, 480)])).cuda()
+    kps = torch.from_numpy(inputs.landmarks(131, 360, 480, 40).reshape(40, 10)).cuda()
+    fidx = torch.zeros(40, dtype=torch.int32, device="cuda")
+    full = rec.embed_batch(frames, fidx, kps)
+    for n in range(1, 41):
+        part = rec.embed_batch(frames, fidx[:n].contiguous(), kps[:n].contiguous())
+        assert torch.equal(part, full[:n])
+    eng = rec._engine
+    assert sorted(eng._pools) == [1, 2, 4, 8, 16, 32, 64]
+    one_set = sum(b.numel() for b in eng._pools[64])
+    assert eng.buffer_bytes() <= 2.2 * one_set                      # geometric: at most ~2x the largest capacity
+
+
 def test_qdrant_manager_surface():
     from oracle import restate
     from scrfd_arcface_facerecognition_b200.vector_store import QdrantManager
