@@ -48,10 +48,13 @@ class FacePipeline:
         return out
 
     # ---- CUDA-graph replay of the whole step -----------------------------------------------------
-    def capture(self, b: int, h: int, w: int):
-        """Warm up and capture `process` for a [b,h,w,3] batch.  Returns (static_frames, outputs, graph, kernels)."""
+    def capture(self, b: int, h: int, w: int, slot: int = 0):
+        """Warm up and capture `process` for a [b,h,w,3] batch.  Returns (static_frames, outputs, graph, kernels).
+        `slot` distinguishes several graphs of one shape, each bound to its own input buffer: a feeder that uploads
+        batch i+1 straight into the other slot's input while batch i runs needs no device-to-device staging copy.
+        All slots write the same output tensors (the models' persistent buffers)."""
         version = self.gallery.version if self.gallery is not None else -1
-        key = (b, h, w)
+        key = (b, h, w, slot)
         if key in self._graphs:
             if self._graphs[key][4] == version:
                 return self._graphs[key][:4]
