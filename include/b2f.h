@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define B2F_ABI_VERSION 2
+#define B2F_ABI_VERSION 3
 
 /* dtype codes */
 #define B2F_F16 0

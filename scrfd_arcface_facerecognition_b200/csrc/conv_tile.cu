@@ -368,135 +368,119 @@ __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& 
   if (c.leader) bulk_wait_all();
 }
 
-// Epilogue with a fused 3x3 / stride 2 / pad 1 max-pool (tiles of 8 x 16 pixels, ReLU, no residual): a 32-channel slice
-// goes TMEM -> registers -> bias + ReLU -> swizzled staging tile as usual; then the group's 128 threads reduce it to the
-// 5 x 9 window maxima this tile contributes to (windows that straddle a tile edge are partial) and one TMA reduce-store
-// max-merges them into the zero-initialised pooled map -- ReLU outputs are >= 0, so 0 is the identity of the max.
-// The conv result itself never reaches HBM.
-constexpr int kPoolW = 5, kPoolH = 9, kPoolBufBytes = 3072;
+// Epilogue with a fused 3x3 / stride 2 / pad 1 max-pool (tiles of 8 x 16 pixels, ReLU, no residual).  The conv result
+// never leaves the registers: a warp owns a 8 x 4 strip of the tile (one TMEM lane quarter), a 32-channel slice of a
+// pixel is 16 packed 16-bit pairs per thread, and the window maxima are built with warp shuffles -- horizontally over
+// lanes +-1, vertically over lanes +-8.  A strip contributes to 3 x 5 pooled pixels (windows that straddle a strip or
+// tile edge are partial); the 15 lanes that hold them write 64 bytes each into the warp's own 1 KB buffer and ONE TMA
+// reduce-store per warp max-merges them into the zero-initialised pooled map (ReLU outputs are >= 0, so 0 is the
+// identity of the max and partial maxima of neighbouring strips / tiles combine in L2).  No staging tile, no block-level
+// barrier, no shared-memory reads.
+constexpr int kPoolW = 5, kPoolH = 3, kPoolBufBytes = 1024;      // per warp and buffer; two buffers per warp
 template <bool BF16>
-__device__ __forceinline__ uint4 max8(const uint4& a, const uint4& b) {
-  uint4 r;
+__device__ __forceinline__ uint32_t hmax2u(uint32_t a, uint32_t b) {
   if (BF16) {
-    const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&a);
-    const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&b);
-    __nv_bfloat162* z = reinterpret_cast<__nv_bfloat162*>(&r);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) z[i] = __hmax2(x[i], y[i]);
-  } else {
-    const __half2* x = reinterpret_cast<const __half2*>(&a);
-    const __half2* y = reinterpret_cast<const __half2*>(&b);
-    __half2* z = reinterpret_cast<__half2*>(&r);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) z[i] = __hmax2(x[i], y[i]);
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
   }
-  return r;
+  __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
 }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
 template <bool BF16>
-__device__ __forceinline__ void epilogue_pool(const TileParams& p, const EpiCtx& c, uint8_t* pbuf) {
+__device__ __forceinline__ void epilogue_pool(const TileParams& p, const EpiCtx& c, uint8_t* pbuf_warp) {
   const int G = p.groups, n_sub = p.n_sub, group = c.group;
   const int n_acc_mask = (1 << p.n_acc_log2) - 1;
-  const int m = c.q * 32 + c.lane;                     // pixel of the 8 x 16 tile: lx = m & 7, ly = m >> 3
-  const int NB = p.stg_bufs;
+  const int lane = c.lane, lx = lane & 7, lr = lane >> 3;       // pixel of the strip: column lx, row lr of rows 4q .. 4q+3
+  const int ly = c.q * 4 + lr;
   const int my_tiles = c.tiles_cta > group ? (c.tiles_cta - group + G - 1) / G : 0;
-  const uint32_t row_off = (uint32_t)m * 64u;
-  uint32_t off[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t o = row_off + (uint32_t)i * 16;
-    off[i] = o ^ (((o >> 7) & 3u) << 4);
-  }
-  const int stg_bytes = p.stg_bytes, cout_p = p.cout_p;
-  // pooling work of this thread: 45 windows x four 16-byte pieces = 180 items over 128 threads (item m, and m + 128 for
-  // the first 52).  An item is the maximum over the 3 x 3 window clipped to the tile: out-of-tile taps are replaced by
-  // a clipped neighbour (a duplicate does not change a maximum), so the nine loads are unconditional and independent.
-  // The byte offsets into the swizzled staging tile are fixed for full tiles and computed once.
-  auto window = [](int it, int rows_in, int cols_in, uint32_t (&po)[9]) -> bool {
-    const int pp = it >> 2, piece = it & 3;
-    const int pyl = pp / kPoolW, pxl = pp - pyl * kPoolW;
-    const int ylo = max(2 * pyl - 1, 0), yhi = min(2 * pyl + 1, rows_in - 1);
-    const int xlo = max(2 * pxl - 1, 0), xhi = min(2 * pxl + 1, cols_in - 1);
-    if (ylo > yhi || xlo > xhi) return false;                 // the window lies outside the image part of this tile
-    const int ys[3] = {ylo, min(ylo + 1, yhi), yhi}, xs[3] = {xlo, min(xlo + 1, xhi), xhi};
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-      for (int b = 0; b < 3; ++b)
-        po[a * 3 + b] = (uint32_t)((ys[a] * 8 + xs[b]) * 64 + ((piece ^ ((xs[b] >> 1) & 3)) << 4));   // 64-byte swizzle
-    return true;
-  };
-  auto reduce9 = [](const uint8_t* bufp, const uint32_t (&po)[9]) -> uint4 {
-    uint4 v[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) v[i] = *reinterpret_cast<const uint4*>(bufp + po[i]);
-    const uint4 a = max8<BF16>(max8<BF16>(v[0], v[1]), max8<BF16>(v[2], v[3]));
-    const uint4 b = max8<BF16>(max8<BF16>(v[4], v[5]), max8<BF16>(v[6], v[7]));
-    return max8<BF16>(max8<BF16>(a, b), v[8]);
-  };
-  const bool second = m + 128 < kPoolW * kPoolH * 4;
-  uint32_t po0[9], po1[9];
-  window(m, 16, 8, po0);
-  if (second) window(m + 128, 16, 8, po1);
-  const uint32_t dst0 = (uint32_t)((m >> 2) * 64 + (m & 3) * 16), dst1 = (uint32_t)(((m + 128) >> 2) * 64 + (m & 3) * 16);
+  const int cout_p = p.cout_p;
+  // which pooled pixel of the strip's 3 x 5 this lane ends up holding (if any)
+  const int prow = lr == 0 ? 0 : (lr == 2 ? 1 : (lr == 3 ? 2 : -1));
+  const int pcol = lx == 7 ? 4 : ((lx & 1) ? -1 : (lx >> 1));
+  const bool holder = prow >= 0 && pcol >= 0;
+  const uint32_t dst_off = holder ? (uint32_t)((prow * kPoolW + pcol) * 64) : 0u;
   int k = 0;
   for (int tl = 0; tl < my_tiles; ++tl) {
     const int seq = group + tl * G;
     const TileCoord t = tile_of(p, c.first, c.stride, c.rank, seq);
     int cls = 0;
     if (p.bias_classes == 9) {
-      const int ox = t.x0 + (m & 7), oy = t.y0 + (m >> 3);
-      const int iy = oy - 1, ix = ox - 1;
+      const int iy = t.y0 + ly - 1, ix = t.x0 + lx - 1;
       const int cy = iy < 0 ? 0 : (iy + 2 >= p.H ? 2 : 1);
       const int cx = ix < 0 ? 0 : (ix + 2 >= p.W ? 2 : 1);
       cls = cy * 3 + cx;
     }
     const float* bias_row = c.s_bias + cls * cout_p + t.cbase;
+    const bool in_image = t.y0 + ly < p.Ho && t.x0 + lx < p.Wo;     // a tile may overhang the right / bottom edge
     const int acc = seq & n_acc_mask;
     const uint32_t ph = (uint32_t)(seq >> p.n_acc_log2) & 1u;
     mbar_wait(&c.tfull[acc], ph);
     tc_fence_after();
     const uint32_t t_addr = c.tmem_base + ((uint32_t)(c.q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
-    // rows / columns of the tile that exist in the image (a tile may overhang the right / bottom edge)
-    const int rows_in = min(16, p.Ho - t.y0), cols_in = min(8, p.Wo - t.x0);
-    const bool full = rows_in == 16 && cols_in == 8;
     for (int j = 0; j < n_sub; ++j, ++k) {
-      uint8_t* bufp = c.stg + (size_t)(k % NB) * stg_bytes;
       uint32_t r[32];
       tmem_ld32(t_addr + (uint32_t)(j * 32), r);
       tmem_ld_wait();
       if (j == n_sub - 1) {                              // accumulator fully read: hand it back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (c.lane == 0) mbar_arrive(&c.tempty[acc]);
+        if (lane == 0) mbar_arrive(&c.tempty[acc]);
       }
       const int cl = j * 32;
-      epi_slice16<1, BF16, 0>(r, bias_row + cl, nullptr, reinterpret_cast<uint4*>(bufp + off[0]),
-                              reinterpret_cast<uint4*>(bufp + off[1]), t.cbase + cl, 0, nullptr);
-      epi_slice16<1, BF16, 0>(r + 16, bias_row + cl + 16, nullptr, reinterpret_cast<uint4*>(bufp + off[2]),
-                              reinterpret_cast<uint4*>(bufp + off[3]), t.cbase + cl + 16, 0, nullptr);
-      if (c.leader) bulk_wait_read0();                   // the previous reduce-store has left the pooled buffer
-      bar_sync_named(1 + group, 128);                    // the slice is complete in shared memory
-      if (full) {
-        *reinterpret_cast<uint4*>(pbuf + dst0) = reduce9(bufp, po0);
-        if (second) *reinterpret_cast<uint4*>(pbuf + dst1) = reduce9(bufp, po1);
-      } else {                                           // edge tiles: clip the windows to the rows / columns that exist
-        uint32_t pe[9];
-        const bool ok0 = window(m, rows_in, cols_in, pe);
-        *reinterpret_cast<uint4*>(pbuf + dst0) = ok0 ? reduce9(bufp, pe) : make_uint4(0u, 0u, 0u, 0u);
-        if (second) {
-          const bool ok1 = window(m + 128, rows_in, cols_in, pe);
-          *reinterpret_cast<uint4*>(pbuf + dst1) = ok1 ? reduce9(bufp, pe) : make_uint4(0u, 0u, 0u, 0u);
+      uint32_t v[16];
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) {
+        const float4 b4 = *(reinterpret_cast<const float4*>(bias_row + cl) + q4);          // shared memory, broadcast
+        const float f0 = fmaxf(__uint_as_float(r[4 * q4 + 0]) + b4.x, 0.f), f1 = fmaxf(__uint_as_float(r[4 * q4 + 1]) + b4.y, 0.f);
+        const float f2 = fmaxf(__uint_as_float(r[4 * q4 + 2]) + b4.z, 0.f), f3 = fmaxf(__uint_as_float(r[4 * q4 + 3]) + b4.w, 0.f);
+        if (BF16) {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(f0, f1), h1 = __floats2bfloat162_rn(f2, f3);
+          v[2 * q4] = *reinterpret_cast<uint32_t*>(&h0), v[2 * q4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+        } else {
+          __half2 h0 = __floats2half2_rn(f0, f1), h1 = __floats2half2_rn(f2, f3);
+          v[2 * q4] = *reinterpret_cast<uint32_t*>(&h0), v[2 * q4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
         }
       }
+      if (!in_image) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        // horizontal: columns lx-1, lx, lx+1 of this row, clipped to the strip; column 7 also serves, alone, the window
+        // centred on column 8 (which belongs to the next tile)
+        const uint32_t left = __shfl_up_sync(0xFFFFFFFFu, v[i], 1), right = __shfl_down_sync(0xFFFFFFFFu, v[i], 1);
+        uint32_t h = v[i];
+        if (lx > 0) h = hmax2u<BF16>(h, left);
+        if (lx < 7) h = hmax2u<BF16>(h, right);
+        const uint32_t hs = lx == 7 ? v[i] : h;
+        // vertical: rows lr-1, lr, lr+1 of the strip.  Row 0 centres the window whose upper row lies in the strip above,
+        // row 2 a complete window, row 3 alone serves the window centred on the row below the strip
+        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, hs, 8), down = __shfl_down_sync(0xFFFFFFFFu, hs, 8);
+        uint32_t o = hs;
+        if (lr == 0) o = hmax2u<BF16>(hs, down);
+        if (lr == 2) o = hmax2u<BF16>(hmax2u<BF16>(up, hs), down);
+        v[i] = o;
+      }
+      uint8_t* buf = pbuf_warp + (k & 1) * kPoolBufBytes;
+      if (lane == 0) bulk_wait_read1();                  // the reduce-store issued two slices ago has left this buffer
+      __syncwarp();
+      if (holder) {
+        uint4* d4 = reinterpret_cast<uint4*>(buf + dst_off);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d4[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
       fence_proxy_async();
-      bar_sync_named(1 + group, 128);
-      if (c.leader && !(p.debug & 1)) {
-        tma_reduce_max_4d(c.tmO, pbuf, t.cbase + cl, t.x0 >> 1, t.y0 >> 1, t.n0);
+      __syncwarp();
+      if (lane == 0 && !(p.debug & 1)) {
+        tma_reduce_max_4d(c.tmO, buf, t.cbase + cl, t.x0 >> 1, (t.y0 >> 1) + 2 * c.q, t.n0);
         bulk_commit();
       }
     }
   }
-  if (c.leader) bulk_wait_all();
+  if (lane == 0) bulk_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1058,8 +1042,8 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         B2F_EPI_CASE(3)
         case 24: epilogue_tma<0, false, 3, CG2>(p, c); break;
         case 25: epilogue_tma<0, true, 3, CG2>(p, c); break;
-        case 26: if constexpr (!CG2) epilogue_pool<false>(p, c, smem + p.off_pool + group * kPoolBufBytes); break;
-        case 27: if constexpr (!CG2) epilogue_pool<true>(p, c, smem + p.off_pool + group * kPoolBufBytes); break;
+        case 26: if constexpr (!CG2) epilogue_pool<false>(p, c, smem + p.off_pool + (warp - 2) * 2 * kPoolBufBytes); break;
+        case 27: if constexpr (!CG2) epilogue_pool<true>(p, c, smem + p.off_pool + (warp - 2) * 2 * kPoolBufBytes); break;
         default: break;
       }
 #undef B2F_EPI_CASE
@@ -1234,7 +1218,7 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
     p.res_global = (res_eff == 1 && wide) ? 1 : 0;
   }
   const int tab_bytes = round_up((p.bias_classes + 1) * p.cout_p * 4, 256);
-  const int pool_bytes = p.pool ? kTGroups * kPoolBufBytes : 0;
+  const int pool_bytes = p.pool ? kTGroups * 4 * 2 * kPoolBufBytes : 0;      // two 1 KB buffers per epilogue warp
   const int fixed = 1024 /*align*/ + 1024 /*barriers*/ + tab_bytes + pool_bytes;
 
   // ---- choose A mode, tile geometry, weight sharing and epilogue groups with a per-tile cycle model -----------
@@ -1286,7 +1270,7 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
         for (int groups = 4; groups >= 2; groups -= 2) {
           if (groups > (1 << p.n_acc_log2)) continue;          // a group must never be a whole accumulator phase ahead
           if (f_groups && groups != f_groups && f_groups <= (1 << p.n_acc_log2)) continue;
-          const int staging = p.epi_tma ? groups * p.stg_bufs * p.stg_bytes : 0;
+          const int staging = (p.epi_tma && !p.pool) ? groups * p.stg_bufs * p.stg_bytes : 0;   // pooled layers stage nothing
           int avail = kSmemMax - fixed - staging;
           int stages_a = 0, stages_b = 0;
           const int tpb = taps / boxes;
@@ -1381,7 +1365,7 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   if (p.combined) p.stages_a = 0;                      // activation boxes live inside the weight stages
   p.off_b = p.stages_a * p.a_stage_bytes;
   p.off_stg = p.off_b + (p.b_resident ? b_all : p.stages_b * p.b_stride);
-  p.off_bar = p.off_stg + (p.epi_tma ? p.groups * p.stg_bufs * p.stg_bytes : 0);
+  p.off_bar = p.off_stg + ((p.epi_tma && !p.pool) ? p.groups * p.stg_bufs * p.stg_bytes : 0);
   p.off_tab = p.off_bar + 1024;
   p.off_pool = p.off_tab + tab_bytes;
   size_t smem = (size_t)p.off_pool + pool_bytes + 1024;
