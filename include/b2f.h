@@ -59,8 +59,8 @@ int b2f_preprocess_patches(const uint8_t* frames, int batch, int h, int w, int n
                            int stride, float mean, float scale, void* out_patches, int dtype, void* stream);
 
 /* a2 + a3 + the detector's FIRST convolution (3x3 / stride 2 / pad 1, 3 -> cout_p in {16, 32}, bias, optional ReLU) in one
- * kernel: letterboxed, normalised pixels are produced in shared memory and consumed there, so neither the blob nor a
- * patch tensor reaches HBM (reference models/scrfd.py:76-83, 135-138: resize + blobFromImage + the first Conv node of
+ * kernel: letterboxed, normalised pixels are produced in shared memory, assembled there into the K-major operand tiles of
+ * a tcgen05 GEMM (K = 27) and consumed by it, so neither the blob nor a patch tensor reaches HBM (reference models/scrfd.py:76-83, 135-138: resize + blobFromImage + the first Conv node of
  * session.run).  weight [cout_p][32] 16-bit with k = tap * 3 + rgb (27 used), bias [cout_p] f32,
  * out [batch][in_h/2][in_w/2][cout_p] 16-bit. */
 int b2f_preprocess_conv1(const uint8_t* frames, int batch, int h, int w, int new_w, int new_h, int in_w, int in_h,

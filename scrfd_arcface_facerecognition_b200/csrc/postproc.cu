@@ -177,122 +177,144 @@ letterbox_patches_kernel(const uint8_t* __restrict__ frames, ResizeGeom g, int s
 
 // ---- letterbox + normalise + the detector's FIRST CONVOLUTION (3x3 / stride 2 / pad 1, 3 -> cout_p <= 32) in one pass ----
 // The stem layer has K = 27: its arithmetic is 0.6 % of the detector's and it is bound by writing its 320 x 320 x 32
-// output, so it is computed where the pixels are produced instead of materialising a 419 MB patch tensor for the tcgen05
-// kernel (one HBM round trip and one launch less).  A CTA owns a 32 x 8 tile of output pixels: the letterboxed,
-// normalised source pixels it touches are evaluated once into shared memory as [y][x][R,G,B,0] 16-bit values (taps
-// outside the canvas are the convolution's zero padding, the letterbox pad inside it a real normalised zero pixel);
-// warp w computes output row w as two m16 tiles with mma.sync.m16n8k16 (fp16 / bf16 operands, fp32 accumulation; K
-// order k = tap * 3 + rgb, 27 used, the same weight layout [cout_p][32] the patch GEMM reads), adds the bias, applies
-// ReLU and stores whole 64-byte pixels through a per-warp staging row.
-__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, bool bf16) {
-  if (bf16)
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-  else
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-template <bool BF16, int NT>     // NT = cout_p / 8 n-tiles
+// output, so it is computed where the pixels are produced instead of materialising a 419 MB patch tensor for the
+// convolution kernel (one HBM round trip and one launch less).  A CTA owns a 32 x 8 tile of output pixels:
+//   1. the letterboxed source pixels the tile touches are evaluated once into shared memory (uint8 BGR + an
+//      inside-the-canvas flag: taps outside the canvas are the convolution's zero padding, the letterbox pad inside it a
+//      real normalised zero pixel, reference models/scrfd.py:76-82, 135-138);
+//   2. every thread assembles the 27 normalised values of its pixel (k = tap * 3 + rgb, the order of the weight layout
+//      [cout_p][32]) and writes them as one 64-byte row of the A operand -- two 128-row K-major tiles in the canonical
+//      64-byte-swizzled layout a TMA load would have produced; the weights go to shared memory the same way;
+//   3. one thread issues four tcgen05.mma (2 tiles x K = 32 in two steps, M = 128, N = cout_p) into 2 x cout_p TMEM columns;
+//   4. each warp reads its TMEM lane quarter back (tcgen05.ld), adds the bias, applies ReLU and stores the pixel's 64
+//      bytes (a warp covers 2 KB of contiguous output).
+template <bool BF16, int COUT>
 __global__ void __launch_bounds__(kLpW * kLpH)
 letterbox_conv1_kernel(const uint8_t* __restrict__ frames, ResizeGeom g, int ho, int wo, float mean, float scale,
                        const uint16_t* __restrict__ weight, const float* __restrict__ bias, int act,
                        uint16_t* __restrict__ out) {
-  constexpr int IW = kLpW * 2 + 1, IH = kLpH * 2 + 1, COUT = NT * 8;
-  __shared__ __align__(16) uint16_t tile[IH * IW * 4];
-  __shared__ __align__(16) uint16_t stage[kLpH][kLpW * COUT];
+  constexpr int IW = kLpW * 2 + 1, IH = kLpH * 2 + 1;
+  constexpr uint32_t kCols = 2 * COUT < 32 ? 32 : 2 * COUT;          // TMEM columns: two accumulators of COUT
+  __shared__ __align__(1024) uint8_t a_tile[2 * 128 * 64];            // [m tile][row][32 k] 16-bit, SWIZZLE_64B
+  __shared__ __align__(1024) uint8_t b_tile[COUT * 64];               // [cout][32 k] 16-bit, SWIZZLE_64B
+  __shared__ uint8_t tile[IH * IW * 4];                               // b, g, r, inside flag
+  __shared__ uint16_t lut[256];
+  __shared__ __align__(8) uint64_t done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, ox0 = blockIdx.x * kLpW, oy0 = blockIdx.y * kLpH;
   const int ix0 = ox0 * 2 - 1, iy0 = oy0 * 2 - 1;
   const uint8_t* img = frames + (size_t)b * g.H * g.W * 3;
-  for (int t = threadIdx.x; t < IW * IH; t += blockDim.x) {
+  if (warp == 0) {
+    tmem_alloc(&tmem_slot, kCols);
+    tmem_relinquish();
+  }
+  if (tid == 32) {
+    mbar_init(&done_bar, 1);
+    fence_barrier_init();
+  }
+  lut[tid] = norm16(tid, mean, scale, BF16);                          // blockDim.x == 256
+  for (int t = tid; t < IW * IH; t += blockDim.x) {
     const int ty = t / IW, tx = t - ty * IW;
     const int iy = iy0 + ty, ix = ix0 + tx;
-    uint2 v = make_uint2(0u, 0u);
-    if (iy >= 0 && iy < g.in_h && ix >= 0 && ix < g.in_w) {
-      int bgr[3];
-      letterbox_pixel(img, g, ix, iy, bgr);
-      v.x = norm16(bgr[2], mean, scale, BF16) | ((uint32_t)norm16(bgr[1], mean, scale, BF16) << 16);   // R, G
-      v.y = norm16(bgr[0], mean, scale, BF16);                                                          // B, 0
-    }
-    *reinterpret_cast<uint2*>(tile + t * 4) = v;
+    int bgr[3] = {0, 0, 0};
+    const bool inside = iy >= 0 && iy < g.in_h && ix >= 0 && ix < g.in_w;
+    if (inside) letterbox_pixel(img, g, ix, iy, bgr);
+    *reinterpret_cast<uchar4*>(tile + t * 4) = make_uchar4((unsigned char)bgr[0], (unsigned char)bgr[1],
+                                                           (unsigned char)bgr[2], inside ? 1 : 0);
   }
+  for (int c = tid; c < COUT * 4; c += blockDim.x) {                  // weights: 16-byte chunks into the swizzled rows
+    const uint32_t o = (uint32_t)c * 16;
+    *reinterpret_cast<uint4*>(b_tile + (o ^ (((o >> 7) & 3u) << 4))) = __ldg(reinterpret_cast<const uint4*>(weight) + c);
+  }
+  tc_fence_before();
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g4 = lane >> 2, t4 = lane & 3;
-  // offsets (in 16-bit elements, relative to the tap-0 pixel of an output pixel) of the K entries this thread feeds:
-  // k = ks * 16 + {2t, 2t+1, 2t+8, 2t+9}; k = tap * 3 + rgb; K entries 27..31 read the always-zero fourth channel
-  int koff[2][4];
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  // A operand: thread (ly, lx) = row (tid & 127) of M tile (tid >> 7)
+  const int lx = tid & (kLpW - 1), ly = tid / kLpW;
+  {
+    uint16_t v[32];
 #pragma unroll
-  for (int ks = 0; ks < 2; ++ks)
+    for (int tap = 0; tap < 9; ++tap) {
+      const uchar4 px = *reinterpret_cast<const uchar4*>(tile + ((ly * 2 + tap / 3) * IW + lx * 2 + tap % 3) * 4);
+      v[tap * 3 + 0] = px.w ? lut[px.z] : (uint16_t)0;      // R
+      v[tap * 3 + 1] = px.w ? lut[px.y] : (uint16_t)0;      // G
+      v[tap * 3 + 2] = px.w ? lut[px.x] : (uint16_t)0;      // B
+    }
+#pragma unroll
+    for (int k = 27; k < 32; ++k) v[k] = 0;
+    uint8_t* row_base = a_tile + (tid >> 7) * (128 * 64);
+    const uint32_t row_off = (uint32_t)(tid & 127) * 64u;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int k = ks * 16 + 2 * t4 + (j & 1) + (j >> 1) * 8;
-      const int tap = k / 3, c = k - tap * 3;
-      koff[ks][j] = k < 27 ? ((tap / 3) * IW + tap % 3) * 4 + c : 3;
-    }
-  uint32_t bw[2][NT][2];
-#pragma unroll
-  for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      const uint16_t* wr = weight + (size_t)(nt * 8 + g4) * 32 + ks * 16 + 2 * t4;
-      bw[ks][nt][0] = *reinterpret_cast<const uint32_t*>(wr);
-      bw[ks][nt][1] = *reinterpret_cast<const uint32_t*>(wr + 8);
-    }
-  const int ly = warp;
-  float acc[2][NT][4];
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
-    const uint16_t* p0 = tile + ((ly * 2) * IW + (mt * 16 + g4) * 2) * 4;      // output pixel lx = mt*16 + g4 (rows g)
-    const uint16_t* p1 = p0 + 8 * 2 * 4;                                        // lx + 8 (rows g + 8)
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      uint32_t a[4];
-      a[0] = p0[koff[ks][0]] | ((uint32_t)p0[koff[ks][1]] << 16);
-      a[1] = p1[koff[ks][0]] | ((uint32_t)p1[koff[ks][1]] << 16);
-      a[2] = p0[koff[ks][2]] | ((uint32_t)p0[koff[ks][3]] << 16);
-      a[3] = p1[koff[ks][2]] | ((uint32_t)p1[koff[ks][3]] << 16);
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) mma16816(acc[mt][nt], a, bw[ks][nt][0], bw[ks][nt][1], BF16);
+      const uint32_t o = row_off + (uint32_t)j * 16;
+      *reinterpret_cast<uint4*>(row_base + (o ^ (((o >> 7) & 3u) << 4))) =
+          make_uint4(v[8 * j] | ((uint32_t)v[8 * j + 1] << 16), v[8 * j + 2] | ((uint32_t)v[8 * j + 3] << 16),
+                     v[8 * j + 4] | ((uint32_t)v[8 * j + 5] << 16), v[8 * j + 6] | ((uint32_t)v[8 * j + 7] << 16));
     }
   }
-  // bias + activation -> 16-bit -> the warp's staging row [pixel][COUT]
+  fence_proxy_async();                                        // generic-proxy writes -> visible to the tensor core
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc(128, COUT, BF16 ? 1u : 0u);
+      const uint64_t bd = umma_smem_desc(smem_u32(b_tile), 64);
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    const int col = nt * 8 + 2 * t4;
-    const float b0 = __ldg(bias + col), b1 = __ldg(bias + col + 1);
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int hrow = 0; hrow < 2; ++hrow) {
-        float v0 = acc[mt][nt][2 * hrow] + b0, v1 = acc[mt][nt][2 * hrow + 1] + b1;
-        if (act == 1) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f);
-        uint32_t packed;
-        if (BF16) {
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
-          packed = *reinterpret_cast<uint32_t*>(&h2);
-        } else {
-          __half2 h2 = __floats2half2_rn(v0, v1);
-          packed = *reinterpret_cast<uint32_t*>(&h2);
-        }
-        *reinterpret_cast<uint32_t*>(&stage[warp][(mt * 16 + g4 + 8 * hrow) * COUT + col]) = packed;
+      for (int mt = 0; mt < 2; ++mt) {
+        const uint64_t ad = umma_smem_desc(smem_u32(a_tile) + (uint32_t)mt * 128u * 64u, 64);
+        umma_f16(tmem_base + (uint32_t)mt * COUT, ad, bd, idesc, 0u);
+        umma_f16(tmem_base + (uint32_t)mt * COUT, ad + 2, bd + 2, idesc, 1u);
       }
+      umma_commit(&done_bar);
+    }
+    __syncwarp();
   }
-  __syncwarp();
-  const int oy = oy0 + ly;
-  if (oy >= ho) return;
-  uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)b * ho + oy) * wo + ox0) * COUT);
-  const uint4* src = reinterpret_cast<const uint4*>(stage[warp]);
-  constexpr int PIECES = kLpW * COUT / 8;                  // 16-byte pieces of the row segment
-  const int valid = min(kLpW, wo - ox0) * COUT / 8;
-  for (int i = lane; i < PIECES && i < valid; i += 32) dst[i] = src[i];
+  mbar_wait(&done_bar, 0);
+  tc_fence_after();
+  // epilogue: warp w reads lanes 32 (w & 3) .. +31 of accumulator w >> 2, i.e. output row ly == w, pixel lx == lane
+  {
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * COUT;
+    uint32_t r[COUT];
+    if (COUT == 32) {
+      uint32_t (&r32)[32] = reinterpret_cast<uint32_t (&)[32]>(r);
+      tmem_ld32(taddr, r32);
+    } else {
+      uint32_t (&r16)[16] = reinterpret_cast<uint32_t (&)[16]>(r);
+      tmem_ld16(taddr, r16);
+    }
+    tmem_ld_wait();
+    const int oy = oy0 + ly, ox = ox0 + lx;
+    if (oy < ho && ox < wo) {
+      uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)b * ho + oy) * wo + ox) * COUT);
+#pragma unroll
+      for (int j = 0; j < COUT / 8; ++j) {
+        uint32_t w4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v0 = __uint_as_float(r[8 * j + 2 * i]) + __ldg(bias + 8 * j + 2 * i);
+          float v1 = __uint_as_float(r[8 * j + 2 * i + 1]) + __ldg(bias + 8 * j + 2 * i + 1);
+          if (act == 1) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f);
+          if (BF16) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+            w4[i] = *reinterpret_cast<uint32_t*>(&h2);
+          } else {
+            __half2 h2 = __floats2half2_rn(v0, v1);
+            w4[i] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+        }
+        dst[j] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kCols);
+  }
 }
 
 static int make_geom(ResizeGeom* g, int h, int w, int new_w, int new_h, int in_w, int in_h) {
@@ -979,11 +1001,11 @@ extern "C" int b2f_preprocess_conv1(const uint8_t* frames, int batch, int h, int
   uint16_t* o = reinterpret_cast<uint16_t*>(out);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B2F_BF16) {
-    if (cout_p == 32) letterbox_conv1_kernel<true, 4><<<grid, kLpW * kLpH, 0, st>>>(frames, g, ho, wo, mean, scale, wt, bias, act, o);
-    else letterbox_conv1_kernel<true, 2><<<grid, kLpW * kLpH, 0, st>>>(frames, g, ho, wo, mean, scale, wt, bias, act, o);
+    if (cout_p == 32) letterbox_conv1_kernel<true, 32><<<grid, kLpW * kLpH, 0, st>>>(frames, g, ho, wo, mean, scale, wt, bias, act, o);
+    else letterbox_conv1_kernel<true, 16><<<grid, kLpW * kLpH, 0, st>>>(frames, g, ho, wo, mean, scale, wt, bias, act, o);
   } else {
-    if (cout_p == 32) letterbox_conv1_kernel<false, 4><<<grid, kLpW * kLpH, 0, st>>>(frames, g, ho, wo, mean, scale, wt, bias, act, o);
-    else letterbox_conv1_kernel<false, 2><<<grid, kLpW * kLpH, 0, st>>>(frames, g, ho, wo, mean, scale, wt, bias, act, o);
+    if (cout_p == 32) letterbox_conv1_kernel<false, 32><<<grid, kLpW * kLpH, 0, st>>>(frames, g, ho, wo, mean, scale, wt, bias, act, o);
+    else letterbox_conv1_kernel<false, 16><<<grid, kLpW * kLpH, 0, st>>>(frames, g, ho, wo, mean, scale, wt, bias, act, o);
   }
   g_launches.fetch_add(1);
   B2F_LAUNCH_CHECK();
