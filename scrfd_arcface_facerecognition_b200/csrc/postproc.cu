@@ -189,7 +189,7 @@ letterbox_patches_kernel(const uint8_t* __restrict__ frames, ResizeGeom g, int s
 //   4. each warp reads its TMEM lane quarter back (tcgen05.ld), adds the bias, applies ReLU and stores the pixel's 64
 //      bytes (a warp covers 2 KB of contiguous output).
 template <bool BF16, int COUT>
-__global__ void __launch_bounds__(kLpW * kLpH)
+__global__ void __launch_bounds__(kLpW * kLpH, 4)
 letterbox_conv1_kernel(const uint8_t* __restrict__ frames, ResizeGeom g, int ho, int wo, float mean, float scale,
                        const uint16_t* __restrict__ weight, const float* __restrict__ bias, int act,
                        uint16_t* __restrict__ out) {
@@ -197,8 +197,9 @@ letterbox_conv1_kernel(const uint8_t* __restrict__ frames, ResizeGeom g, int ho,
   constexpr uint32_t kCols = 2 * COUT < 32 ? 32 : 2 * COUT;          // TMEM columns: two accumulators of COUT
   __shared__ __align__(1024) uint8_t a_tile[2 * 128 * 64];            // [m tile][row][32 k] 16-bit, SWIZZLE_64B
   __shared__ __align__(1024) uint8_t b_tile[COUT * 64];               // [cout][32 k] 16-bit, SWIZZLE_64B
-  __shared__ uint8_t tile[IH * IW * 4];                               // b, g, r, inside flag
+  __shared__ __align__(8) uint16_t tile[IH * IW * 4];                 // normalised R, G, B, 0 (all zero outside the canvas)
   __shared__ uint16_t lut[256];
+  __shared__ __align__(16) float s_bias[COUT];
   __shared__ __align__(8) uint64_t done_bar;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -214,33 +215,64 @@ letterbox_conv1_kernel(const uint8_t* __restrict__ frames, ResizeGeom g, int ho,
     fence_barrier_init();
   }
   lut[tid] = norm16(tid, mean, scale, BF16);                          // blockDim.x == 256
-  for (int t = tid; t < IW * IH; t += blockDim.x) {
-    const int ty = t / IW, tx = t - ty * IW;
-    const int iy = iy0 + ty, ix = ix0 + tx;
-    int bgr[3] = {0, 0, 0};
-    const bool inside = iy >= 0 && iy < g.in_h && ix >= 0 && ix < g.in_w;
-    if (inside) letterbox_pixel(img, g, ix, iy, bgr);
-    *reinterpret_cast<uchar4*>(tile + t * 4) = make_uchar4((unsigned char)bgr[0], (unsigned char)bgr[1],
-                                                           (unsigned char)bgr[2], inside ? 1 : 0);
-  }
+  if (tid < COUT) s_bias[tid] = bias[tid];
   for (int c = tid; c < COUT * 4; c += blockDim.x) {                  // weights: 16-byte chunks into the swizzled rows
     const uint32_t o = (uint32_t)c * 16;
     *reinterpret_cast<uint4*>(b_tile + (o ^ (((o >> 7) & 3u) << 4))) = __ldg(reinterpret_cast<const uint4*>(weight) + c);
+  }
+  __syncthreads();                                                    // the table is complete
+  // source pixels of the tile, normalised once.  The sweeps over the tile are unrolled with every load ahead of the
+  // first use, so a thread's loads are in flight together; the odd-ratio and copy modes (1080p -> 640 x 360 is
+  // img[1::3, 1::3]) take a byte-offset fast path, the general bilinear / 2x-area modes go through letterbox_pixel.
+  const bool direct = g.mode == 0 || g.mode == 3;
+  const int ratio = g.mode == 3 ? g.ratio : 1, roff = (ratio - 1) >> 1;
+  {
+    constexpr int kSweeps = (IW * IH + kLpW * kLpH - 1) / (kLpW * kLpH);
+    int bgr[kSweeps][3];
+    bool in[kSweeps];
+#pragma unroll
+    for (int i = 0; i < kSweeps; ++i) {                       // all loads of the CTA's sweeps are issued before any use
+      const int t = tid + i * (kLpW * kLpH);
+      const int ty = t / IW, tx = t - ty * IW;
+      const int iy = iy0 + ty, ix = ix0 + tx;
+      bgr[i][0] = bgr[i][1] = bgr[i][2] = 0;
+      in[i] = t < IW * IH && ix >= 0 && ix < g.in_w && iy >= 0 && iy < g.in_h;
+      if (in[i]) {
+        if (direct) {
+          if (ix < g.new_w && iy < g.new_h) {
+            const uint8_t* px = img + ((size_t)(iy * ratio + roff) * g.W + (ix * ratio + roff)) * 3;
+            bgr[i][0] = px[0], bgr[i][1] = px[1], bgr[i][2] = px[2];
+          }
+        } else {
+          letterbox_pixel(img, g, ix, iy, bgr[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kSweeps; ++i) {
+      const int t = tid + i * (kLpW * kLpH);
+      uint2 v = make_uint2(0u, 0u);
+      if (in[i]) {
+        v.x = lut[bgr[i][2]] | ((uint32_t)lut[bgr[i][1]] << 16);      // R, G
+        v.y = lut[bgr[i][0]];                                         // B, 0
+      }
+      if (t < IW * IH) *reinterpret_cast<uint2*>(tile + t * 4) = v;
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  // A operand: thread (ly, lx) = row (tid & 127) of M tile (tid >> 7)
+  // A operand: thread (ly, lx) = row (tid & 127) of M tile (tid >> 7); k = tap * 3 + rgb, 27 used
   const int lx = tid & (kLpW - 1), ly = tid / kLpW;
   {
     uint16_t v[32];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
-      const uchar4 px = *reinterpret_cast<const uchar4*>(tile + ((ly * 2 + tap / 3) * IW + lx * 2 + tap % 3) * 4);
-      v[tap * 3 + 0] = px.w ? lut[px.z] : (uint16_t)0;      // R
-      v[tap * 3 + 1] = px.w ? lut[px.y] : (uint16_t)0;      // G
-      v[tap * 3 + 2] = px.w ? lut[px.x] : (uint16_t)0;      // B
+      const uint2 px = *reinterpret_cast<const uint2*>(tile + ((ly * 2 + tap / 3) * IW + lx * 2 + tap % 3) * 4);
+      v[tap * 3 + 0] = (uint16_t)(px.x & 0xFFFFu);           // R
+      v[tap * 3 + 1] = (uint16_t)(px.x >> 16);               // G
+      v[tap * 3 + 2] = (uint16_t)(px.y & 0xFFFFu);           // B
     }
 #pragma unroll
     for (int k = 27; k < 32; ++k) v[k] = 0;
@@ -294,8 +326,8 @@ letterbox_conv1_kernel(const uint8_t* __restrict__ frames, ResizeGeom g, int ho,
         uint32_t w4[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          float v0 = __uint_as_float(r[8 * j + 2 * i]) + __ldg(bias + 8 * j + 2 * i);
-          float v1 = __uint_as_float(r[8 * j + 2 * i + 1]) + __ldg(bias + 8 * j + 2 * i + 1);
+          float v0 = __uint_as_float(r[8 * j + 2 * i]) + s_bias[8 * j + 2 * i];
+          float v1 = __uint_as_float(r[8 * j + 2 * i + 1]) + s_bias[8 * j + 2 * i + 1];
           if (act == 1) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f);
           if (BF16) {
             __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
@@ -868,7 +900,7 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(WarpParams p) {
 // 16-byte pieces of the [size][size][32] patch tensor the first ArcFace convolution consumes as a 1x1 conv.
 constexpr int kPatchCrop = 112;
 template <bool IMG8>   // IMG8: emit the crop itself as 16-byte pixels (R, G, B, 0 x 5) for the stem-form convolution
-__global__ void __launch_bounds__(512) warp_patches_kernel(WarpParams p, uint16_t* __restrict__ out) {
+__global__ void __launch_bounds__(512, 2) warp_patches_kernel(WarpParams p, uint16_t* __restrict__ out) {
   __shared__ uint8_t crop[kPatchCrop * kPatchCrop * 3];
   __shared__ uint16_t lut[256];
   __shared__ double sM[6];
@@ -884,6 +916,7 @@ __global__ void __launch_bounds__(512) warp_patches_kernel(WarpParams p, uint16_
   const double i02 = __dsub_rn(__dmul_rn(-i00, sM[2]), __dmul_rn(i01, sM[5]));
   const double i12 = __dsub_rn(__dmul_rn(-i10, sM[2]), __dmul_rn(i11, sM[5]));
   const uint8_t* img = p.frames + (size_t)p.frame_idx[f] * p.h * p.w * 3;
+#pragma unroll 2
   for (int idx = threadIdx.x; idx < size * size; idx += blockDim.x) {
     const int x = idx % size, y = idx / size;
     const int adelta = (int)__double2ll_rn(__dmul_rn(__dmul_rn(i00, (double)x), 1024.0));
