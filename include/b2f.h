@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define B2F_ABI_VERSION 3
+#define B2F_ABI_VERSION 4
 
 /* dtype codes */
 #define B2F_F16 0
@@ -162,6 +162,13 @@ typedef struct b2f_conv_desc {
    * window maxima into it through TMA (the entry zeroes `out` first).  Needs a 3x3 / stride 1 / pad 1 convolution with
    * act == RELU, a 16-bit output, cout_p % 32 == 0 and no residual (reference graph: Conv-Relu-MaxPool of the SCRFD stem). */
   int pool;
+  /* optional split-K workspace (device, >= 8 * n * ho * wo * cout_p * 4 bytes; NULL = never split).  A layer with an fp32
+   * output, no activation / residual and >= 128 K chunks per tile (the 7 x 7 x 512 -> 512 embedding layer, reference
+   * models/arcface.py:51: 16 work items for 148 SMs) then deals its filter taps to up to 8 work items per tile that store
+   * fp32 partial sums here; a second kernel adds them in a fixed order.  Whether a layer splits depends on the layer and on
+   * this pointer only, never on n. */
+  void* splitk_ws;
+  long long splitk_ws_bytes;
 } b2f_conv_desc;
 int b2f_conv2d(const b2f_conv_desc* desc, void* stream);
 
@@ -234,6 +241,25 @@ int b2f_pairs_threshold(const void* emb16, int n, int dim, int dtype, int row_be
                         long long* pairs /*[max_pairs] (i<<32|j), j>i*/, long long max_pairs,
                         unsigned long long* pair_count, void* stream);
 int b2f_cluster_resolve(const long long* pairs_sorted, long long n_pairs, int n, int* leader, void* stream);
+
+/* ---- 8f rank 3: overlay drawing on device-resident frames -----------------------------------------
+ * replaces the cv2.rectangle / cv2.line / cv2.putText calls of reference utils/helpers.py:126-179 (draw_bbox,
+ * draw_bbox_info; called per face at reference main.py:144-148) for frames that stay in HBM.  The caller lowers those
+ * calls to draw commands (overlay.py): kind 0 = fill the inclusive rectangle [x0, x1] x [y0, y1] (clipped to the frame),
+ * kind 1 = paint `bgr` wherever the 1-byte-per-pixel mask at masks + mask_off (x1 columns, y1 rows, row-major) is
+ * non-zero, mask pixel (0, 0) landing on frame pixel (x0, y0).  Commands are grouped (one group = the commands of one
+ * face, which share a colour); group g holds commands [group_cmds[g], group_cmds[g + 1]) and frame f owns groups
+ * [frame_groups[f], frame_groups[f + 1]), painted in that order (a later face paints over an earlier one, as in the
+ * reference loop).  frames: [batch][h][w][3] u8 BGR, modified in place.  All pointers are device pointers. */
+typedef struct b2f_draw_cmd {
+  int kind;
+  int x0, y0, x1, y1;
+  unsigned int bgr;      /* b | g << 8 | r << 16 */
+  int mask_off;
+  int reserved;
+} b2f_draw_cmd;
+int b2f_draw_overlay(uint8_t* frames, int batch, int h, int w, const b2f_draw_cmd* cmds, const int* frame_groups,
+                     const int* group_cmds, const uint8_t* masks, void* stream);
 
 /* ---- debug: one TMA box -> raw shared-memory image (tests the tensor-map conventions) -------------- */
 int b2f_debug_tma_probe(const void* src, const long long* dims4, const int* box4, const int* estr4,

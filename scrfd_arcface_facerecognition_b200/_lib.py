@@ -14,7 +14,7 @@ from typing import List
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libb2f.so")
-SOURCES = ["core.cu", "postproc.cu", "aux_ops.cu", "umma_conv.cu", "conv_tile.cu", "match_pair.cu"]
+SOURCES = ["core.cu", "postproc.cu", "aux_ops.cu", "umma_conv.cu", "conv_tile.cu", "match_pair.cu", "overlay.cu"]
 HEADERS = ["b2f_common.cuh", "umma_shared.cuh", os.path.join("..", "..", "include", "b2f.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -90,6 +90,11 @@ class DetLevels(C.Structure):
                 ("score_ps", C.c_int * 3), ("bbox_ps", C.c_int * 3), ("kps_ps", C.c_int * 3)]
 
 
+class DrawCmd(C.Structure):
+    _fields_ = [("kind", C.c_int), ("x0", C.c_int), ("y0", C.c_int), ("x1", C.c_int), ("y1", C.c_int),
+                ("bgr", C.c_uint), ("mask_off", C.c_int), ("reserved", C.c_int)]
+
+
 class ConvDesc(C.Structure):
     _fields_ = [("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("cin_p", C.c_int),
                 ("ho", C.c_int), ("wo", C.c_int), ("cout_p", C.c_int),
@@ -100,7 +105,8 @@ class ConvDesc(C.Structure):
                 ("in_", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p), ("slope", C.c_void_p),
                 ("residual", C.c_void_p), ("out", C.c_void_p),
                 ("sc_in", C.c_void_p), ("sc_weight", C.c_void_p),
-                ("sc_cin_p", C.c_int), ("sc_stride", C.c_int), ("sc_h", C.c_int), ("sc_w", C.c_int), ("pool", C.c_int)]
+                ("sc_cin_p", C.c_int), ("sc_stride", C.c_int), ("sc_h", C.c_int), ("sc_w", C.c_int), ("pool", C.c_int),
+                ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_longlong)]
 
 
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
@@ -146,6 +152,7 @@ SIGNATURES = {
     "b2f_topk_unpack_keys": [_vp, _ll, _vp, _vp, _vp],
     "b2f_pairs_threshold": [_vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _ll, _vp, _vp],
     "b2f_cluster_resolve": [_vp, _ll, _i, _vp, _vp],
+    "b2f_draw_overlay": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "b2f_debug_tma_probe": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp],
 }
 _RESTYPES = {"b2f_last_error": C.c_char_p, "b2f_launch_count": _ll, "b2f_decode_nms_workspace": _ll}

@@ -79,6 +79,8 @@ struct TileParams {
   const void* residual;
   int res_mode, res_h, res_w;
   int off_b, off_stg, off_bar, off_tab;
+  int ksplit;               // split-K: an item covers taps [split * taps / ksplit, +taps / ksplit) and stores fp32 partial sums
+  long long split_stride;   // floats between the partial outputs of consecutive splits (p.out is then the workspace)
 };
 
 __device__ __forceinline__ void unpack8(const uint4& v, int is_bf16, float* f) {
@@ -238,17 +240,19 @@ struct EpiCtx {
 };
 
 struct TileCoord {
-  int x0, y0, n0, cbase, m_tile;
+  int x0, y0, n0, cbase, m_tile, split;
 };
 
 __device__ __forceinline__ TileCoord tile_of(const TileParams& p, int first, int stride, int rank, int seq) {
   // an item = `pair` consecutive M tiles of one N tile: mt tiles of one CTA, or one tile for each CTA of a pair
   const int l = seq / p.mt, u = seq - l * p.mt;
-  const int i = first + l * stride;
+  const int is = first + l * stride;
+  const int i = is / p.ksplit;
   const int nt = i % p.n_tiles, mp = i / p.n_tiles;
   const int m_tile = p.cg2 ? (mp * 2 + rank) * p.mt + u : mp * p.mt + u;
   const int tiles_xy = p.tiles_x * p.tiles_y;
   TileCoord t;
+  t.split = is - i * p.ksplit;
   t.m_tile = m_tile;
   t.x0 = (m_tile % p.tiles_x) * p.tw;
   t.y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.th;
@@ -515,7 +519,7 @@ __device__ __forceinline__ void mma_issuer(const TileParams& p, const MmaCtx& c)
   constexpr int TPB = MODE == 0 ? 1 : (MODE == 1 ? 3 : 9);
   const uint32_t row_bytes = p.kchunk * 2;
   const uint32_t idesc = umma_idesc(CG2 ? 256 : 128, (uint32_t)p.block_n, (uint32_t)p.is_bf16);
-  const int groups_per_item = p.cchunks * p.boxes_per_chunk + p.sc_cchunks;      // shortcut chunks ride as extra taps
+  const int groups_per_item = p.cchunks * p.boxes_per_chunk / p.ksplit + p.sc_cchunks;   // shortcut chunks ride as extra taps
   const int stages_a = p.stages_a, stages_b = p.stages_b, items_cta = c.items_cta;
   const int acc_mask = (1 << p.n_acc_log2) - 1, acc_log2 = p.n_acc_log2;
   const uint32_t acc_stride = (uint32_t)p.acc_stride, tmem_base = c.tmem_base;
@@ -889,7 +893,9 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int nsx = mode == 2 ? 3 : 1, nr = mode == 0 ? 1 : 3;
       const bool skip_a = (p.debug & 8) != 0, combined = p.combined != 0;
       const int b_stride = p.b_stride;
-      for (int i = first; i < p.items; i += stride_items) {
+      const int ksplit = p.ksplit;
+      for (int is = first; is < p.items; is += stride_items) {
+        const int i = is / ksplit, split = is - i * ksplit;            // split-K (mode 0 only): this item's share of the taps
         const int nt = i % n_tiles, mp = i / n_tiles;
         const int nrow = nt * block_n + b_row_off;
         const int m0 = cg2 ? (mp * 2 + cta_rank) * mt : mp * mt, m1 = m0 + 1;
@@ -899,8 +905,8 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int an1 = (m1 / tiles_xy) * p.tn;
         // mode 0 walks taps outer / channel chunks inner (the accumulation order of the first persistent kernel, so
         // either kernel yields the same bits); the halo modes walk chunks outer / boxes inner
-        const int n_outer = mode == 0 ? nby * nbx : cchunks, n_inner = mode == 0 ? cchunks : nbx;
-        int dy = 0, dx = 0;
+        const int n_outer = (mode == 0 ? nby * nbx : cchunks) / ksplit, n_inner = mode == 0 ? cchunks : nbx;
+        int dy = (split * n_outer) / nbx, dx = (split * n_outer) % nbx;
         for (int o = 0; o < n_outer; ++o) {
           for (int in = 0; in < n_inner; ++in) {
             const int c0 = (mode == 0 ? in : o) * kchunk;
@@ -1061,7 +1067,9 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int cx = ix < 0 ? 0 : (ix + p.kw - 1 >= p.W ? 2 : 1);
           cls = cy * 3 + cx;
         }
-        const float* bias_row = s_bias + cls * p.cout_p;
+        // split-K: the first split carries the bias (the slope table is all zeros without PReLU), each split its own plane
+        const float* bias_row = t.split ? s_slope : s_bias + cls * p.cout_p;
+        uint8_t* out_base = reinterpret_cast<uint8_t*>(p.out) + (size_t)t.split * (size_t)p.split_stride * 4;
         const size_t pix = ((size_t)on * p.Ho + oy) * p.Wo + ox;
         size_t res_pix = pix;
         if (p.res_mode == 2) {
@@ -1087,7 +1095,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   load16_as_float(reinterpret_cast<const uint8_t*>(p.residual) + (res_pix * p.cout_p + c) * 2, p.is_bf16, rs);
                 epi_math16(p, r + h * 16, bias_row, s_slope, c, p.res_mode ? rs : nullptr, f);
                 if (!(p.debug & 1))
-                  store16(reinterpret_cast<uint8_t*>(p.out) + (pix * p.cout_p + c) * esz, p.out_dtype, f);
+                  store16(out_base + (pix * p.cout_p + c) * esz, p.out_dtype, f);
               }
             }
           }
@@ -1109,6 +1117,19 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     if constexpr (CG2) tmem_dealloc2(tmem_base, 512);
     else tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// sum of the split-K partial planes, split 0 first (fixed order: the result is reproducible bit for bit)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float4* __restrict__ ws, int ksplit, long long n4,
+                                                            float4* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = ws[i];
+    for (int s = 1; s < ksplit; ++s) {
+      const float4 b = ws[(long long)s * n4 + i];
+      a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+    }
+    out[i] = a;
   }
 }
 
@@ -1361,6 +1382,21 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
   p.stg_box_bytes = p.tw * p.th * p.tn * p.ochunk * 2;
   p.combined = (p.a_mode == 0 && !p.b_resident) ? 1 : 0;
   if (p.cg2) p.items = n_tiles * ((p.m_tiles + 2 * p.mt - 1) / (2 * p.mt));      // an item = 2 x mt M tiles, mt per CTA
+  // split-K for long-K layers with a handful of work items (the 7 x 7 x 512 -> 512 embedding layer: 16 items of 392 K
+  // chunks for 148 SMs, bound by what one SM can pull from L2): the taps are dealt to `ksplit` items per tile, which store
+  // fp32 partial sums into the caller's workspace; splitk_reduce_kernel adds them in a fixed order.  The choice depends on
+  // the layer and the workspace only, never on the batch, so an image's result does not depend on its batch mates.
+  p.ksplit = 1;
+  if (d->splitk_ws != nullptr && p.combined && !p.epi_tma && d->out_dtype == 2 && p.sc_cchunks == 0 && p.res_mode == 0 &&
+      d->act == 0 && d->bias_classes == 1 && taps * p.cchunks >= 128) {
+    int ks = 8;
+    while (ks > 1 && taps % ks != 0) --ks;
+    const long long plane = (long long)d->n * Ho * Wo * d->cout_p;
+    if (ks > 1 && d->splitk_ws_bytes >= (long long)ks * plane * 4) {
+      p.ksplit = ks, p.split_stride = plane, p.items *= ks;
+      p.out = d->splitk_ws;
+    }
+  }
   p.b_stride = p.combined ? p.b_tile_bytes + p.a_stage_bytes : p.b_tile_bytes;
   if (p.combined) p.stages_a = 0;                      // activation boxes live inside the weight stages
   p.off_b = p.stages_a * p.a_stage_bytes;
@@ -1477,6 +1513,14 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
     B2F_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tile_kernel<false>, tmA, tmB, tmO, tmR, tmA2, tmB2, p));
   }
   g_launches.fetch_add(1);
+  if (p.ksplit > 1) {
+    const long long n4 = p.split_stride / 4;              // cout_p is a multiple of 16
+    const int blocks = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(d->splitk_ws), p.ksplit, n4,
+                                                      reinterpret_cast<float4*>(d->out));
+    g_launches.fetch_add(1);
+    B2F_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -158,7 +158,10 @@ class NetEngine:
             backing[op.dst] = raw
             view = raw[:n * per_image].view(torch.float32 if spec.f32 else torch_dtype(self.dtype))
             tens[op.dst] = view.view(n, spec.h, spec.w, spec.cp)
-            bound.append(self._bind_op(i, op, n, tens))
+            ws = alloc(8 * cap * per_image) if self._wants_splitk(op, spec) else None    # lives for this launch only
+            bound.append(self._bind_op(i, op, n, tens, ws))
+            if ws is not None:
+                free.append(ws)
             for name in (op.src, op.residual, op.sc_src):
                 if name and name in backing and self._last_use.get(name) == i and name not in self._out_tensors:
                     free.append(backing.pop(name))
@@ -174,7 +177,18 @@ class NetEngine:
         return (op.residual in backing and op.residual not in (op.src, op.sc_src) and self._last_use.get(op.residual) == i
                 and op.residual not in self._out_tensors and not d.f32 and not r.f32 and (r.h, r.w, r.cp) == (d.h, d.w, d.cp))
 
-    def _bind_op(self, i: int, op: FusedOp, n: int, tens: Dict[str, torch.Tensor]) -> _Bound:
+    @staticmethod
+    def _wants_splitk(op: FusedOp, spec_out) -> bool:
+        """Layers `b2f_conv2d` may split along K (include/b2f.h, `splitk_ws`): an fp32 output without activation or
+        residual and a long reduction -- the embedding layer (Flatten + Gemm as a 7 x 7 valid convolution)."""
+        a = op.attrs
+        if os.environ.get("B2F_SPLITK", "1") == "0":          # A/B knob for bench.py
+            return False
+        return (op.kind == "conv" and spec_out.f32 and op.act == 0 and not op.residual and not op.sc_src
+                and a["bias_classes"] == 1 and a["kh"] * a["kw"] >= 16)
+
+    def _bind_op(self, i: int, op: FusedOp, n: int, tens: Dict[str, torch.Tensor],
+                 ws: Optional[torch.Tensor] = None) -> _Bound:
         a, w = op.attrs, self._weights[i]
         lib = self.lib
         src, dst = tens[op.src], tens[op.dst]
@@ -204,7 +218,9 @@ class NetEngine:
             if sc is not None:                      # projection shortcut fused as extra K
                 d.sc_in, d.sc_weight = sc.data_ptr(), w["sc_weight"].data_ptr()
                 d.sc_cin_p, d.sc_stride, d.sc_h, d.sc_w = self.plan.tensors[op.sc_src].cp, a["sc_stride"], a["sc_h"], a["sc_w"]
-            return _Bound(lib.b2f_conv2d, (C.byref(d),), (d, src, dst, res, sc))
+            if ws is not None:
+                d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), ws.numel()
+            return _Bound(lib.b2f_conv2d, (C.byref(d),), (d, src, dst, res, sc, ws))
         if op.kind == "im2col":
             return _Bound(lib.b2f_im2col3x3,
                           (src.data_ptr(), n, a["h"], a["w"], a["stride"], a["ho"], a["wo"], self.dtype, dst.data_ptr()),

@@ -95,15 +95,13 @@ def draw_bbox(image, bbox, color=(0, 255, 0), thickness=3, proportion=0.2):
 
 
 def draw_bbox_info(frame, bbox, similarity, name, color):
+    """Label, cornered box and similarity bar of one recognised face, on a host frame  -- utils/helpers.py:155-179.
+    Same cv2 calls as the reference, so the same pixels (tests/test_overlay_host.py); `overlay.FrameOverlay` paints the
+    identical overlay on frames that stay on the GPU."""
     import cv2
     x1, y1, x2, y2 = map(int, bbox)
-    label = f"{name}: {similarity:.2f}"
-    (tw, th), _ = cv2.getTextSize(label, cv2.FONT_HERSHEY_SIMPLEX, 1, 2)
-    cv2.rectangle(frame, (x1, y1 - th - 10), (x1 + tw, y1), color, cv2.FILLED)
-    cv2.putText(frame, label, (x1, y1 - 5), cv2.FONT_HERSHEY_SIMPLEX, 1, (255, 255, 255), 2)
+    cv2.putText(frame, f"{name}: {similarity:.2f}", org=(x1, y1 - 10), fontFace=cv2.FONT_HERSHEY_COMPLEX_SMALL,
+                fontScale=1, color=color, thickness=1)
     draw_bbox(frame, bbox, color)
-    bar_w, bar_h = 8, y2 - y1
-    fill = int(bar_h * float(similarity))
-    cv2.rectangle(frame, (x2 + 5, y1), (x2 + 5 + bar_w, y2), color, 1)
-    cv2.rectangle(frame, (x2 + 5, y2 - fill), (x2 + 5 + bar_w, y2), color, cv2.FILLED)
-    return frame
+    bar_x, bar_top = x2 + 10, y2 - int(similarity * (y2 - y1))       # a bar right of the box, filled from the bottom
+    cv2.rectangle(frame, (bar_x, bar_top), (bar_x + 10, y2), color, cv2.FILLED)

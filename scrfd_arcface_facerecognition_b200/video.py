@@ -9,7 +9,8 @@ thousands of faces per second that loop is the bottleneck, so this module keeps 
                     while batch i is being processed
   * `VideoRunner`   detect -> align -> embed -> match for a whole batch (`FacePipeline`), then per frame the list the
                     reference would have drawn: (bbox int32[4], name or "Unknown", similarity), with the reference's
-                    strict `>` matching rule (main.py:136-142) and its drawing calls (draw_bbox_info / draw_bbox)
+                    strict `>` matching rule (main.py:136-142) and its drawing calls (draw_bbox_info / draw_bbox),
+                    on the host frame with cv2 or on the device batch with one kernel (`overlay.FrameOverlay`)
 
 Enrolment (`build_targets`, main.py:78-105) is `VideoRunner.enroll(images_with_names)`: largest face of each image.
 """
@@ -116,13 +117,19 @@ class VideoRunner:
         return list(self.names)
 
     # ---- reference frame_processor over a whole stream (main.py:108-188) ------------------------------------
-    def run(self, source, on_frame: Optional[Callable[[np.ndarray, list], None]] = None, draw: bool = False) -> List[list]:
+    def run(self, source, on_frame: Optional[Callable[[np.ndarray, list], None]] = None, draw=False) -> List[list]:
         """For every frame: [(bbox int32[4], name | "Unknown", similarity float)], in detection order.
-        `on_frame(frame, faces)` is called per frame (e.g. a cv2.VideoWriter.write); `draw` overlays the reference's
-        boxes and labels on the host frame first."""
+        `on_frame(frame, faces)` is called per frame (e.g. a cv2.VideoWriter.write).  `draw=True` overlays the
+        reference's boxes and labels on the host frame first (cv2, as main.py:144-148 does); `draw="gpu"` paints the same
+        pixels on the batch while it is still in HBM (`overlay.FrameOverlay`, one kernel per batch) and copies the drawn
+        frames back over the host frames."""
         from . import helpers
         results: List[list] = []
         colors: Dict[str, tuple] = {}
+        overlay = None
+        if draw == "gpu":
+            from .overlay import FrameOverlay
+            overlay = FrameOverlay()
         for dev_batch, n, frames in FrameFeeder(source, self.batch):
             out = self.pipe.process(dev_batch)
             det = out["det"][:n].cpu().numpy()
@@ -130,6 +137,7 @@ class VideoRunner:
             if len(self.names):
                 score = out["match_score"][:n].cpu().numpy()
                 idx = out["match_idx"][:n].cpu().numpy()
+            batch_faces = []
             for f in range(n):
                 faces = []
                 for s in range(int(counts[f])):
@@ -138,13 +146,20 @@ class VideoRunner:
                     if len(self.names) and idx[f, s] >= 0:
                         name, sim = self.names[int(idx[f, s])], float(score[f, s])
                     faces.append((bbox, name, sim))
-                    if draw:
+                    if name != "Unknown" and draw:
+                        colors.setdefault(name, tuple(int(v) for v in np.random.default_rng(len(colors)).integers(0, 256, 3)))
+                    if draw is True:
                         if name != "Unknown":
-                            color = colors.setdefault(name, tuple(int(v) for v in np.random.default_rng(len(colors)).integers(0, 256, 3)))
-                            helpers.draw_bbox_info(frames[f], bbox, similarity=sim, name=name, color=color)
+                            helpers.draw_bbox_info(frames[f], bbox, similarity=sim, name=name, color=colors[name])
                         else:
                             helpers.draw_bbox(frames[f], bbox, (255, 0, 0))
-                results.append(faces)
+                batch_faces.append(faces)
+            if overlay is not None:
+                drawn = overlay.draw(dev_batch[:n], batch_faces, colors).cpu().numpy()
+                for f in range(n):
+                    np.copyto(frames[f], drawn[f])
+            for f in range(n):
+                results.append(batch_faces[f])
                 if on_frame is not None:
-                    on_frame(frames[f], faces)
+                    on_frame(frames[f], batch_faces[f])
         return results

@@ -13,7 +13,7 @@ def test_library_builds_and_loads():
     path = _lib.build()
     assert os.path.exists(path)
     lib = _lib.lib()
-    assert lib.b2f_version() == 3
+    assert lib.b2f_version() == 4
     assert lib.b2f_launch_count() == 0 or lib.b2f_launch_count() > 0
 
 

@@ -93,7 +93,7 @@ def _pad16(c):
 
 
 def run_conv(lib, x_nchw, w_oihw, bias, stride, pad, act=0, slope=None, residual=None, res_mode=0,
-             out_f32=False, bias_tab=None, dtype=0, force_kchunk=0, in_place=False):
+             out_f32=False, bias_tab=None, dtype=0, force_kchunk=0, in_place=False, splitk=False):
     """x (N,C,H,W) f32 torch cpu; returns (N,Cout,Ho,Wo) f32 cpu computed by b2f_conv2d."""
     tdt = torch.bfloat16 if dtype == 1 else torch.float16
     n, cin, h, w = x_nchw.shape
@@ -133,8 +133,13 @@ def run_conv(lib, x_nchw, w_oihw, bias, stride, pad, act=0, slope=None, residual
         out = keep[-1]
         d.residual = out.data_ptr()
     d.out = out.data_ptr()
+    before = lib.b2f_launch_count()
+    if splitk:                                    # the caller's workspace lets long-K fp32 layers split along K
+        keep.append(torch.full((8 * out.numel(),), float("nan"), dtype=torch.float32, device="cuda"))
+        d.splitk_ws, d.splitk_ws_bytes = keep[-1].data_ptr(), keep[-1].numel() * 4
     _lib.check(lib.b2f_conv2d(C.byref(d), sp()), "b2f_conv2d")
     torch.cuda.synchronize()
+    run_conv.launches = lib.b2f_launch_count() - before
     res = out.float().cpu()
     assert torch.isfinite(res).all(), "conv left unwritten / non-finite outputs"
     assert (res[..., cout:] == (0.5 if act == 3 else 0.0)).all(), "padding channels must stay neutral"
@@ -979,6 +984,27 @@ def test_clustering_results_written_from_gpu_labels(lib, tmp_path):
         assert {k: v for k, v in a.items() if k not in ("group_score", "visits")} == {k: v for k, v in b.items() if k not in ("group_score", "visits")}
         assert abs(a["group_score"] - b["group_score"]) <= 1e-3 + 1e-9
         assert abs(a["visits"][0]["similarity"] - b["visits"][0]["similarity"]) <= 2e-6
+
+
+@pytest.mark.parametrize("n,cin,k", [(4, 512, 7), (300, 512, 7), (1024, 512, 7), (130, 64, 5), (5, 256, 4)], ids=lambda v: str(v))
+def test_conv2d_split_k(lib, n, cin, k):
+    """the embedding layer (Flatten + Gemm as a k x k valid convolution over a k x k map) with a split-K workspace: the
+    filter taps are dealt to several work items per tile and a second kernel adds the fp32 partial sums; same result as
+    the unsplit launch up to the order of the fp32 additions, and independent of the batch"""
+    g = torch.Generator().manual_seed(n + cin + k)
+    x = _q(torch.randn((n, cin, k, k), generator=g))
+    w = _q(torch.randn((512, cin, k, k), generator=g) * (1.0 / (cin * k * k)) ** 0.5)
+    b = torch.randn(512, generator=g) * 0.1
+    ref = F.conv2d(x, w, b)
+    plain = run_conv(lib, x, w, b, 1, 0, out_f32=True)
+    assert run_conv.launches == 1
+    split = run_conv(lib, x, w, b, 1, 0, out_f32=True, splitk=True)
+    assert run_conv.launches == (2 if k * k * (cin // 64) >= 128 else 1)       # split only when K is long
+    scale = max(1.0, ref.abs().max().item())
+    assert (split - ref).abs().max().item() <= 2e-3 * scale
+    assert (split - plain).abs().max().item() <= 1e-4 * scale                # fp32 summation order only (K = 25 088)
+    first = run_conv(lib, x[:1], w, b, 1, 0, out_f32=True, splitk=True)      # an image's bits do not depend on its batch mates
+    assert torch.equal(first[0], split[0])
 
 
 @pytest.mark.parametrize("n,cin,k,f32", [(4, 64, 7, True), (4, 64, 7, False), (3, 512, 3, True), (1, 128, 1, True)],

@@ -324,6 +324,11 @@ def test_video_runner_matches_the_per_frame_reference_loop():
     drawn = [f.copy() for f in frames[:4]]
     runner.run(drawn, draw=True)
     assert any((d != f).any() for d, f in zip(drawn, frames[:4]))
+    # ... and the overlay painted on the device batch (one kernel per batch) is the same image, byte for byte
+    drawn_gpu = [f.copy() for f in frames[:4]]
+    runner.run(drawn_gpu, draw="gpu")
+    for a, b in zip(drawn, drawn_gpu):
+        np.testing.assert_array_equal(a, b)
     # the feeder alone: batches of 4, 4, 2 with the frames intact
     sizes = []
     for dev_batch, n, kept in FrameFeeder(frames, 4):
