@@ -405,6 +405,10 @@ __device__ __forceinline__ void epilogue_pool(const TileParams& p, const EpiCtx&
   const int pcol = lx == 7 ? 4 : ((lx & 1) ? -1 : (lx >> 1));
   const bool holder = prow >= 0 && pcol >= 0;
   const uint32_t dst_off = holder ? (uint32_t)((prow * kPoolW + pcol) * 64) : 0u;
+  // which neighbours a lane's window takes in (see the loop below): none to the left of column 0, none at all for
+  // column 7; the row above only for row 2, the row below for rows 0 and 2
+  const uint32_t m_left = (lx > 0 && lx < 7) ? 0xFFFFFFFFu : 0u, m_right = lx < 7 ? 0xFFFFFFFFu : 0u;
+  const uint32_t m_up = lr == 2 ? 0xFFFFFFFFu : 0u, m_down = (lr == 0 || lr == 2) ? 0xFFFFFFFFu : 0u;
   int k = 0;
   for (int tl = 0; tl < my_tiles; ++tl) {
     const int seq = group + tl * G;
@@ -447,26 +451,22 @@ __device__ __forceinline__ void epilogue_pool(const TileParams& p, const EpiCtx&
           v[2 * q4] = *reinterpret_cast<uint32_t*>(&h0), v[2 * q4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
         }
       }
-      if (!in_image) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0u;
-      }
+      // Branch-free window maxima.  Everything is a ReLU output (>= +0), so a neighbour that must not take part is
+      // replaced by +0, the identity of the maximum, with lane masks -- lane-dependent `if`s around the shuffles compile
+      // to divergent branches with a reconvergence barrier per register (ncu: the vertical shuffles stalled on
+      // branch resolving for a quarter of all samples).
+      const uint32_t m_img = in_image ? 0xFFFFFFFFu : 0u;           // a tile may overhang the right / bottom edge
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
+        const uint32_t x = v[i] & m_img;
         // horizontal: columns lx-1, lx, lx+1 of this row, clipped to the strip; column 7 also serves, alone, the window
         // centred on column 8 (which belongs to the next tile)
-        const uint32_t left = __shfl_up_sync(0xFFFFFFFFu, v[i], 1), right = __shfl_down_sync(0xFFFFFFFFu, v[i], 1);
-        uint32_t h = v[i];
-        if (lx > 0) h = hmax2u<BF16>(h, left);
-        if (lx < 7) h = hmax2u<BF16>(h, right);
-        const uint32_t hs = lx == 7 ? v[i] : h;
+        const uint32_t left = __shfl_up_sync(0xFFFFFFFFu, x, 1) & m_left, right = __shfl_down_sync(0xFFFFFFFFu, x, 1) & m_right;
+        const uint32_t hs = hmax2u<BF16>(hmax2u<BF16>(x, left), right);
         // vertical: rows lr-1, lr, lr+1 of the strip.  Row 0 centres the window whose upper row lies in the strip above,
         // row 2 a complete window, row 3 alone serves the window centred on the row below the strip
-        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, hs, 8), down = __shfl_down_sync(0xFFFFFFFFu, hs, 8);
-        uint32_t o = hs;
-        if (lr == 0) o = hmax2u<BF16>(hs, down);
-        if (lr == 2) o = hmax2u<BF16>(hmax2u<BF16>(up, hs), down);
-        v[i] = o;
+        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, hs, 8) & m_up, down = __shfl_down_sync(0xFFFFFFFFu, hs, 8) & m_down;
+        v[i] = hmax2u<BF16>(hmax2u<BF16>(up, hs), down);
       }
       uint8_t* buf = pbuf_warp + (k & 1) * kPoolBufBytes;
       if (lane == 0) bulk_wait_read1();                  // the reduce-store issued two slices ago has left this buffer
