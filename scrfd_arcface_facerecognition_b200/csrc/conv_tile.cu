@@ -50,6 +50,23 @@ constexpr int kStgBufs = 3;
 constexpr int kSmemMax = 227 * 1024;
 constexpr int kTileDeclined = -1000;
 
+// Division by a launch-invariant divisor: q = (x * mul) >> shift, exact for 0 <= x < 2^31 (mul = ceil(2^shift / d),
+// shift = 31 + ceil(log2 d)).  The producer thread turns a work-item index into tile coordinates once per tile; with
+// hardware-emulated `/` and `%` (eight of them, ~200 dependent clocks each) that chain alone took ~1500 clocks per tile
+// and bounded every layer whose tile has fewer MMA clocks than that (the 32- and 64-channel layers).
+struct FastDiv {
+  uint32_t mul, shift, d;
+  __host__ void set(int div) {
+    d = (uint32_t)div;
+    uint32_t s = 0;
+    while ((1u << s) < d) ++s;
+    shift = 31 + s;
+    mul = (uint32_t)((((unsigned long long)1 << shift) + d - 1) / d);
+  }
+  __device__ __forceinline__ int div(int x) const { return (int)(((unsigned long long)(uint32_t)x * mul) >> shift); }
+  __device__ __forceinline__ void divmod(int x, int& q, int& r) const { q = div(x), r = x - q * (int)d; }
+};
+
 struct TileParams {
   int N, Ho, Wo, H, W, cout_p;
   int kh, kw, stride, pad;
@@ -79,6 +96,7 @@ struct TileParams {
   const void* residual;
   int res_mode, res_h, res_w;
   int off_b, off_stg, off_bar, off_tab;
+  FastDiv fd_ntiles, fd_tx, fd_ty, fd_mt, fd_ksplit;   // n_tiles, tiles_x, tiles_y, mt, ksplit
   int ksplit;               // split-K: an item covers taps [split * taps / ksplit, +taps / ksplit) and stores fp32 partial sums
   long long split_stride;   // floats between the partial outputs of consecutive splits (p.out is then the workspace)
 };
@@ -245,18 +263,18 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord tile_of(const TileParams& p, int first, int stride, int rank, int seq) {
   // an item = `pair` consecutive M tiles of one N tile: mt tiles of one CTA, or one tile for each CTA of a pair
-  const int l = seq / p.mt, u = seq - l * p.mt;
-  const int is = first + l * stride;
-  const int i = is / p.ksplit;
-  const int nt = i % p.n_tiles, mp = i / p.n_tiles;
-  const int m_tile = p.cg2 ? (mp * 2 + rank) * p.mt + u : mp * p.mt + u;
-  const int tiles_xy = p.tiles_x * p.tiles_y;
+  int l, u, i, nt, mp, tx, ty, tyx, tn;
   TileCoord t;
-  t.split = is - i * p.ksplit;
+  p.fd_mt.divmod(seq, l, u);
+  p.fd_ksplit.divmod(first + l * stride, i, t.split);
+  p.fd_ntiles.divmod(i, mp, nt);
+  const int m_tile = p.cg2 ? (mp * 2 + rank) * p.mt + u : mp * p.mt + u;
+  p.fd_tx.divmod(m_tile, tyx, tx);
+  p.fd_ty.divmod(tyx, tn, ty);
   t.m_tile = m_tile;
-  t.x0 = (m_tile % p.tiles_x) * p.tw;
-  t.y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.th;
-  t.n0 = (m_tile / tiles_xy) * p.tn;
+  t.x0 = tx * p.tw;
+  t.y0 = ty * p.th;
+  t.n0 = tn * p.tn;
   t.cbase = nt * p.block_n;
   return t;
 }
@@ -289,15 +307,21 @@ __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& 
   }
   const bool skip_math = (p.debug & 16) != 0, skip_store = (p.debug & 1) != 0;
   const int stg_bytes = p.stg_bytes, sig_hi = p.sig_hi, cout_p = p.cout_p;
-  auto issue_res = [&](int s) {                                      // leader only: residual slice of sub s
-    const TileCoord t = tile_of(p, c.first, c.stride, c.rank, group + (s / n_sub) * G);
-    const int buf = s % NB;
-    mbar_arrive_expect_tx(&c.rbar[buf], (uint32_t)p.stg_box_bytes);
-    tma_load_4d(c.stg + (size_t)buf * stg_bytes, c.tmR, &c.rbar[buf], t.cbase + (s % n_sub) * och, t.x0, t.y0, t.n0);
+  // running (tile, slice, buffer) of the residual prefetch, NB - 1 slices ahead of the arithmetic: no `/` or `%` by
+  // launch-time values on the per-slice path (each is ~200 dependent clocks)
+  int rs_tile = 0, rs_sub = 0, rs_buf = 0, rs_s = 0;
+  auto issue_res = [&]() {                                           // leader only: residual slice rs_s
+    const TileCoord t = tile_of(p, c.first, c.stride, c.rank, group + rs_tile * G);
+    mbar_arrive_expect_tx(&c.rbar[rs_buf], (uint32_t)p.stg_box_bytes);
+    tma_load_4d(c.stg + (size_t)rs_buf * stg_bytes, c.tmR, &c.rbar[rs_buf], t.cbase + rs_sub * och, t.x0, t.y0, t.n0);
+    ++rs_s;
+    if (++rs_sub == n_sub) rs_sub = 0, ++rs_tile;
+    if (++rs_buf == NB) rs_buf = 0;
   };
   if (RES == 1 && c.leader)
-    for (int s = 0; s < NB - 1 && s < total_sub; ++s) issue_res(s);
-  int k = 0;
+    for (int s = 0; s < NB - 1 && s < total_sub; ++s) issue_res();
+  int k = 0, buf = 0;
+  uint32_t buf_phase = 0;                                            // (k / NB) & 1
   for (int tl = 0; tl < my_tiles; ++tl) {
     const int seq = group + tl * G;
     const TileCoord t = tile_of(p, c.first, c.stride, c.rank, seq);
@@ -323,7 +347,6 @@ __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& 
     tc_fence_after();
     const uint32_t t_addr = c.tmem_base + ((uint32_t)(c.q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
     for (int j = 0; j < n_sub; ++j, ++k) {
-      const int buf = k % NB;
       uint8_t* bufp = c.stg + (size_t)buf * stg_bytes;
       uint32_t r[32];
       if (och == 16) {
@@ -344,7 +367,7 @@ __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& 
           else mbar_arrive(&c.tempty[acc]);
         }
       }
-      if (RES == 1) mbar_wait(&c.rbar[buf], (uint32_t)(k / NB) & 1u);
+      if (RES == 1) mbar_wait(&c.rbar[buf], buf_phase);
       if (!skip_math) {
         const int cl = j * och;
         const uint4* g0 = (RES == 2 && gres_row) ? reinterpret_cast<const uint4*>(gres_row + cl * 2) : nullptr;
@@ -359,7 +382,7 @@ __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& 
         // the store issued one slice ago has had this slice's arithmetic to leave its buffer; once it has, the
         // residual of the slice two steps ahead may land there
         bulk_wait_read0();
-        if (RES == 1 && k + NB - 1 < total_sub) issue_res(k + NB - 1);
+        if (RES == 1 && rs_s < total_sub) issue_res();
       }
       bar_sync_named(1 + group, 128);
       if (c.leader && !skip_store) {
@@ -367,6 +390,7 @@ __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& 
         else tma_store_4d(c.tmO, bufp, t.cbase + j * och, t.x0, t.y0, t.n0);
         bulk_commit();
       }
+      if (++buf == NB) buf = 0, buf_phase ^= 1u;
     }
   }
   if (c.leader) bulk_wait_all();
@@ -812,7 +836,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int boxes = p.boxes_per_chunk, tpb = p.taps_per_box, kw = p.kw, block_n = p.block_n;
       const int stages_a = p.stages_a, stages_b = p.stages_b;
       const int a_stage_bytes = p.a_stage_bytes, a_box_bytes = p.a_box_bytes, b_tile_bytes = p.b_tile_bytes;
-      const int tiles_x = p.tiles_x, tiles_y = p.tiles_y, tiles_xy = tiles_x * tiles_y;
+      const int tiles_x = p.tiles_x, tiles_y = p.tiles_y;
       const int sx_scale = p.tw * p.stride, sy_scale = p.th * p.stride, org = mode == 0 ? p.pad : 1;
       const bool resident = p.b_resident != 0;
       const uint32_t a_tx = (uint32_t)(p.a_bytes * mt);
@@ -843,7 +867,10 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           int sa = 0;
           uint32_t pa = 0;
           for (int i = first; i < p.items; i += stride_items) {
-            const int ax = (i % tiles_x) * p.tw - 1, ay = ((i / tiles_x) % tiles_y) * p.th - 1, an = i / tiles_xy;
+            int tyx, tx, ty, an;
+            p.fd_tx.divmod(i, tyx, tx);
+            p.fd_ty.divmod(tyx, an, ty);
+            const int ax = tx * p.tw - 1, ay = ty * p.th - 1;
             mbar_wait(&emptyA[sa], pa ^ 1);
             mbar_arrive_expect_tx(&fullA[sa], (uint32_t)kStemBoxBytes);
             tma_load_3d(a_ring + (size_t)sa * kStemBoxStage, &tmA, &fullA[sa], ax * 8, ay, an);
@@ -859,7 +886,10 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           int sa = 0;
           uint32_t pa = 0;
           for (int i = first; i < p.items; i += stride_items) {
-            const int ax = (i % tiles_x) * sxs - p.pad, ay = ((i / tiles_x) % tiles_y) * sys - p.pad, an = (i / tiles_xy) * p.tn;
+            int tile_yz, tile_x, tile_y, tile_z;
+            p.fd_tx.divmod(i, tile_yz, tile_x);
+            p.fd_ty.divmod(tile_yz, tile_z, tile_y);
+            const int ax = tile_x * sxs - p.pad, ay = tile_y * sys - p.pad, an = tile_z * p.tn;
             mbar_wait(&emptyA[sa], pa ^ 1);
             mbar_arrive_expect_tx(&fullA[sa], tx);
             uint8_t* dst = a_ring + (size_t)sa * a_stage_bytes;
@@ -893,20 +923,23 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int nsx = mode == 2 ? 3 : 1, nr = mode == 0 ? 1 : 3;
       const bool skip_a = (p.debug & 8) != 0, combined = p.combined != 0;
       const int b_stride = p.b_stride;
-      const int ksplit = p.ksplit;
+      // mode 0 walks taps outer / channel chunks inner (the accumulation order of the first persistent kernel, so
+      // either kernel yields the same bits); the halo modes walk chunks outer / boxes inner
+      const int n_outer = (mode == 0 ? nby * nbx : cchunks) / p.ksplit, n_inner = mode == 0 ? cchunks : nbx;
       for (int is = first; is < p.items; is += stride_items) {
-        const int i = is / ksplit, split = is - i * ksplit;            // split-K (mode 0 only): this item's share of the taps
-        const int nt = i % n_tiles, mp = i / n_tiles;
+        int i, split, nt, mp, tyx, tx, ty, tz;                         // split-K (mode 0 only): this item's share of the taps
+        p.fd_ksplit.divmod(is, i, split);
+        p.fd_ntiles.divmod(i, mp, nt);
         const int nrow = nt * block_n + b_row_off;
         const int m0 = cg2 ? (mp * 2 + cta_rank) * mt : mp * mt, m1 = m0 + 1;
-        const int ax0 = (m0 % tiles_x) * sx_scale - org, ay0 = ((m0 / tiles_x) % tiles_y) * sy_scale - org;
-        const int an0 = (m0 / tiles_xy) * p.tn;
-        const int ax1 = (m1 % tiles_x) * sx_scale - org, ay1 = ((m1 / tiles_x) % tiles_y) * sy_scale - org;
-        const int an1 = (m1 / tiles_xy) * p.tn;
-        // mode 0 walks taps outer / channel chunks inner (the accumulation order of the first persistent kernel, so
-        // either kernel yields the same bits); the halo modes walk chunks outer / boxes inner
-        const int n_outer = (mode == 0 ? nby * nbx : cchunks) / ksplit, n_inner = mode == 0 ? cchunks : nbx;
-        int dy = (split * n_outer) / nbx, dx = (split * n_outer) % nbx;
+        p.fd_tx.divmod(m0, tyx, tx);
+        p.fd_ty.divmod(tyx, tz, ty);
+        const int ax0 = tx * sx_scale - org, ay0 = ty * sy_scale - org, an0 = tz * p.tn;
+        // the second tile of an mt = 2 item is the next tile in raster order
+        if (++tx == tiles_x) { tx = 0; if (++ty == tiles_y) ty = 0, ++tz; }
+        const int ax1 = tx * sx_scale - org, ay1 = ty * sy_scale - org, an1 = tz * p.tn;
+        int dy = 0, dx = 0;
+        if (split) dy = (split * n_outer) / nbx, dx = (split * n_outer) % nbx;
         for (int o = 0; o < n_outer; ++o) {
           for (int in = 0; in < n_inner; ++in) {
             const int c0 = (mode == 0 ? in : o) * kchunk;
@@ -1397,6 +1430,7 @@ static int conv_tile_plan_launch(const b2f_conv_desc* d, int kchunk, cudaStream_
       p.out = d->splitk_ws;
     }
   }
+  p.fd_ntiles.set(p.n_tiles), p.fd_tx.set(p.tiles_x), p.fd_ty.set(p.tiles_y), p.fd_mt.set(p.mt), p.fd_ksplit.set(p.ksplit);
   p.b_stride = p.combined ? p.b_tile_bytes + p.a_stage_bytes : p.b_tile_bytes;
   if (p.combined) p.stages_a = 0;                      // activation boxes live inside the weight stages
   p.off_b = p.stages_a * p.a_stage_bytes;
