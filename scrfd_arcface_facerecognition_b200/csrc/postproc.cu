@@ -188,12 +188,16 @@ letterbox_patches_kernel(const uint8_t* __restrict__ frames, ResizeGeom g, int s
 //   3. one thread issues four tcgen05.mma (2 tiles x K = 32 in two steps, M = 128, N = cout_p) into 2 x cout_p TMEM columns;
 //   4. each warp reads its TMEM lane quarter back (tcgen05.ld), adds the bias, applies ReLU and stores the pixel's 64
 //      bytes (a warp covers 2 KB of contiguous output).
+// The CTAs are persistent (four per SM): TMEM, the barrier, the normalisation table, weights and bias are set up once,
+// and the source pixels of the NEXT tile are fetched into registers (one packed register per pixel) while the tensor
+// core and the epilogue work on the current one, so the strided gather's latency is off the critical path.
 template <bool BF16, int COUT>
 __global__ void __launch_bounds__(kLpW * kLpH, 4)
 letterbox_conv1_kernel(const uint8_t* __restrict__ frames, ResizeGeom g, int ho, int wo, float mean, float scale,
                        const uint16_t* __restrict__ weight, const float* __restrict__ bias, int act,
-                       uint16_t* __restrict__ out) {
+                       uint16_t* __restrict__ out, int tiles_x, int tiles_y, int n_tiles) {
   constexpr int IW = kLpW * 2 + 1, IH = kLpH * 2 + 1;
+  constexpr int kSweeps = (IW * IH + kLpW * kLpH - 1) / (kLpW * kLpH);
   constexpr uint32_t kCols = 2 * COUT < 32 ? 32 : 2 * COUT;          // TMEM columns: two accumulators of COUT
   __shared__ __align__(1024) uint8_t a_tile[2 * 128 * 64];            // [m tile][row][32 k] 16-bit, SWIZZLE_64B
   __shared__ __align__(1024) uint8_t b_tile[COUT * 64];               // [cout][32 k] 16-bit, SWIZZLE_64B
@@ -202,10 +206,8 @@ letterbox_conv1_kernel(const uint8_t* __restrict__ frames, ResizeGeom g, int ho,
   __shared__ __align__(16) float s_bias[COUT];
   __shared__ __align__(8) uint64_t done_bar;
   __shared__ uint32_t tmem_slot;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.z, ox0 = blockIdx.x * kLpW, oy0 = blockIdx.y * kLpH;
-  const int ix0 = ox0 * 2 - 1, iy0 = oy0 * 2 - 1;
-  const uint8_t* img = frames + (size_t)b * g.H * g.W * 3;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  // ---- once per CTA (the CTA is persistent: it walks tiles blockIdx.x, + gridDim.x, ...) ----
   if (warp == 0) {
     tmem_alloc(&tmem_slot, kCols);
     tmem_relinquish();
@@ -220,133 +222,153 @@ letterbox_conv1_kernel(const uint8_t* __restrict__ frames, ResizeGeom g, int ho,
     const uint32_t o = (uint32_t)c * 16;
     *reinterpret_cast<uint4*>(b_tile + (o ^ (((o >> 7) & 3u) << 4))) = __ldg(reinterpret_cast<const uint4*>(weight) + c);
   }
-  __syncthreads();                                                    // the table is complete
-  // source pixels of the tile, normalised once.  The sweeps over the tile are unrolled with every load ahead of the
-  // first use, so a thread's loads are in flight together; the odd-ratio and copy modes (1080p -> 640 x 360 is
-  // img[1::3, 1::3]) take a byte-offset fast path, the general bilinear / 2x-area modes go through letterbox_pixel.
-  const bool direct = g.mode == 0 || g.mode == 3;
-  const int ratio = g.mode == 3 ? g.ratio : 1, roff = (ratio - 1) >> 1;
-  {
-    constexpr int kSweeps = (IW * IH + kLpW * kLpH - 1) / (kLpW * kLpH);
-    int bgr[kSweeps][3];
-    bool in[kSweeps];
-#pragma unroll
-    for (int i = 0; i < kSweeps; ++i) {                       // all loads of the CTA's sweeps are issued before any use
-      const int t = tid + i * (kLpW * kLpH);
-      const int ty = t / IW, tx = t - ty * IW;
-      const int iy = iy0 + ty, ix = ix0 + tx;
-      bgr[i][0] = bgr[i][1] = bgr[i][2] = 0;
-      in[i] = t < IW * IH && ix >= 0 && ix < g.in_w && iy >= 0 && iy < g.in_h;
-      if (in[i]) {
-        if (direct) {
-          if (ix < g.new_w && iy < g.new_h) {
-            const uint8_t* px = img + ((size_t)(iy * ratio + roff) * g.W + (ix * ratio + roff)) * 3;
-            bgr[i][0] = px[0], bgr[i][1] = px[1], bgr[i][2] = px[2];
-          }
-        } else {
-          letterbox_pixel(img, g, ix, iy, bgr[i]);
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < kSweeps; ++i) {
-      const int t = tid + i * (kLpW * kLpH);
-      uint2 v = make_uint2(0u, 0u);
-      if (in[i]) {
-        v.x = lut[bgr[i][2]] | ((uint32_t)lut[bgr[i][1]] << 16);      // R, G
-        v.y = lut[bgr[i][0]];                                         // B, 0
-      }
-      if (t < IW * IH) *reinterpret_cast<uint2*>(tile + t * 4) = v;
-    }
-  }
+  fence_proxy_async();                                                // the weight tile is read by the tensor core
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  // A operand: thread (ly, lx) = row (tid & 127) of M tile (tid >> 7); k = tap * 3 + rgb, 27 used
+  const bool direct = g.mode == 0 || g.mode == 3;
+  const int ratio = g.mode == 3 ? g.ratio : 1, roff = (ratio - 1) >> 1;
   const int lx = tid & (kLpW - 1), ly = tid / kLpW;
-  {
-    uint16_t v[32];
+  const int tiles_xy = tiles_x * tiles_y;
+
+  // source pixels of a tile as packed b | g << 8 | r << 16 | inside << 24, one register per sweep.  The odd-ratio and
+  // copy modes (1080p -> 640 x 360 is img[1::3, 1::3]) take a byte-offset fast path, the general bilinear / 2x-area modes
+  // go through letterbox_pixel.  All loads of a thread are issued before the first use.
+  auto fetch = [&](int t_idx, uint32_t (&px)[kSweeps]) {
+    const int b = t_idx / tiles_xy, rem = t_idx - b * tiles_xy;
+    const int ty0 = rem / tiles_x, tx0 = rem - ty0 * tiles_x;
+    const int ix0 = tx0 * kLpW * 2 - 1, iy0 = ty0 * kLpH * 2 - 1;
+    const uint8_t* img = frames + (size_t)b * g.H * g.W * 3;
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const uint2 px = *reinterpret_cast<const uint2*>(tile + ((ly * 2 + tap / 3) * IW + lx * 2 + tap % 3) * 4);
-      v[tap * 3 + 0] = (uint16_t)(px.x & 0xFFFFu);           // R
-      v[tap * 3 + 1] = (uint16_t)(px.x >> 16);               // G
-      v[tap * 3 + 2] = (uint16_t)(px.y & 0xFFFFu);           // B
-    }
-#pragma unroll
-    for (int k = 27; k < 32; ++k) v[k] = 0;
-    uint8_t* row_base = a_tile + (tid >> 7) * (128 * 64);
-    const uint32_t row_off = (uint32_t)(tid & 127) * 64u;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t o = row_off + (uint32_t)j * 16;
-      *reinterpret_cast<uint4*>(row_base + (o ^ (((o >> 7) & 3u) << 4))) =
-          make_uint4(v[8 * j] | ((uint32_t)v[8 * j + 1] << 16), v[8 * j + 2] | ((uint32_t)v[8 * j + 3] << 16),
-                     v[8 * j + 4] | ((uint32_t)v[8 * j + 5] << 16), v[8 * j + 6] | ((uint32_t)v[8 * j + 7] << 16));
-    }
-  }
-  fence_proxy_async();                                        // generic-proxy writes -> visible to the tensor core
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (warp == 0) {
-    if (elect_one()) {
-      const uint32_t idesc = umma_idesc(128, COUT, BF16 ? 1u : 0u);
-      const uint64_t bd = umma_smem_desc(smem_u32(b_tile), 64);
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const uint64_t ad = umma_smem_desc(smem_u32(a_tile) + (uint32_t)mt * 128u * 64u, 64);
-        umma_f16(tmem_base + (uint32_t)mt * COUT, ad, bd, idesc, 0u);
-        umma_f16(tmem_base + (uint32_t)mt * COUT, ad + 2, bd + 2, idesc, 1u);
-      }
-      umma_commit(&done_bar);
-    }
-    __syncwarp();
-  }
-  mbar_wait(&done_bar, 0);
-  tc_fence_after();
-  // epilogue: warp w reads lanes 32 (w & 3) .. +31 of accumulator w >> 2, i.e. output row ly == w, pixel lx == lane
-  {
-    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * COUT;
-    uint32_t r[COUT];
-    if (COUT == 32) {
-      uint32_t (&r32)[32] = reinterpret_cast<uint32_t (&)[32]>(r);
-      tmem_ld32(taddr, r32);
-    } else {
-      uint32_t (&r16)[16] = reinterpret_cast<uint32_t (&)[16]>(r);
-      tmem_ld16(taddr, r16);
-    }
-    tmem_ld_wait();
-    const int oy = oy0 + ly, ox = ox0 + lx;
-    if (oy < ho && ox < wo) {
-      uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)b * ho + oy) * wo + ox) * COUT);
-#pragma unroll
-      for (int j = 0; j < COUT / 8; ++j) {
-        uint32_t w4[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float v0 = __uint_as_float(r[8 * j + 2 * i]) + s_bias[8 * j + 2 * i];
-          float v1 = __uint_as_float(r[8 * j + 2 * i + 1]) + s_bias[8 * j + 2 * i + 1];
-          if (act == 1) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f);
-          if (BF16) {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
-            w4[i] = *reinterpret_cast<uint32_t*>(&h2);
-          } else {
-            __half2 h2 = __floats2half2_rn(v0, v1);
-            w4[i] = *reinterpret_cast<uint32_t*>(&h2);
+    for (int i = 0; i < kSweeps; ++i) {
+      const int t = tid + i * (kLpW * kLpH);
+      const int ty = t / IW, tx = t - ty * IW;
+      const int iy = iy0 + ty, ix = ix0 + tx;
+      uint32_t v = 0;
+      if (t < IW * IH && ix >= 0 && ix < g.in_w && iy >= 0 && iy < g.in_h) {
+        int bgr[3] = {0, 0, 0};
+        if (direct) {
+          if (ix < g.new_w && iy < g.new_h) {
+            const uint8_t* p = img + ((size_t)(iy * ratio + roff) * g.W + (ix * ratio + roff)) * 3;
+            bgr[0] = p[0], bgr[1] = p[1], bgr[2] = p[2];
           }
+        } else {
+          letterbox_pixel(img, g, ix, iy, bgr);
         }
-        dst[j] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        v = (uint32_t)bgr[0] | ((uint32_t)bgr[1] << 8) | ((uint32_t)bgr[2] << 16) | (1u << 24);
+      }
+      px[i] = v;
+    }
+  };
+
+  uint32_t px[kSweeps];
+  int t_idx = blockIdx.x;
+  if (t_idx < n_tiles) fetch(t_idx, px);
+  uint32_t phase = 0;
+  for (; t_idx < n_tiles; t_idx += gridDim.x) {
+    const int b = t_idx / tiles_xy, rem = t_idx - b * tiles_xy;
+    const int ty0 = rem / tiles_x, tx0 = rem - ty0 * tiles_x;
+    const int ox0 = tx0 * kLpW, oy0 = ty0 * kLpH;
+    // 1. the tile's source pixels, normalised once (taps outside the canvas are the convolution's zero padding)
+#pragma unroll
+    for (int i = 0; i < kSweeps; ++i) {
+      const int t = tid + i * (kLpW * kLpH);
+      uint2 v = make_uint2(0u, 0u);
+      if (px[i] >> 24) {
+        v.x = lut[(px[i] >> 16) & 0xFF] | ((uint32_t)lut[(px[i] >> 8) & 0xFF] << 16);      // R, G
+        v.y = lut[px[i] & 0xFF];                                                            // B, 0
+      }
+      if (t < IW * IH) *reinterpret_cast<uint2*>(tile + t * 4) = v;
+    }
+    __syncthreads();
+    // 2. A operand: thread (ly, lx) = row (tid & 127) of M tile (tid >> 7); k = tap * 3 + rgb, 27 used
+    {
+      uint16_t v[32];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const uint2 q = *reinterpret_cast<const uint2*>(tile + ((ly * 2 + tap / 3) * IW + lx * 2 + tap % 3) * 4);
+        v[tap * 3 + 0] = (uint16_t)(q.x & 0xFFFFu);           // R
+        v[tap * 3 + 1] = (uint16_t)(q.x >> 16);               // G
+        v[tap * 3 + 2] = (uint16_t)(q.y & 0xFFFFu);           // B
+      }
+#pragma unroll
+      for (int k = 27; k < 32; ++k) v[k] = 0;
+      uint8_t* row_base = a_tile + (tid >> 7) * (128 * 64);
+      const uint32_t row_off = (uint32_t)(tid & 127) * 64u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t o = row_off + (uint32_t)j * 16;
+        *reinterpret_cast<uint4*>(row_base + (o ^ (((o >> 7) & 3u) << 4))) =
+            make_uint4(v[8 * j] | ((uint32_t)v[8 * j + 1] << 16), v[8 * j + 2] | ((uint32_t)v[8 * j + 3] << 16),
+                       v[8 * j + 4] | ((uint32_t)v[8 * j + 5] << 16), v[8 * j + 6] | ((uint32_t)v[8 * j + 7] << 16));
       }
     }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
+    fence_proxy_async();                                        // generic-proxy writes -> visible to the tensor core
+    tc_fence_before();
+    __syncthreads();
     tc_fence_after();
-    tmem_dealloc(tmem_base, kCols);
+    // 3. four MMAs (two M tiles x K = 32 in two steps)
+    if (warp == 0) {
+      if (elect_one()) {
+        const uint32_t idesc = umma_idesc(128, COUT, BF16 ? 1u : 0u);
+        const uint64_t bd = umma_smem_desc(smem_u32(b_tile), 64);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const uint64_t ad = umma_smem_desc(smem_u32(a_tile) + (uint32_t)mt * 128u * 64u, 64);
+          umma_f16(tmem_base + (uint32_t)mt * COUT, ad, bd, idesc, 0u);
+          umma_f16(tmem_base + (uint32_t)mt * COUT, ad + 2, bd + 2, idesc, 1u);
+        }
+        umma_commit(&done_bar);
+      }
+      __syncwarp();
+    }
+    // the next tile's source pixels travel while the tensor core works and the epilogue stores
+    if (t_idx + (int)gridDim.x < n_tiles) fetch(t_idx + gridDim.x, px);
+    mbar_wait(&done_bar, phase);
+    phase ^= 1u;
+    tc_fence_after();
+    // 4. epilogue: warp w reads lanes 32 (w & 3) .. +31 of accumulator w >> 2, i.e. output row ly == w, pixel lx == lane
+    {
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * COUT;
+      uint32_t r[COUT];
+      if (COUT == 32) {
+        uint32_t (&r32)[32] = reinterpret_cast<uint32_t (&)[32]>(r);
+        tmem_ld32(taddr, r32);
+      } else {
+        uint32_t (&r16)[16] = reinterpret_cast<uint32_t (&)[16]>(r);
+        tmem_ld16(taddr, r16);
+      }
+      tmem_ld_wait();
+      const int oy = oy0 + ly, ox = ox0 + lx;
+      if (oy < ho && ox < wo) {
+        uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)b * ho + oy) * wo + ox) * COUT);
+#pragma unroll
+        for (int j = 0; j < COUT / 8; ++j) {
+          uint32_t w4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float v0 = __uint_as_float(r[8 * j + 2 * i]) + s_bias[8 * j + 2 * i];
+            float v1 = __uint_as_float(r[8 * j + 2 * i + 1]) + s_bias[8 * j + 2 * i + 1];
+            if (act == 1) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f);
+            if (BF16) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+              w4[i] = *reinterpret_cast<uint32_t*>(&h2);
+            } else {
+              __half2 h2 = __floats2half2_rn(v0, v1);
+              w4[i] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+          }
+          dst[j] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        }
+      }
+    }
+    // the accumulators are read (next tile's MMAs overwrite them), and every thread is past its reads of `tile`
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
   }
+  if (warp == 0) tmem_dealloc(tmem_base, kCols);
 }
 
 static int make_geom(ResizeGeom* g, int h, int w, int new_w, int new_h, int in_w, int in_h) {
@@ -1028,17 +1050,27 @@ extern "C" int b2f_preprocess_conv1(const uint8_t* frames, int batch, int h, int
   if (rc) return rc;
   const int ho = (in_h + 2 - 3) / 2 + 1, wo = (in_w + 2 - 3) / 2 + 1;
   if (batch <= 0) return 0;
-  B2F_REQUIRE(batch <= 65535, "b2f_preprocess_conv1: batch too large");
-  const dim3 grid((wo + kLpW - 1) / kLpW, (ho + kLpH - 1) / kLpH, batch);
+  // persistent CTAs, four per SM (29 KB of shared memory, 64 TMEM columns and <= 64 registers per thread each)
+  const int tiles_x = (wo + kLpW - 1) / kLpW, tiles_y = (ho + kLpH - 1) / kLpH;
+  const long long n_tiles_ll = (long long)tiles_x * tiles_y * batch;
+  B2F_REQUIRE(n_tiles_ll < (1LL << 31), "b2f_preprocess_conv1: too many tiles");
+  const int n_tiles = (int)n_tiles_ll;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    B2F_CHECK_CUDA(cudaGetDevice(&dev));
+    B2F_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = n_tiles < sms * 4 ? n_tiles : sms * 4;
   const uint16_t* wt = reinterpret_cast<const uint16_t*>(weight);
   uint16_t* o = reinterpret_cast<uint16_t*>(out);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B2F_BF16) {
-    if (cout_p == 32) letterbox_conv1_kernel<true, 32><<<grid, kLpW * kLpH, 0, st>>>(frames, g, ho, wo, mean, scale, wt, bias, act, o);
-    else letterbox_conv1_kernel<true, 16><<<grid, kLpW * kLpH, 0, st>>>(frames, g, ho, wo, mean, scale, wt, bias, act, o);
+    if (cout_p == 32) letterbox_conv1_kernel<true, 32><<<grid, kLpW * kLpH, 0, st>>>(frames, g, ho, wo, mean, scale, wt, bias, act, o, tiles_x, tiles_y, n_tiles);
+    else letterbox_conv1_kernel<true, 16><<<grid, kLpW * kLpH, 0, st>>>(frames, g, ho, wo, mean, scale, wt, bias, act, o, tiles_x, tiles_y, n_tiles);
   } else {
-    if (cout_p == 32) letterbox_conv1_kernel<false, 32><<<grid, kLpW * kLpH, 0, st>>>(frames, g, ho, wo, mean, scale, wt, bias, act, o);
-    else letterbox_conv1_kernel<false, 16><<<grid, kLpW * kLpH, 0, st>>>(frames, g, ho, wo, mean, scale, wt, bias, act, o);
+    if (cout_p == 32) letterbox_conv1_kernel<false, 32><<<grid, kLpW * kLpH, 0, st>>>(frames, g, ho, wo, mean, scale, wt, bias, act, o, tiles_x, tiles_y, n_tiles);
+    else letterbox_conv1_kernel<false, 16><<<grid, kLpW * kLpH, 0, st>>>(frames, g, ho, wo, mean, scale, wt, bias, act, o, tiles_x, tiles_y, n_tiles);
   }
   g_launches.fetch_add(1);
   B2F_LAUNCH_CHECK();
