@@ -543,6 +543,34 @@ def compile_graph(g: Graph, in_hw: Tuple[int, int], stem_im2col: bool = True, me
             conv.dst, conv.order = pool.dst, max(conv.order, pool.order)
             ops.remove(pool)
 
+    # ---- a 2x2 / stride 2 AveragePool in front of a 1x1 convolution IS a 2x2 / stride 2 convolution ----------------
+    # (the ResNet-D style down-sampling shortcut of the SCRFD backbones: AvgPool -> Conv1x1 -> BN, + main branch, ReLU).
+    # conv1x1(avgpool(x)) = sum over the four taps of x_tap * (W / 4): the pooling pass, its launch and the pooled tensor
+    # disappear, and the pooled value is no longer rounded to 16 bits before the convolution.  Only for even maps (no
+    # partial windows, so ceil_mode / count_include_pad do not matter).  W / 4 is exact in fp16 / bf16 (a power of two).
+    # `macs_per_image` stays the algorithmic count of the 1x1 layer.  B2F_FOLD_AVGPOOL=0 keeps the two ops.
+    if os.environ.get("B2F_FOLD_AVGPOOL", "1") != "0":
+        readers = {}
+        for op in ops:
+            for t in (op.src, op.residual, op.sc_src):
+                if t:
+                    readers[t] = readers.get(t, 0) + 1
+        by_dst = {op.dst: op for op in ops}
+        for conv in [o for o in ops if o.kind == "conv"]:
+            pool = by_dst.get(conv.src)
+            ca = conv.attrs
+            if (pool is None or pool.kind != "pool" or pool.attrs["mode"] != 1 or pool.attrs["k"] != 2
+                    or pool.attrs["stride"] != 2 or pool.attrs["pad"] != 0 or pool.attrs["h"] % 2 or pool.attrs["w"] % 2
+                    or readers.get(pool.dst, 0) != 1 or pool.dst in out_names or conv.sc_src
+                    or (ca["kh"], ca["kw"], ca["stride"], ca["pad"]) != (1, 1, 1, 0) or ca["bias_classes"] != 1
+                    or conv.residual == pool.dst):
+                continue
+            w1 = conv.arrays["weight"]                                   # [1][cout_p][cin_p]
+            conv.arrays["weight"] = np.ascontiguousarray(np.repeat(w1 * np.asarray(0.25, w1.dtype), 4, axis=0))
+            conv.attrs.update(kh=2, kw=2, stride=2, pad=0, h=pool.attrs["h"], w=pool.attrs["w"])
+            conv.src = pool.src
+            ops.remove(pool)
+
     # ---- topological order over fused ops ------------------------------------------------------------
     inp = g.real_inputs()[0].name
     produced_by = {op.dst: op for op in ops}

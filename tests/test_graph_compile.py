@@ -37,8 +37,18 @@ def test_scrfd_500m_plan_matches_oracle():
 def test_scrfd_2p5g_plan_matches_oracle():
     plan = _check("scrfd_2.5g", (160, 192))
     assert sum(o.res_mode == 2 for o in plan.ops) == 2            # both top-down upsample-adds are fused
-    assert sum(o.kind == "pool" for o in plan.ops) == 3            # the three avg_down shortcuts
+    # the three avg_down shortcuts (AveragePool 2x2 / s2 -> Conv1x1) are 2x2 / stride 2 convolutions, no pooling pass
+    assert sum(o.kind == "pool" for o in plan.ops) == 0
+    assert sum(o.kind == "conv" and (o.attrs["kh"], o.attrs["stride"]) == (2, 2) for o in plan.ops) == 3
     assert sum(o.attrs.get("pool", 0) for o in plan.ops) == 1      # the stem max-pool rides in its convolution's epilogue
+
+
+def test_avgpool_fold_is_optional(monkeypatch):
+    """B2F_FOLD_AVGPOOL=0 keeps AveragePool + Conv1x1 as two ops; both plans reproduce the oracle.  (Detector inputs are
+    multiples of 32, so the pooled maps are always even and the fold's odd-size guard never triggers there.)"""
+    monkeypatch.setenv("B2F_FOLD_AVGPOOL", "0")
+    plan = _check("scrfd_2.5g", (160, 192))
+    assert sum(o.kind == "pool" for o in plan.ops) == 3
 
 
 def test_arcface_mbf_plan_matches_oracle():
