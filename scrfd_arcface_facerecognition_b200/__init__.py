@@ -8,6 +8,8 @@ Public surface (mirrors Kumar2421/scrfd_arcface_facerecognition):
                                                                        qdrant_manager.py, duplicate.py:2726-2797
     QdrantManager (same method surface, GPU resident)                  reference qdrant_manager.py:17-300
     FaceAnalysis(name).prepare(...).get(img) -> [Face]                 reference duplicate.py:353-359, 1473-1496
+    VideoRunner / FrameFeeder / FrameOverlay (batched video loop,      reference main.py:108-188,
+        overlay painted on device-resident frames)                     utils/helpers.py:126-179
 Importing the package does not touch CUDA; the heavy modules load lazily.
 """
 __version__ = "0.1.0"
@@ -15,7 +17,7 @@ __version__ = "0.1.0"
 _LAZY = {"SCRFD": ".scrfd", "ArcFace": ".arcface", "Gallery": ".gallery", "FacePipeline": ".pipeline",
          "helpers": ".helpers", "FaceAnalysis": ".face_analysis", "Face": ".face_analysis",
          "QdrantManager": ".vector_store", "GalleryManager": ".vector_store",
-         "VideoRunner": ".video", "FrameFeeder": ".video",
+         "VideoRunner": ".video", "FrameFeeder": ".video", "FrameOverlay": ".overlay",
          "PersonDatabase": ".result_store", "save_clustering_results": ".result_store"}
 
 
