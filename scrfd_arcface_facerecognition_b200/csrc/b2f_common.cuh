@@ -85,12 +85,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a pipeline bug traps (launch failure) instead of hanging the GPU box.
+#ifdef B2F_POLL_WAIT     // experiment: pure polling everywhere (mbarrier.test_wait never suspends the thread)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity);
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if (++spins > (1u << 28)) __trap();
+  }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 23)) __trap();
   }
 }
+#endif
 
 // pure polling (mbarrier.test_wait never suspends the thread): lower wake-up latency than try_wait's time-sliced sleep
 __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {

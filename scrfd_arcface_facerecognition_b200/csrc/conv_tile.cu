@@ -355,7 +355,7 @@ __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& 
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) r[i] = r16[i];
-      } else {
+      } else if (!(p.debug & 256)) {
         tmem_ld32(t_addr + (uint32_t)(j * och), r);
         tmem_ld_wait();
       }
@@ -377,14 +377,14 @@ __device__ __forceinline__ void epilogue_tma(const TileParams& p, const EpiCtx& 
           epi_slice16<ACT, BF16, MR>(r + 16, bias_row + cl + 16, slope_row + cl + 16, reinterpret_cast<uint4*>(bufp + off[2]),
                                       reinterpret_cast<uint4*>(bufp + off[3]), t.cbase + cl + 16, sig_hi, g0 ? g0 + 2 : nullptr);
       }
-      fence_proxy_async();
+      if (!(p.debug & 128)) fence_proxy_async();
       if (c.leader) {
         // the store issued one slice ago has had this slice's arithmetic to leave its buffer; once it has, the
         // residual of the slice two steps ahead may land there
         bulk_wait_read0();
         if (RES == 1 && rs_s < total_sub) issue_res();
       }
-      bar_sync_named(1 + group, 128);
+      if (!(p.debug & 512)) bar_sync_named(1 + group, 128);
       if (c.leader && !skip_store) {
         if (RES == 3) tma_reduce_add_4d(c.tmO, bufp, t.cbase + j * och, t.x0, t.y0, t.n0);
         else tma_store_4d(c.tmO, bufp, t.cbase + j * och, t.x0, t.y0, t.n0);
