@@ -13,7 +13,7 @@ from typing import List
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-SO_PATH = os.path.join(CSRC, "libb2f.so")
+SO_PATH = os.environ.get("B2F_SO") or os.path.join(CSRC, "libb2f.so")     # B2F_SO: an experimental build to A/B against
 SOURCES = ["core.cu", "postproc.cu", "aux_ops.cu", "umma_conv.cu", "conv_tile.cu", "match_pair.cu", "overlay.cu"]
 HEADERS = ["b2f_common.cuh", "umma_shared.cuh", os.path.join("..", "..", "include", "b2f.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
