@@ -85,7 +85,8 @@ struct TileParams {
   int groups;
   int pool, pool_h, pool_w, off_pool;   // fused 3x3 / s2 / p1 max-pool: pooled map size, per-group pooled staging
   int res_reduce;   // residual == out and no activation: the epilogue reduce-adds into the output instead of loading it
-  int is_bf16, debug;
+  int is_bf16, debug;       // debug (b2f_set_tuning key 4) = the bits of umma_conv.cu plus, in the TMA-store epilogue: 64 polling wait
+                            // on the accumulator, 128 no proxy fence, 256 no TMEM read, 512 no group barrier (timing experiments only)
   int epi_tma, res_smem, res_global, ochunk, n_sub, stg_bytes, stg_box_bytes, stg_bufs;
   void* out;
   int out_dtype;
