@@ -62,3 +62,26 @@ def test_compute_without_cuda_fails_loudly():
     from models import SCRFD
     with pytest.raises(_lib.B2FError):
         SCRFD("weights/det_500m.onnx")
+
+
+def test_fastdiv_formula_is_exact():
+    """The multiply-shift division the conv kernels use for tile coordinates (csrc/conv_tile.cu, `FastDiv`):
+    q = (x * ceil(2^(31+s) / d)) >> (31+s) with s = ceil(log2 d) must equal x // d for every 0 <= x < 2^31, and the
+    multiplier must fit 32 bits."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    divisors = list(range(1, 70)) + [98, 100, 127, 128, 129, 392, 784, 1000, 3136, 4097, 65535, 65536, 1 << 20, (1 << 20) + 1]
+    for d in divisors:
+        s = 0
+        while (1 << s) < d:
+            s += 1
+        shift = 31 + s
+        mul = ((1 << shift) + d - 1) // d
+        assert mul < (1 << 32), d
+        xs = np.concatenate([rng.integers(0, 1 << 31, 4000, dtype=np.int64),
+                             np.arange(0, 4 * d + 2, dtype=np.int64),
+                             (np.arange(1, 2000, dtype=np.int64) * d - 1) % (1 << 31),
+                             np.array([(1 << 31) - 1, (1 << 31) - d, ((1 << 31) - 1) // d * d], dtype=np.int64)])
+        xs = xs[(xs >= 0) & (xs < (1 << 31))]
+        q = np.array([(int(x) * mul) >> shift for x in xs], dtype=np.int64)
+        assert (q == xs // d).all(), d
